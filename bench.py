@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark of the plane-sweep hot path (BASELINE.json metric: cost-volume Mvox/s + depth maps/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload = BASELINE.json configs[1]: MVSNet (variance), 1 reference + 4 source views, 640x512 images ->
+32-channel 160x128 feature maps, D = 192 hypotheses (3.93 Mvox per depth map).  One "step" = one pass of the
+hot path (fused warp+variance cost volume -> 3-D U-Net regulariser -> softmax/depth/confidence) for ONE
+reference view per GPU; with N GPUs every rank processes its own reference view (weak scaling, independent
+units) and the per-view depth maps are all-gathered once per step.
+
+`value` is measured with the feature maps already resident in HBM; `e2e` is the same metric through
+MVSNet.depth_from_features with the features in pinned host memory (H2D + hot path + D2H of depth and
+confidence inside the timed region).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = {"name": "cfg2", "views": 5, "C": 32, "h": 128, "w": 160, "D": 192}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def voxels():
+    return CFG["D"] * CFG["h"] * CFG["w"]
+
+
+def algorithmic_bytes():
+    """Layer-wise compulsory fp32 traffic of one cfg2 pass: every seam tensor written once by its
+    producer and read once per consumer, BN/ReLU/skip fused.  Returns (total, per-kernel dict)."""
+    V, C, h, w, D = CFG["views"], CFG["C"], CFG["h"], CFG["w"], CFG["D"]
+    vox = D * h * w
+    per = {"k1_cost_volume": 4 * (V * C * h * w + C * vox)}
+    # (name, cin, cout, in_vox_div, out_vox_div, skip)
+    layers = [("conv0", 32, 8, 1, 1, 0), ("conv1", 8, 16, 1, 8, 0), ("conv2", 16, 16, 8, 8, 0), ("conv3", 16, 32, 8, 64, 0),
+              ("conv4", 32, 32, 64, 64, 0), ("conv5", 32, 64, 64, 512, 0), ("conv6", 64, 64, 512, 512, 0),
+              ("conv7", 64, 32, 512, 64, 1), ("conv9", 32, 16, 64, 8, 1), ("conv11", 16, 8, 8, 1, 1), ("prob", 8, 1, 1, 1, 0)]
+    for name, cin, cout, di, do, skip in layers:
+        per[name] = 4 * (cin * vox // di + cout * vox // do * (1 + skip))
+    per["k3_regress"] = 4 * (vox + 2 * h * w)
+    return sum(per.values()), per
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (pynvml), runs during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.nv:
+            self.t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload construction (shared by both arms)
+# ------------------------------------------------------------------------------------------------
+def make_workload(seed):
+    from wild_deep_mvs_b200 import synth
+    from wild_deep_mvs_b200.mvsnet import MVSNet, build_proj_matrices
+    torch.manual_seed(0)
+    net = MVSNet("variance")
+    synth.randomize_norm_stats(net, seed=1)
+    synth.scale_param(net.cost_regularization.prob.weight, 40.0)
+    net.num_depth = CFG["D"]
+    net.eval()
+    feats = synth.make_features(1, CFG["views"], CFG["C"], CFG["h"], CFG["w"], seed=seed)
+    K, R, t, dmin, dmax = synth.make_cameras(1, CFG["views"], 4 * CFG["h"], 4 * CFG["w"])
+    K = K.clone()
+    K[:, :, :2] /= 4
+    projs = build_proj_matrices(K, R, t)
+    D = CFG["D"]
+    depth = dmin[:, :1] + (dmax[:, :1] - dmin[:, :1]) / (D - 1) * torch.arange(D).view(1, -1)
+    return net, feats, projs, depth
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: oracle/torch_port.py on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_port_pass(net, feats, projs, depth, d_sample):
+    from oracle import torch_port as tp
+    sd = net.state_dict()
+    pl = list(torch.unbind(projs, 1))
+    tm = {}
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        tp.mvsnet_hot_path(sd, feats, pl, depth[:, :d_sample].contiguous(), "variance", None, tm)
+        dt = time.perf_counter() - t0
+    return dt, tm
+
+
+def run_cpu_baseline(budget_s, steps, warmup):
+    """Times the ATen port of the reference path on all host cores.  The sample is the full cfg2 pass unless
+    (steps+warmup) passes would exceed `budget_s`; then the depth axis is cut to a multiple of 8 that fits."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    net, feats, projs, depth = make_workload(seed=0)
+    D = CFG["D"]
+    d_sample = D
+    dt, _ = cpu_port_pass(net, feats, projs, depth, 48)  # probe on a quarter slab (also warms the allocator)
+    est_full = dt * D / 48
+    if est_full * (steps + warmup) > budget_s:
+        d_sample = max(8, int(D * budget_s / (est_full * (steps + warmup))) // 8 * 8)
+    for _ in range(warmup):
+        cpu_port_pass(net, feats, projs, depth, d_sample)
+    times, parts = [], []
+    for _ in range(steps):
+        dt, tm = cpu_port_pass(net, feats, projs, depth, d_sample)
+        times.append(dt)
+        parts.append(tm)
+    vox = d_sample * CFG["h"] * CFG["w"]
+    mean = sum(times) / len(times)
+    best = min(range(len(times)), key=lambda i: times[i])
+    return {"value": vox / mean / 1e6, "unit": "Mvox/s", "cores": cores, "kind": "port",
+            "sample": "oracle/torch_port.py (ATen restatement of the reference path), %d timed pass(es) of cfg2 with D=%d of %d "
+                      "hypotheses (%.3f Mvox each), %d threads" % (steps, d_sample, D, vox / 1e6, torch.get_num_threads()),
+            "ms_per_step": mean * 1e3, "split_ms": {k: v * 1e3 for k, v in parts[best].items()}}, mean, vox
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, mean, vox = run_cpu_baseline(budget_s=150.0, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": "cost-volume Mvox/s (build+regularise+regress)", "value": cb["value"], "unit": "Mvox/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus), "maps_per_s": 1.0 / (mean * CFG["D"] * CFG["h"] * CFG["w"] / vox),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "Mvox/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(n):
+    return {"workload": "BASELINE cfg2: MVSNet variance, 1 ref + 4 src views, 640x512 images -> 32ch 160x128 features, D=192, "
+                        "features->depth+confidence (K1 warp+variance, K2 3-D U-Net, K3 softmax/regress)",
+            "views": CFG["views"], "feature_hw": [CFG["h"], CFG["w"]], "D": CFG["D"], "voxels_per_map": voxels(),
+            "maps_per_step": n, "parallelism": "view-sharded replicas x%d + 1 all-gather of depth maps" % n,
+            "l2": "flushed between timed steps (512 MiB memset, untimed); intermediate volumes (503 MB) exceed L2"}
+
+
+# ------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------
+def own_arm(args):
+    import torch.distributed as dist
+    from wild_deep_mvs_b200 import ops, shard
+    from wild_deep_mvs_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback exists for the hot path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.load()
+
+    net, feats, projs, depth = make_workload(seed=rank)  # each rank: its own reference view sample
+    net = net.to(dev)
+    host_feats = [ops_pin(f) for f in feats]
+    dfeats = [ops.to_nhwc(f.to(dev)) for f in feats]
+    dprojs = list(torch.unbind(projs.to(dev), 1))
+    ddepth = depth.to(dev)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    h, w = CFG["h"], CFG["w"]
+    gathered = None
+
+    def step():
+        d, c = net.depth_from_features(dfeats, dprojs, ddepth)
+        if world > 1:
+            return shard.gather_depth_maps(d)
+        return d
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            gathered = step()
+            b.record()
+        barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = t.item()
+    ms_per_step = total_ms / args.steps
+    value = world * voxels() / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: pinned host features -> H2D -> hot path -> D2H depth + confidence -------------------
+    e2e = None
+    if not args.no_e2e:
+        out_d = torch.empty(1, h, w, dtype=torch.float32).pin_memory()
+        out_c = torch.empty(1, h, w, dtype=torch.float32).pin_memory()
+        h2d = sum(f.numel() * 4 for f in host_feats) + projs.numel() * 4 + depth.numel() * 4
+        hp, hd = projs.pin_memory(), depth.pin_memory()
+
+        def e2e_step():
+            fd = [ops.to_nhwc(f.to(dev, non_blocking=True)) for f in host_feats]
+            pj = list(torch.unbind(hp.to(dev, non_blocking=True), 1))
+            dd = hd.to(dev, non_blocking=True)
+            d, c = net.depth_from_features(fd, pj, dd)
+            out_d.copy_(d, non_blocking=True)
+            out_c.copy_(c, non_blocking=True)
+
+        for _ in range(max(3, args.warmup)):
+            e2e_step()
+        barrier()
+        ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in ee:
+            flush.zero_()
+            a.record()
+            e2e_step()
+            b.record()
+        barrier()
+        te = torch.tensor([sum(a.elapsed_time(b) for a, b in ee)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms = te.item() / args.steps
+        e2e = {"value": world * voxels() / (e2e_ms * 1e-3) / 1e6, "unit": "Mvox/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 2 * h * w * 4, "ms_per_step": e2e_ms,
+               "api": "MVSNet.depth_from_features on pinned host feature maps (NCHW->NHWC repack on device, untimed nothing)"}
+
+    # ---- per-kernel timing (CUDA events on the launching stream) for the roofline ------------------
+    roof, kernels = kernel_roofline(net, dfeats, dprojs, ddepth, flush) if rank == 0 else (None, None)
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        total_bytes, _ = algorithmic_bytes()
+        line = {"metric": "cost-volume Mvox/s (build+regularise+regress)", "value": value, "unit": "Mvox/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(world), "maps_per_s": world / (ms_per_step * 1e-3),
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": 14 * args.steps,
+                "roofline": roof, "kernels": kernels,
+                "path_hbm": {"algorithmic_bytes_per_map": total_bytes, "achieved_GBps": total_bytes / (ms_per_step * 1e-3) / 1e9,
+                             "frac_of_measured_hbm": total_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak()[0]}}
+        if not args.no_cpu_baseline and world == 1:
+            cb, _, _ = run_cpu_baseline(budget_s=25.0, steps=1, warmup=1)
+            line["cpu_baseline"] = cb
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ops_pin(t):
+    return t.contiguous().pin_memory()
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def kernel_roofline(net, dfeats, dprojs, ddepth, flush, iters=5):
+    """Time every kernel launch of one step with CUDA events (L2 flushed before each launch) and report the
+    dominant one against the measured HBM peak."""
+    from wild_deep_mvs_b200 import ops
+    from wild_deep_mvs_b200 import _lib as L
+    reg = net.cost_regularization
+    pk = reg._pack()
+    _, per_bytes = algorithmic_bytes()
+    times = {}
+
+    def timed(name, fn):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        b.synchronize()
+        times.setdefault(name, []).append(a.elapsed_time(b))
+        return out
+
+    for _ in range(iters):
+        warp = ops.mvs_relative_proj(dprojs[0], torch.stack(dprojs[1:], 1))
+        vol = timed("k1_cost_volume", lambda: ops.build_cost_volume(dfeats[0], dfeats[1:], warp, ddepth, CFG["D"], L.GEOM_MVS, L.AGG_VARIANCE))
+        c0 = timed("conv0", lambda: ops.conv3d(vol, pk["conv0"]))
+        del vol
+        c1 = timed("conv1", lambda: ops.conv3d(c0, pk["conv1"]))
+        c2 = timed("conv2", lambda: ops.conv3d(c1, pk["conv2"]))
+        c3 = timed("conv3", lambda: ops.conv3d(c2, pk["conv3"]))
+        c4 = timed("conv4", lambda: ops.conv3d(c3, pk["conv4"]))
+        c5 = timed("conv5", lambda: ops.conv3d(c4, pk["conv5"]))
+        c6 = timed("conv6", lambda: ops.conv3d(c5, pk["conv6"]))
+        x = timed("conv7", lambda: ops.conv3d(c6, pk["conv7"], skip=c4))
+        x = timed("conv9", lambda: ops.conv3d(x, pk["conv9"], skip=c2))
+        x = timed("conv11", lambda: ops.conv3d(x, pk["conv11"], skip=c0))
+        s = timed("prob", lambda: ops.conv3d(x, pk["prob"]).squeeze(-1))
+        timed("k3_regress", lambda: ops.depth_regress(s, ddepth, conf_mode=L.CONF_SUM4))
+    peak, how = hbm_peak()
+    kernels = []
+    for name, ts in times.items():
+        ms = sum(ts[1:]) / len(ts[1:])
+        kernels.append({"name": name, "ms": ms, "algorithmic_bytes": per_bytes[name], "GBps": per_bytes[name] / (ms * 1e-3) / 1e9})
+    top = max(kernels, key=lambda k: k["ms"])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(top["name"])
+    roof = {"kernel": top["name"], "bound": "hbm", "achieved": top["GBps"], "peak": peak, "unit": "GB/s",
+            "frac": top["GBps"] / peak, "traffic": traffic, "peak_source": how,
+            "share_of_step": top["ms"] / sum(k["ms"] for k in kernels)}
+    return roof, kernels
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        own_arm(a)

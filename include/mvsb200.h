@@ -1,0 +1,161 @@
+/*
+ * mvsb200.h -- C ABI of libmvsb200.so, the B200 (sm_100a) plane-sweep cost-volume engine.
+ *
+ * This is the drop-in boundary for the hot path of fdarmon/wild_deep_mvs.  The reference has
+ * no FFI layer (it is pure PyTorch); each entry point below replaces a Python function or
+ * nn.Module.forward of the reference, cited as file:line.  A reference maintainer binds these
+ * with ctypes; wild_deep_mvs_b200/_lib.py is exactly that binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter is documented as "host";
+ *   - all tensors are dense fp32;
+ *   - feature maps are channels-last  [B, H, W, C]      (== torch NCHW tensor in channels_last);
+ *   - volumes are channels-last       [B, D, H, W, C]   (== torch NCDHW tensor in channels_last_3d);
+ *   - single-channel volumes/maps are therefore plain [B, D, H, W] / [B, H, W];
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing syncs;
+ *   - no entry point allocates device memory; the caller owns every buffer;
+ *   - return value 0 = success, negative = MVSB200_E_* (message via mvsb200_last_error()).
+ */
+#ifndef MVSB200_H_
+#define MVSB200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVSB200_ABI_VERSION 1
+
+#define MVSB200_OK 0
+#define MVSB200_E_INVALID (-1)  /* bad argument / unsupported shape */
+#define MVSB200_E_CUDA (-2)     /* a CUDA runtime call or launch failed */
+#define MVSB200_E_NODEVICE (-3) /* no sm_100-class device */
+
+#define MVSB200_MAX_SRC 16 /* maximum number of source views per call */
+
+typedef void *mvsb200_stream_t;
+
+#if defined(__GNUC__)
+#define MVSB200_API __attribute__((visibility("default")))
+#else
+#define MVSB200_API
+#endif
+
+MVSB200_API int mvsb200_abi_version(void);
+/* Thread-local message describing the last failure on the calling thread ("" if none). */
+MVSB200_API const char *mvsb200_last_error(void);
+/* Fills SM count and compute capability of the current device. */
+MVSB200_API int mvsb200_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---------------------------------------------------------------------------------------
+ * Geometry prologues (one thread per (batch, source view); fp64 inside, fp32 out).
+ * --------------------------------------------------------------------------------------- */
+
+/* warp[b][s] = { rot[9] row-major, trans[3], 0,0,0,0 } with  [rot|trans] = (src_proj @ inv(ref_proj))[:3,:4]
+ * Replaces `proj = torch.matmul(src_proj, torch.inverse(ref_proj))`
+ *   models/MVSNet/module.py:128, models/CVP_MVSNet/models/modules.py:89-97,247-252.
+ * ref_proj [B,4,4], src_proj [B,S,4,4], warp [B,S,16]. */
+MVSB200_API int mvsb200_mvs_relative_proj(const float *ref_proj, const float *src_proj, float *warp, int B, int S,
+                              mvsb200_stream_t stream);
+
+/* Closed form of get_homographies (models/VisMVSNet/homography.py:23-74) after
+ * scale_camera(cam, scale) (models/VisMVSNet/preproc.py:63-92):
+ *   H_d p = A p - b (n.p) / (depth_d + 1e-9),  A = K_s R_s R_r^T K_r^-1,  b = K_s R_s (c_s - c_r),
+ *   n = R_r[2,:] R_r^T K_r^-1.      warp[b][s] = { A[9], b[3], n[3], 0 }.
+ * ref_cam [B,2,4,4], src_cam [B,S,2,4,4] ([.,0]=R|t, [.,1]=K as built by fill_cam_array,
+ * models/VisMVSNet/frontend.py:14-24). */
+MVSB200_API int mvsb200_vis_homography_params(const float *ref_cam, const float *src_cam, float scale, float *warp, int B,
+                                  int S, mvsb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K1: fused homography warp + cross-view aggregation.  The warped volumes, sampling grids
+ * and per-voxel homographies of the reference are never stored.
+ * --------------------------------------------------------------------------------------- */
+#define MVSB200_GEOM_MVS 0 /* homo_warping: models/MVSNet/module.py:111-169, CVP modules.py:74-128,229-286 */
+#define MVSB200_GEOM_VIS 1 /* homography_warping + interpolate: models/VisMVSNet/homography.py:77-121 */
+
+#define MVSB200_AGG_VARIANCE 0      /* M2/V - M1^2/V^2    models/MVSNet/model.py:113-139              */
+#define MVSB200_AGG_VARIANCE_MEAN 1 /* M2/V - (M1/V)^2    CVP net.py:152, modules.py:289               */
+#define MVSB200_AGG_SOFTMIN 2       /* MVSNet-s           models/MVSNet/model.py:141-173               */
+#define MVSB200_AGG_GROUPCORR 3     /* 8-group correlation per source view, VisMVSNet/nn_utils.py:473-490,
+                                       model_cas.py:176-186,340 */
+
+#define MVSB200_DEPTH_VALUES 0       /* depth [B,D]            (module.py:140-141)                      */
+#define MVSB200_DEPTH_VOLUME 1       /* depth [B,D,H,W]        (CVP modules.py:262-263)                 */
+#define MVSB200_DEPTH_START 2        /* depth [B] start, interval [B]:  start + interval*d              */
+#define MVSB200_DEPTH_START_MAP 3    /* depth [B,H,W] start, interval [B]  (homography.py:24-40)        */
+
+typedef struct {
+    int geom, agg, depth_mode;
+    int B, S, C;  /* batch, number of SOURCE views (<= MVSB200_MAX_SRC), feature channels (8,16 or 32) */
+    int D, H, W;  /* hypotheses and reference feature size */
+    int groups;   /* GROUPCORR only (C/groups must be 4) */
+    int src_h[MVSB200_MAX_SRC], src_w[MVSB200_MAX_SRC]; /* source maps may differ in size (module.py:119-125) */
+    long long out_view_stride; /* GROUPCORR: element stride between the per-source output volumes */
+} mvsb200_cost_volume_desc;
+
+/* ref [B,H,W,C]; src: HOST array of S device pointers, src[s] is [B,src_h[s],src_w[s],C];
+ * warp [B,S,16] from one of the geometry prologues; depth/interval per depth_mode; temp: device scalar
+ * (SOFTMIN only, models/MVSNet/model.py:94-95).
+ * out: [B,D,H,W,C] (VARIANCE*, SOFTMIN) or S volumes [B,D,H,W,groups] (GROUPCORR). */
+MVSB200_API int mvsb200_build_cost_volume(const mvsb200_cost_volume_desc *desc, const float *ref, const float *const *src,
+                              const float *warp, const float *depth, const float *interval, const float *temp,
+                              float *out, mvsb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K2: 3-D convolution / transposed convolution with fused BN (scale,bias) + ReLU + skip.
+ * Replaces ConvBnReLU3D (models/MVSNet/module.py:41-48), the nn.ConvTranspose3d+BN+ReLU blocks
+ * and skip adds of CostRegNet (models/MVSNet/model.py:43-84), BasicBlock / UNet of Vis-MVSNet
+ * (models/VisMVSNet/nn_utils.py:123-278) and CVP's CostRegNet (CVP_MVSNet/models/net.py:50-85).
+ * --------------------------------------------------------------------------------------- */
+#define MVSB200_SKIP_NONE 0
+#define MVSB200_SKIP_BEFORE_RELU 1 /* relu(bn(conv) + skip)   BasicBlock, nn_utils.py:166-169        */
+#define MVSB200_SKIP_AFTER_RELU 2  /* skip + relu(bn(deconv)) CostRegNet, MVSNet/model.py:79-81      */
+
+typedef struct {
+    int B, D, H, W;     /* INPUT spatial size */
+    int Cin, Cin2;      /* channels of x and of the optional second input x2 (torch.cat([x, x2], 1)) */
+    int Cout;
+    int kd, kh, kw;     /* each 1 or 3; padding is k/2 */
+    int stride;         /* 1 or 2 */
+    int transposed;     /* 1: ConvTranspose3d(k=3, stride=2, padding=1, output_padding=1) */
+    int relu;
+    int skip_mode;
+} mvsb200_conv3d_desc;
+
+/* Output spatial size for a descriptor (PyTorch's rules). */
+MVSB200_API int mvsb200_conv3d_out_shape(const mvsb200_conv3d_desc *desc, int *Do, int *Ho, int *Wo);
+
+/* x [B,D,H,W,Cin]; x2 [B,D,H,W,Cin2] or NULL; w packed [kd*kh*kw][Cin+Cin2][Cout] (tap-major; for a
+ * transposed conv the tap index is that of the ConvTranspose3d weight); scale,bias [Cout] or NULL
+ * (y = conv*scale + bias); skip [B,Do,Ho,Wo,Cout] or NULL; y [B,Do,Ho,Wo,Cout]. */
+MVSB200_API int mvsb200_conv3d(const mvsb200_conv3d_desc *desc, const float *x, const float *x2, const float *w,
+                   const float *scale, const float *bias, const float *skip, float *y,
+                   mvsb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3: softmax over D + depth regression + confidence (+ entropy, + probability volume).
+ * Replaces F.softmax + depth_regression (+ photometric confidence): models/MVSNet/model.py:207-215,
+ * module.py:174-182; soft_argmin / entropy: models/VisMVSNet/nn_utils.py:453-470; CVP net.py:161-162,
+ * 203-219.
+ * --------------------------------------------------------------------------------------- */
+#define MVSB200_CONF_NONE 0
+#define MVSB200_CONF_SUM4 1   /* sum of p over [idx-1, idx+2], idx = trunc(E[d])  (MVSNet/model.py:211-215) */
+#define MVSB200_CONF_WINDOW 2 /* sum of p over |d - E[d]| <= 2                    (nn_utils.py:463-465)     */
+
+/* score [B,D,H,W]; depth/interval as in K1 (depth_mode); outputs [B,H,W] (NULL to skip);
+ * prob_out [B,D,H,W] or NULL. */
+MVSB200_API int mvsb200_depth_regress(const float *score, int B, int D, int H, int W, int depth_mode, const float *depth,
+                          const float *interval, int conf_mode, float *depth_out, float *conf_out,
+                          float *entropy_out, float *prob_out, mvsb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4: visibility-weighted fusion of per-pair volumes (models/VisMVSNet/model_cas.py:354-357,385-386):
+ *   fused = sum_s exp(-uncert_s) * interm_s / sum_s exp(-uncert_s)
+ * interm, uncert: HOST arrays of S device pointers; interm[s] [B,D,H,W,G], uncert[s] [B,H,W]. */
+MVSB200_API int mvsb200_vis_fuse(const float *const *interm, const float *const *uncert, int S, int B, int D, int H, int W,
+                     int G, float *fused, mvsb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVSB200_H_ */

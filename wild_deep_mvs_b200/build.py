@@ -1,0 +1,66 @@
+"""Compile libmvsb200.so (CUDA, sm_100a only) in-tree with nvcc.
+
+    python -m wild_deep_mvs_b200.build [--force] [--verbose]
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+SO = os.path.join(HERE, "libmvsb200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
+    "--shared",
+    "-I", os.path.join(ROOT, "include"),
+    "-I", CSRC,
+]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def needs_build():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(ROOT, "include", "mvsb200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return SO
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    for src in sources():
+        obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--shared"] + ["-c", src, "-o", obj]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    failed = False
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0 or verbose:
+            sys.stderr.write(out)
+        failed |= pr.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    subprocess.check_call([nvcc, "--shared", "-o", SO] + objs)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,138 @@
+// K3: softmax over the depth axis + regression heads, and K4: visibility-weighted fusion.
+//
+// K3 reads the score volume [B,D,H,W] with one thread per pixel, consecutive lanes on consecutive
+// pixels, so every load of a depth slice is a fully coalesced 128-byte line per warp.  Three sweeps
+// over D (max, normaliser, heads); the second and third sweep hit L2 (a 148-SM wave touches
+// 148*256*D*4 bytes, far below the 126 MB L2).
+#include "common.cuh"
+
+namespace mvsb200 {
+
+constexpr int K3_THREADS = 128;
+
+struct K3Params {
+    const float *score, *depth, *interval;
+    float *depth_out, *conf_out, *entropy_out, *prob_out;
+    int B, D, depth_mode, conf_mode;
+    long long HW;
+};
+
+__global__ void __launch_bounds__(K3_THREADS) k3_depth_regress_kernel(const K3Params p)
+{
+    const int b = blockIdx.y;
+    const long long pix = (long long)blockIdx.x * K3_THREADS + threadIdx.x;
+    if (pix >= p.HW) return;
+    const float *s = p.score + (long long)b * p.D * p.HW + pix;
+    const int D = p.D;
+
+    float mx = -INFINITY;
+    for (int d = 0; d < D; d++) mx = fmaxf(mx, __ldg(s + d * p.HW));
+    float sum = 0.f;
+    for (int d = 0; d < D; d++) sum += expf(__ldg(s + d * p.HW) - mx);
+
+    const float interval = (p.depth_mode >= MVSB200_DEPTH_START) ? __ldg(p.interval + b) : 0.f;
+    float e_idx = 0.f, e_dep = 0.f, ent = 0.f;
+    float *prob = p.prob_out ? p.prob_out + (long long)b * D * p.HW + pix : nullptr;
+    for (int d = 0; d < D; d++) {
+        const float pr = expf(__ldg(s + d * p.HW) - mx) / sum;
+        if (prob) prob[d * p.HW] = pr;
+        e_idx += pr * (float)d;
+        if (p.depth_mode == MVSB200_DEPTH_VALUES) e_dep += pr * __ldg(p.depth + (long long)b * D + d);
+        else if (p.depth_mode == MVSB200_DEPTH_VOLUME) e_dep += pr * __ldg(p.depth + ((long long)b * D + d) * p.HW + pix);
+        if (p.entropy_out) ent += -pr * logf(fminf(fmaxf(pr, 1e-9f), 1.f));
+    }
+    if (p.depth_mode == MVSB200_DEPTH_START) e_dep = e_idx * interval + __ldg(p.depth + b);
+    else if (p.depth_mode == MVSB200_DEPTH_START_MAP) e_dep = e_idx * interval + __ldg(p.depth + (long long)b * p.HW + pix);
+    p.depth_out[(long long)b * p.HW + pix] = e_dep;
+    if (p.entropy_out) p.entropy_out[(long long)b * p.HW + pix] = ent;
+    if (p.conf_out) {
+        float c = 0.f;
+        if (p.conf_mode == MVSB200_CONF_SUM4) {
+            const int idx = (int)e_idx;  // .long() truncation, models/MVSNet/model.py:214
+            for (int j = idx - 1; j <= idx + 2; j++)
+                if (j >= 0 && j < D) c += expf(__ldg(s + j * p.HW) - mx) / sum;
+        } else {
+            // |d - E[d]| <= 2 touches at most 5 bins
+            const int lo = max((int)ceilf(e_idx - 2.f), 0), hi = min((int)floorf(e_idx + 2.f), D - 1);
+            for (int j = lo; j <= hi; j++)
+                if (fabsf((float)j - e_idx) <= 2.f) c += expf(__ldg(s + j * p.HW) - mx) / sum;
+        }
+        p.conf_out[(long long)b * p.HW + pix] = c;
+    }
+}
+
+constexpr int K4_THREADS = 256;
+
+struct K4Params {
+    const float *interm[MVSB200_MAX_SRC];
+    const float *uncert[MVSB200_MAX_SRC];
+    float *fused;
+    int S, D, G;
+    long long HW, total4;  // total4 = B*D*HW*G/4
+};
+
+// One thread per float4 of the fused volume; the per-pixel weights exp(-u_s) are recomputed per voxel
+// (S expf per float4 is noise next to the S+1 16-byte memory accesses).
+__global__ void __launch_bounds__(K4_THREADS) k4_vis_fuse_kernel(const K4Params p)
+{
+    const long long i = (long long)blockIdx.x * K4_THREADS + threadIdx.x;
+    if (i >= p.total4) return;
+    const long long vox = (i * 4) / p.G;              // b*D*HW + d*HW + pix
+    const long long b = vox / ((long long)p.D * p.HW);
+    const long long pix = vox % p.HW;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wsum = 0.f;
+    for (int s = 0; s < p.S; s++) {
+        const float w = expf(-__ldg(p.uncert[s] + b * p.HW + pix));
+        const float4 v = __ldcs(reinterpret_cast<const float4 *>(p.interm[s]) + i);
+        wsum = wsum + w;
+        acc.x = acc.x + v.x * w; acc.y = acc.y + v.y * w; acc.z = acc.z + v.z * w; acc.w = acc.w + v.w * w;
+    }
+    acc.x /= wsum; acc.y /= wsum; acc.z /= wsum; acc.w /= wsum;
+    reinterpret_cast<float4 *>(p.fused)[i] = acc;
+}
+
+}  // namespace mvsb200
+
+using namespace mvsb200;
+
+extern "C" int mvsb200_depth_regress(const float *score, int B, int D, int H, int W, int depth_mode,
+                                     const float *depth, const float *interval, int conf_mode, float *depth_out,
+                                     float *conf_out, float *entropy_out, float *prob_out, mvsb200_stream_t stream)
+{
+    MVSB200_REQUIRE(score && depth && depth_out, "depth_regress: null pointer");
+    MVSB200_REQUIRE(B > 0 && B <= 65535 && D > 0 && H > 0 && W > 0, "depth_regress: bad shape B=%d D=%d H=%d W=%d", B, D, H, W);
+    MVSB200_REQUIRE(depth_mode >= 0 && depth_mode <= 3, "depth_regress: depth_mode=%d", depth_mode);
+    MVSB200_REQUIRE(depth_mode < MVSB200_DEPTH_START || interval, "depth_regress: interval is null");
+    MVSB200_REQUIRE(conf_mode >= 0 && conf_mode <= 2, "depth_regress: conf_mode=%d", conf_mode);
+    MVSB200_REQUIRE(conf_mode == MVSB200_CONF_NONE || conf_out, "depth_regress: conf_out is null");
+    K3Params p;
+    p.score = score; p.depth = depth; p.interval = interval;
+    p.depth_out = depth_out; p.conf_out = conf_mode ? conf_out : nullptr; p.entropy_out = entropy_out; p.prob_out = prob_out;
+    p.B = B; p.D = D; p.depth_mode = depth_mode; p.conf_mode = conf_mode;
+    p.HW = (long long)H * W;
+    dim3 grid((unsigned)((p.HW + K3_THREADS - 1) / K3_THREADS), (unsigned)B);
+    k3_depth_regress_kernel<<<grid, K3_THREADS, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("k3_depth_regress_kernel");
+}
+
+extern "C" int mvsb200_vis_fuse(const float *const *interm, const float *const *uncert, int S, int B, int D, int H,
+                                int W, int G, float *fused, mvsb200_stream_t stream)
+{
+    MVSB200_REQUIRE(interm && uncert && fused, "vis_fuse: null pointer");
+    MVSB200_REQUIRE(S >= 1 && S <= MVSB200_MAX_SRC, "vis_fuse: S=%d", S);
+    MVSB200_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && G > 0 && G % 4 == 0, "vis_fuse: bad shape (G must be a multiple of 4)");
+    K4Params p;
+    for (int s = 0; s < S; s++) {
+        MVSB200_REQUIRE(interm[s] && uncert[s], "vis_fuse: null view %d", s);
+        p.interm[s] = interm[s];
+        p.uncert[s] = uncert[s];
+    }
+    p.fused = fused; p.S = S; p.D = D; p.G = G;
+    p.HW = (long long)H * W;
+    p.total4 = (long long)B * D * p.HW * G / 4;
+    long long blocks = (p.total4 + K4_THREADS - 1) / K4_THREADS;
+    MVSB200_REQUIRE(blocks < (1ll << 31), "vis_fuse: volume too large");
+    k4_vis_fuse_kernel<<<(unsigned)blocks, K4_THREADS, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("k4_vis_fuse_kernel");
+}

@@ -1,0 +1,189 @@
+"""Drop-in MVSNet / MVSNet-s (variance / softmin aggregation) running its hot path on libmvsb200.
+
+Mirrors the reference's interface for this path -- same class name, constructor argument, attribute
+names (`num_depth`, `aggregation`, `temp`), `forward(imgs, K, R, t, depth_min, depth_max,
+reference_frame=0, **kwargs)` signature, returned dict and state_dict key names -- so a checkpoint
+written by the reference's train.py loads unchanged (models/MVSNet/model.py:86-218).
+
+What runs where:
+  * FeatureNet (2-D CNN, models/MVSNet/model.py:21-41): PyTorch/cuDNN, channels_last  ("next" row f1)
+  * build_cost_volume  -> K1 (mvsb200_build_cost_volume), fused warp + aggregation
+  * cost_regularization -> K2 (mvsb200_conv3d), BN/ReLU/skip fused
+  * softmax / depth regression / confidence -> K3 (mvsb200_depth_regress)
+Inference only (eval mode); the backward pass is SURVEY.md 8-f2.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import ops
+
+
+def _cbr2d(cin, cout, k, stride, pad):
+    m = nn.Module()
+    m.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=pad, bias=False)
+    m.bn = nn.BatchNorm2d(cout)
+    return m
+
+
+class FeatureNet(nn.Module):
+    """Same parameters as the reference's FeatureNet (models/MVSNet/model.py:21-41)."""
+
+    def __init__(self):
+        super().__init__()
+        spec = [(3, 8, 3, 1, 1), (8, 8, 3, 1, 1), (8, 16, 5, 2, 2), (16, 16, 3, 1, 1), (16, 16, 3, 1, 1),
+                (16, 32, 5, 2, 2), (32, 32, 3, 1, 1)]
+        for i, s in enumerate(spec):
+            setattr(self, "conv%d" % i, _cbr2d(*s))
+        self.feature = nn.Conv2d(32, 32, 3, 1, 1)
+
+    def forward(self, x):
+        x = x.contiguous(memory_format=torch.channels_last)
+        for i in range(7):
+            m = getattr(self, "conv%d" % i)
+            x = F.relu(m.bn(m.conv(x)), inplace=True)
+        return self.feature(x)
+
+
+def _cbr3d(cin, cout):
+    m = nn.Module()
+    m.conv = nn.Conv3d(cin, cout, 3, padding=1, bias=False)
+    m.bn = nn.BatchNorm3d(cout)
+    return m
+
+
+def _dbr3d(cin, cout):
+    return nn.Sequential(nn.ConvTranspose3d(cin, cout, 3, padding=1, output_padding=1, stride=2, bias=False),
+                         nn.BatchNorm3d(cout), nn.ReLU(inplace=True))
+
+
+class CostRegNet(nn.Module):
+    """3-D U-Net regulariser; parameters named as models/MVSNet/model.py:43-72, executed by K2."""
+
+    _STRIDES = {"conv1": 2, "conv3": 2, "conv5": 2}
+
+    def __init__(self):
+        super().__init__()
+        chans = [(32, 8), (8, 16), (16, 16), (16, 32), (32, 32), (32, 64), (64, 64)]
+        for i, (a, b) in enumerate(chans):
+            setattr(self, "conv%d" % i, _cbr3d(a, b))
+        self.conv7, self.conv9, self.conv11 = _dbr3d(64, 32), _dbr3d(32, 16), _dbr3d(16, 8)
+        self.prob = nn.Conv3d(8, 1, 3, stride=1, padding=1)
+        self._packed = None
+        self._packed_key = None
+
+    def _pack(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + tuple(
+            (b.data_ptr(), b._version) for b in self.buffers())
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        pk = {}
+        for i in range(7):
+            name = "conv%d" % i
+            m = getattr(self, name)
+            pk[name] = ops.PackedConv(m.conv.weight, m.bn, stride=self._STRIDES.get(name, 1), relu=True)
+        for name in ("conv7", "conv9", "conv11"):
+            m = getattr(self, name)
+            pk[name] = ops.PackedConv(m[0].weight, m[1], stride=2, transposed=True, relu=True,
+                                      skip_mode=L.SKIP_AFTER_RELU)  # x = conv4 + relu(bn(deconv)), model.py:79-81
+        pk["prob"] = ops.PackedConv(self.prob.weight, None, conv_bias=self.prob.bias)
+        self._packed, self._packed_key = pk, key
+        return pk
+
+    def run(self, vol):
+        """vol [B,D,H,W,32] channels-last -> score [B,D,H,W]."""
+        if self.training:
+            raise NotImplementedError("libmvsb200 runs the regulariser in eval mode only (SURVEY.md 8-f2)")
+        B, D, H, W, _ = vol.shape
+        if D % 8 or H % 8 or W % 8:
+            raise L.Mvsb200Error("CostRegNet needs D,H,W divisible by 8 (got %d,%d,%d)" % (D, H, W))
+        pk = self._pack()
+        c0 = ops.conv3d(vol, pk["conv0"])
+        c2 = ops.conv3d(ops.conv3d(c0, pk["conv1"]), pk["conv2"])
+        c4 = ops.conv3d(ops.conv3d(c2, pk["conv3"]), pk["conv4"])
+        x = ops.conv3d(ops.conv3d(c4, pk["conv5"]), pk["conv6"])
+        x = ops.conv3d(x, pk["conv7"], skip=c4)
+        x = ops.conv3d(x, pk["conv9"], skip=c2)
+        x = ops.conv3d(x, pk["conv11"], skip=c0)
+        return ops.conv3d(x, pk["prob"]).squeeze(-1)
+
+    def forward(self, x, down_ft=None):
+        """Reference signature: x [B,32,D,H,W] -> [B,1,D,H,W] (models/MVSNet/model.py:74-84)."""
+        return self.run(ops.to_ndhwc(x)).unsqueeze(1)
+
+
+def build_proj_matrices(K, R, t):
+    """[[K R, K t],[0 0 0 1]]  (utils/utils_3D.py:50-62)."""
+    res = torch.zeros(K.shape[:-2] + (4, 4), device=K.device, dtype=K.dtype)
+    res[..., :3, :3] = K @ R
+    res[..., :3, 3:] = K @ t
+    res[..., 3, 3] = 1
+    return res
+
+
+class MVSNet(nn.Module):
+    def __init__(self, aggregation="variance"):
+        super().__init__()
+        self.feature = FeatureNet()
+        self.cost_regularization = CostRegNet()
+        if aggregation == "softmin":
+            self.register_parameter("temp", nn.Parameter(torch.ones(1)))
+        self.aggregation = aggregation
+        self.num_depth = 192
+
+    def extract_features(self, imgs):
+        if self.aggregation.startswith("norm"):
+            return [F.normalize(self.feature(img), dim=1) for img in imgs]
+        return [self.feature(img) for img in imgs]
+
+    # ---- channels-last engine entry (what forward uses) ------------------------------------------
+    def cost_volume_cl(self, ref_nhwc, srcs_nhwc, ref_proj, src_projs, depth_values):
+        """ref [B,H,W,C]; srcs list of [B,Hs,Ws,C]; projections [B,4,4]; depth_values [B,D] or [B,D,H,W]."""
+        if self.aggregation == "variance":
+            agg, temp = L.AGG_VARIANCE, None
+        elif self.aggregation == "softmin":
+            agg, temp = L.AGG_SOFTMIN, self.temp
+        else:
+            raise NotImplementedError("Aggregation: " + self.aggregation)
+        warp = ops.mvs_relative_proj(ref_proj, torch.stack(list(src_projs), 1))
+        return ops.build_cost_volume(ref_nhwc, srcs_nhwc, warp, depth_values, self.num_depth, L.GEOM_MVS, agg, temp=temp)
+
+    def build_cost_volume(self, ref_feature, src_features, ref_proj, src_projs, depth_values):
+        """Reference signature (models/MVSNet/model.py:109): NCHW features in, [B,C,D,H,W] out (a view)."""
+        vol = self.cost_volume_cl(ops.to_nhwc(ref_feature), [ops.to_nhwc(f) for f in src_features], ref_proj,
+                                  src_projs, depth_values)
+        return ops.as_ncdhw(vol)
+
+    def depth_from_features(self, feats_nhwc, proj_matrices, depth_values, reference_frame=0):
+        """The hot path proper: channels-last features -> (depth, confidence).  feats_nhwc: list of V maps."""
+        ref = feats_nhwc[reference_frame]
+        srcs = feats_nhwc[:reference_frame] + feats_nhwc[reference_frame + 1:]
+        ref_proj = proj_matrices[reference_frame]
+        src_projs = proj_matrices[:reference_frame] + proj_matrices[reference_frame + 1:]
+        vol = self.cost_volume_cl(ref, srcs, ref_proj, src_projs, depth_values)
+        score = self.cost_regularization.run(vol)
+        del vol
+        out = ops.depth_regress(score, depth_values, conf_mode=L.CONF_SUM4)
+        return out["depth"], out["conf"]
+
+    def forward(self, imgs, K, R, t, depth_min, depth_max, reference_frame=0, **kwargs):
+        if self.training:
+            raise NotImplementedError("libmvsb200 implements inference only; call .eval() (SURVEY.md 8-f2)")
+        try:
+            imgs = torch.unbind(imgs, 1)
+        except TypeError:  # already a list (views of different sizes)
+            pass
+        scaled_K = K.clone()
+        scaled_K[:, :, :2] /= 4
+        proj_matrices = torch.unbind(build_proj_matrices(scaled_K, R, t), 1)
+        steps = torch.arange(self.num_depth, device=depth_min.device).view(1, 1, -1)
+        depth_range = (depth_max - depth_min) / (self.num_depth - 1)
+        depth_values = depth_min.unsqueeze(-1) + depth_range.unsqueeze(-1) * steps
+        assert len(imgs) == len(proj_matrices), "Different number of images and projection matrices"
+
+        with torch.no_grad():
+            feats = [ops.to_nhwc(f) for f in self.extract_features(imgs)]
+            depth, conf = self.depth_from_features(list(feats), list(proj_matrices),
+                                                   depth_values[:, reference_frame].contiguous(), reference_frame)
+        return {"depth": depth, "depth_est_list": [depth], "depth_pair_list": [], "photometric_confidence": conf}

@@ -1,0 +1,227 @@
+"""Tensor <-> pointer marshalling for libmvsb200.so.  PyTorch provides device memory and the
+current stream; every computation below happens inside the library's CUDA kernels.
+
+Layouts (include/mvsb200.h): feature maps [B,H,W,C], volumes [B,D,H,W,C], single-channel volumes
+[B,D,H,W].  `to_nhwc` / `to_ndhwc` turn reference-layout tensors (NCHW / NCDHW) into these without a
+copy when the tensor is already channels-last in memory.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _dev_f32(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise L.Mvsb200Error("%s must be a contiguous float32 CUDA tensor" % name)
+    return t
+
+
+def to_nhwc(x):
+    """[B,C,H,W] (any strides) -> contiguous [B,H,W,C]."""
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def to_ndhwc(x):
+    """[B,C,D,H,W] (any strides) -> contiguous [B,D,H,W,C]."""
+    return x.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def as_ncdhw(v):
+    """[B,D,H,W,C] -> reference-shaped view [B,C,D,H,W] (no copy)."""
+    return v.permute(0, 4, 1, 2, 3)
+
+
+# ------------------------------------------------------------------------------------------------
+# geometry prologues
+# ------------------------------------------------------------------------------------------------
+def mvs_relative_proj(ref_proj, src_projs):
+    """ref_proj [B,4,4], src_projs [B,S,4,4] -> warp [B,S,16]; replaces MVSNet/module.py:128."""
+    ref_proj = _dev_f32(ref_proj.contiguous(), "ref_proj")
+    src_projs = _dev_f32(src_projs.contiguous(), "src_projs")
+    B, S = src_projs.shape[:2]
+    warp = torch.empty(B, S, 16, device=ref_proj.device, dtype=torch.float32)
+    L.check(L.load().mvsb200_mvs_relative_proj(_ptr(ref_proj), _ptr(src_projs), _ptr(warp), B, S, _stream()),
+            "mvsb200_mvs_relative_proj")
+    return warp
+
+
+def vis_homography_params(ref_cam, src_cams, scale):
+    """ref_cam [B,2,4,4], src_cams [B,S,2,4,4] -> warp [B,S,16]; replaces VisMVSNet/homography.py:23-74."""
+    ref_cam = _dev_f32(ref_cam.contiguous(), "ref_cam")
+    src_cams = _dev_f32(src_cams.contiguous(), "src_cams")
+    B, S = src_cams.shape[:2]
+    warp = torch.empty(B, S, 16, device=ref_cam.device, dtype=torch.float32)
+    L.check(L.load().mvsb200_vis_homography_params(_ptr(ref_cam), _ptr(src_cams), ctypes.c_float(scale), _ptr(warp),
+                                                   B, S, _stream()), "mvsb200_vis_homography_params")
+    return warp
+
+
+# ------------------------------------------------------------------------------------------------
+# K1
+# ------------------------------------------------------------------------------------------------
+def _depth_mode(depth, interval, B, D, H, W):
+    if interval is None:
+        if depth.dim() == 2:
+            assert depth.shape == (B, D), depth.shape
+            return L.DEPTH_VALUES
+        assert depth.shape == (B, D, H, W), depth.shape
+        return L.DEPTH_VOLUME
+    assert interval.numel() == B
+    if depth.numel() == B:
+        return L.DEPTH_START
+    assert depth.numel() == B * H * W, depth.shape
+    return L.DEPTH_START_MAP
+
+
+def build_cost_volume(ref, srcs, warp, depth, D, geom, agg, interval=None, temp=None, groups=8):
+    """ref [B,H,W,C]; srcs list of [B,Hs,Ws,C]; warp [B,S,16]; depth/interval see mvsb200.h.
+    Returns [B,D,H,W,C] or, for AGG_GROUPCORR, [S,B,D,H,W,groups]."""
+    lib = L.load()
+    ref = _dev_f32(ref, "ref")
+    B, H, W, C = ref.shape
+    S = len(srcs)
+    if not 1 <= S <= L.MAX_SRC:
+        raise L.Mvsb200Error("number of source views %d not in [1,%d]" % (S, L.MAX_SRC))
+    depth = _dev_f32(depth.contiguous(), "depth")
+    if interval is not None:
+        interval = _dev_f32(interval.contiguous().view(-1), "interval")
+    desc = L.CostVolumeDesc()
+    desc.geom, desc.agg = geom, agg
+    desc.depth_mode = _depth_mode(depth, interval, B, D, H, W)
+    desc.B, desc.S, desc.C, desc.D, desc.H, desc.W = B, S, C, D, H, W
+    desc.groups = groups if agg == L.AGG_GROUPCORR else 0
+    ptrs = (ctypes.c_void_p * S)()
+    for i, s in enumerate(srcs):
+        _dev_f32(s, "src[%d]" % i)
+        if s.shape[0] != B or s.shape[3] != C:
+            raise L.Mvsb200Error("src[%d] has shape %s, expected [%d,*,*,%d]" % (i, tuple(s.shape), B, C))
+        ptrs[i] = s.data_ptr()
+        desc.src_h[i], desc.src_w[i] = s.shape[1], s.shape[2]
+    if agg == L.AGG_GROUPCORR:
+        out = torch.empty(S, B, D, H, W, groups, device=ref.device, dtype=torch.float32)
+        desc.out_view_stride = B * D * H * W * groups
+    else:
+        out = torch.empty(B, D, H, W, C, device=ref.device, dtype=torch.float32)
+        desc.out_view_stride = 0
+    if temp is not None:
+        temp = _dev_f32(temp.detach().contiguous(), "temp")
+    L.check(lib.mvsb200_build_cost_volume(ctypes.byref(desc), _ptr(ref), ptrs, _ptr(_dev_f32(warp, "warp")), _ptr(depth),
+                                          _ptr(interval), _ptr(temp), _ptr(out), _stream()),
+            "mvsb200_build_cost_volume")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K2
+# ------------------------------------------------------------------------------------------------
+class PackedConv:
+    """A conv / transposed conv layer packed for mvsb200_conv3d: tap-major weights [taps][Cin][Cout],
+    folded eval-mode BatchNorm as (scale, bias), and the fused epilogue flags."""
+
+    def __init__(self, weight, bn=None, conv_bias=None, stride=1, transposed=False, relu=False,
+                 skip_mode=L.SKIP_NONE):
+        w = weight.detach().float()
+        if w.dim() == 4:  # 2-D conv (UncertNet): [Cout,Cin,kh,kw] -> kd = 1
+            w = w.unsqueeze(2)
+        if transposed and stride == 1:
+            # ConvTranspose3d(k=3, stride=1, padding=1) == Conv3d with the kernel flipped and channels swapped
+            # (CVP conv5, CVP_MVSNet/models/net.py:62-65)
+            w = w.flip(2, 3, 4).transpose(0, 1)
+            transposed = False
+        if transposed:  # [Cin,Cout,k,k,k]
+            self.cin, self.cout = w.shape[0], w.shape[1]
+            packed = w.permute(2, 3, 4, 0, 1)
+        else:           # [Cout,Cin,kd,kh,kw]
+            self.cout, self.cin = w.shape[0], w.shape[1]
+            packed = w.permute(2, 3, 4, 1, 0)
+        self.k = tuple(w.shape[2:])
+        self.w = packed.contiguous()
+        self.stride, self.transposed, self.relu, self.skip_mode = stride, int(transposed), int(relu), skip_mode
+        if bn is not None:
+            scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+            bias = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+            if conv_bias is not None:
+                bias = bias + conv_bias.detach().float() * scale
+            self.scale, self.bias = scale.contiguous(), bias.contiguous()
+        else:
+            self.scale = None
+            self.bias = conv_bias.detach().float().contiguous() if conv_bias is not None else None
+
+
+def conv3d(x, layer, x2=None, skip=None):
+    """x [B,D,H,W,Cin] (+ x2 [B,D,H,W,Cin2] concatenated on channels) -> [B,Do,Ho,Wo,Cout]."""
+    lib = L.load()
+    x = _dev_f32(x, "x")
+    B, D, H, W, C1 = x.shape
+    C2 = 0
+    if x2 is not None:
+        _dev_f32(x2, "x2")
+        assert x2.shape[:4] == x.shape[:4]
+        C2 = x2.shape[4]
+    if C1 + C2 != layer.cin:
+        raise L.Mvsb200Error("conv3d: input has %d channels, layer expects %d" % (C1 + C2, layer.cin))
+    desc = L.Conv3dDesc()
+    desc.B, desc.D, desc.H, desc.W = B, D, H, W
+    desc.Cin, desc.Cin2, desc.Cout = C1, C2, layer.cout
+    desc.kd, desc.kh, desc.kw = layer.k
+    desc.stride, desc.transposed, desc.relu = layer.stride, layer.transposed, layer.relu
+    desc.skip_mode = layer.skip_mode if skip is not None else L.SKIP_NONE
+    if layer.skip_mode != L.SKIP_NONE and skip is None:
+        raise L.Mvsb200Error("conv3d: layer fuses a skip connection but none was given")
+    do, ho, wo = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    L.check(lib.mvsb200_conv3d_out_shape(ctypes.byref(desc), ctypes.byref(do), ctypes.byref(ho), ctypes.byref(wo)),
+            "mvsb200_conv3d_out_shape")
+    y = torch.empty(B, do.value, ho.value, wo.value, layer.cout, device=x.device, dtype=torch.float32)
+    if skip is not None:
+        _dev_f32(skip, "skip")
+        assert skip.shape == y.shape, (skip.shape, y.shape)
+    L.check(lib.mvsb200_conv3d(ctypes.byref(desc), _ptr(x), _ptr(x2), _ptr(layer.w), _ptr(layer.scale), _ptr(layer.bias),
+                               _ptr(skip), _ptr(y), _stream()), "mvsb200_conv3d")
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# K3 / K4
+# ------------------------------------------------------------------------------------------------
+def depth_regress(score, depth, interval=None, conf_mode=L.CONF_NONE, want_entropy=False, want_prob=False):
+    """score [B,D,H,W] -> dict(depth [B,H,W], conf, entropy, prob)."""
+    lib = L.load()
+    score = _dev_f32(score, "score")
+    B, D, H, W = score.shape
+    depth = _dev_f32(depth.contiguous(), "depth")
+    if interval is not None:
+        interval = _dev_f32(interval.contiguous().view(-1), "interval")
+    mode = _depth_mode(depth, interval, B, D, H, W)
+    new = lambda *s: torch.empty(*s, device=score.device, dtype=torch.float32)
+    out = {"depth": new(B, H, W), "conf": new(B, H, W) if conf_mode else None,
+           "entropy": new(B, H, W) if want_entropy else None, "prob": new(B, D, H, W) if want_prob else None}
+    L.check(lib.mvsb200_depth_regress(_ptr(score), B, D, H, W, mode, _ptr(depth), _ptr(interval), conf_mode,
+                                      _ptr(out["depth"]), _ptr(out["conf"]), _ptr(out["entropy"]), _ptr(out["prob"]),
+                                      _stream()), "mvsb200_depth_regress")
+    return out
+
+
+def vis_fuse(interms, uncerts):
+    """interms list of [B,D,H,W,G]; uncerts list of [B,H,W] -> [B,D,H,W,G]."""
+    lib = L.load()
+    S = len(interms)
+    B, D, H, W, G = interms[0].shape
+    ip, up = (ctypes.c_void_p * S)(), (ctypes.c_void_p * S)()
+    for i in range(S):
+        _dev_f32(interms[i], "interm[%d]" % i)
+        _dev_f32(uncerts[i], "uncert[%d]" % i)
+        assert interms[i].shape == interms[0].shape and uncerts[i].numel() == B * H * W
+        ip[i], up[i] = interms[i].data_ptr(), uncerts[i].data_ptr()
+    out = torch.empty_like(interms[0])
+    L.check(lib.mvsb200_vis_fuse(ip, up, S, B, D, H, W, G, _ptr(out), _stream()), "mvsb200_vis_fuse")
+    return out
