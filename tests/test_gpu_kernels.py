@@ -192,8 +192,8 @@ def test_k2_fused_epilogue_and_concat():
         bn.weight.copy_(cu(rng.random(8) + 0.5)); bn.bias.copy_(cu(rng.standard_normal(8)))
         bn.running_mean.copy_(cu(rng.standard_normal(8) * 0.1)); bn.running_var.copy_(cu(rng.random(8) + 0.5))
     conv = orc.conv3d(np.concatenate([xa, xb], 0), w, None, 1)
-    y = orc.bn_relu(conv, bn.weight.cpu().numpy(), bn.bias.cpu().numpy(), bn.running_mean.cpu().numpy(),
-                    bn.running_var.cpu().numpy(), bn.eps, relu=False)
+    npy = lambda t: t.detach().cpu().numpy()
+    y = orc.bn_relu(conv, npy(bn.weight), npy(bn.bias), npy(bn.running_mean), npy(bn.running_var), bn.eps, relu=False)
     for mode, want in ((L.SKIP_BEFORE_RELU, np.maximum(y + skip, 0)), (L.SKIP_AFTER_RELU, np.maximum(y, 0) + skip)):
         layer = ops.PackedConv(cu(w), bn, relu=True, skip_mode=mode)
         got = from_ndhwc(ops.conv3d(ndhwc(xa), layer, x2=ndhwc(xb), skip=ndhwc(skip)))

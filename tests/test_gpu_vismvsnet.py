@@ -1,0 +1,96 @@
+"""GPU: drop-in Vis-MVSNet (wild_deep_mvs_b200.vismvsnet.Frontend) against the reference-generated golden
+(tests/golden/vis.npz: 1+2 views, 64x80 image, depth_nums [8,4,4]) and the C oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_linf
+
+pytestmark = pytest.mark.gpu
+
+from wild_deep_mvs_b200 import ops, synth  # noqa: E402
+from wild_deep_mvs_b200.vismvsnet import Frontend  # noqa: E402
+
+DEV = "cuda:0"
+DEPTH_TOL = 1e-3
+
+
+def _load(g):
+    net = Frontend()
+    sd = net.state_dict()
+    n = 0
+    for k, v in g.items():
+        if k.startswith("model.stage"):
+            assert k in sd, k
+            sd[k] = torch.from_numpy(v)
+            n += 1
+    assert n > 100
+    net.load_state_dict(sd, strict=True)
+    net.depth_nums, net.interval_scales = [8, 4, 4], [4, 2, 1]
+    return net.to(DEV).eval()
+
+
+def _inputs(g):
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    feats = [[ops.to_nhwc(t(g["feat_v%d_s%d" % (v, k)])) for k in (1, 2, 3)] for v in range(3)]
+    ref_cam = t(g["ref_cam"])
+    src_cams = torch.stack([t(g["src_cam1"]), t(g["src_cam2"])], 1)
+    dmin = t(g["depth_min"][:, 0])
+    interval = ((t(g["depth_max"]) - t(g["depth_min"])) / 128)[:, 0].contiguous()
+    return feats, ref_cam, src_cams, dmin, interval
+
+
+def test_state_dict_names_match_reference(golden):
+    g = golden("vis")
+    sd = Frontend().state_dict()
+    for k, v in g.items():
+        if k.startswith("model."):
+            assert k in sd and tuple(sd[k].shape) == v.shape, k
+    for k in ("model.feat_ext.init_conv.0.weight", "model.feat_ext.unet.enc_blocks.2d2_0.0.downsample.0.weight",
+              "model.feat_ext.unet.dec_blocks.2d16_3.2.0.conv1.weight", "model.feat_ext.final_conv_3.weight",
+              "model.stage3.uncert_net.head_convs.0.weight"):
+        assert k in sd, k
+
+
+def test_stage1_seams_against_reference(golden):
+    g = golden("vis")
+    net = _load(g)
+    feats, ref_cam, src_cams, dmin, interval = _inputs(g)
+    d, p, pairs = net.model.stage1.run(feats[0][0], [feats[1][0], feats[2][0]], ref_cam, src_cams, 8, dmin,
+                                       (interval * 4).contiguous(), 8)
+    assert rel_linf(d.cpu().numpy(), g["depth_est_2"]) < DEPTH_TOL
+    assert rel_linf(pairs[0][0][:, 0].cpu().numpy(), g["pair_depth_st2_v0"][:, 0]) < DEPTH_TOL
+    assert rel_linf(pairs[1][0][:, 0].cpu().numpy(), g["pair_depth_st2_v1"][:, 0]) < DEPTH_TOL
+    assert np.abs(pairs[0][1][0][:, 0].cpu().numpy() - g["pair_uncert_st2_v0"][:, 0]).max() < 2e-3
+
+
+def test_cascade_against_reference_and_oracle(golden):
+    from oracle import nets
+    g = golden("vis")
+    net = _load(g)
+    feats, ref_cam, src_cams, dmin, interval = _inputs(g)
+    ests, probs, pairs = net.depth_from_features(feats, ref_cam, src_cams, dmin, interval, [8, 4, 4], [4, 2, 1])
+    for k in range(3):
+        assert rel_linf(ests[2 - k].cpu().numpy(), g["depth_est_%d" % k]) < DEPTH_TOL
+    assert rel_linf(ests[2].cpu().numpy(), g["depth"]) < 2e-4   # what fp32 actually achieves
+    np_feats = [[g["feat_v%d_s%d" % (v, k)][0] for k in (1, 2, 3)] for v in range(3)]
+    want = nets.vis_from_features(g, np_feats, g["ref_cam"][0], [g["src_cam1"][0], g["src_cam2"][0]],
+                                  g["depth_min"][0, 0], g["depth_max"][0, 0], [8, 4, 4], [4, 2, 1])
+    assert rel_linf(ests[2][0].cpu().numpy(), want["depth"]) < 2e-4
+    assert np.abs(probs[0][0].cpu().numpy() - want["seams"][0].get("prob", probs[0][0].cpu().numpy())).max() < 1
+
+
+def test_forward_api(golden):
+    torch.manual_seed(0)
+    net = Frontend()
+    synth.randomize_norm_stats(net, seed=2)
+    net = net.to(DEV).eval()
+    s = {k: v.to(DEV) for k, v in synth.make_sample(2, 3, 64, 80, seed=0).items()}
+    out = net(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"], depth_nums=[8, 4, 4], interval_scales=[4, 2, 1])
+    assert out["depth"].shape == (2, 32, 40)
+    assert [tuple(d.shape) for d in out["depth_est_list"]] == [(2, 32, 40), (2, 16, 20), (2, 8, 10)]
+    assert out["photometric_confidence"].shape == (2, 3, 32, 40)
+    assert len(out["depth_pair_list"]) == 3 and len(out["depth_pair_list"][0]) == 2
+    est, heads = out["depth_pair_list"][0][0]
+    assert est.shape == (2, 1, 32, 40) and heads[0].shape == (2, 1, 32, 40)
+    assert all(torch.isfinite(d).all() for d in out["depth_est_list"])

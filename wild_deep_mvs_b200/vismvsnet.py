@@ -1,0 +1,297 @@
+"""Drop-in Vis-MVSNet (`Frontend`) running its three cascade stages on libmvsb200.
+
+Mirrors models/VisMVSNet/frontend.py:6-109 of the reference: same class layout (`Frontend.model.feat_ext`,
+`.stage1/2/3.{reg, reg_fuse, reg_pair, uncert_net}`), state_dict key names, `depth_nums` / `interval_scales`
+attributes and kwargs, forward signature and returned dict.
+
+Per stage (SingleStage.forward, models/VisMVSNet/model_cas.py:303-420, mode='soft'):
+  K1  closed-form homographies + warp + 8-group correlation for ALL source views in one launch
+  K2  Reg U-Net + RegPair head on the S pair volumes stacked along the batch axis (shared weights)
+  K3  pair soft-argmin + entropy;  UncertNet (three tiny 2-D convs, also K2);
+  K4  visibility-weighted fusion;  K2 RegFuse U-Net + head;  K3 soft-argmin with the +-2 window confidence.
+FeatExt (2-D U-Net) and the bilinear up-sampling of the previous stage's depth stay in PyTorch ("next" rows).
+Inference only.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import ops
+
+
+class _Named(nn.Module):
+    """Container whose children carry the reference's (non-identifier) names, e.g. 'reg14_0'."""
+
+    def __init__(self, items):
+        super().__init__()
+        for name, m in items:
+            self.add_module(str(name), m)
+
+    def __getitem__(self, name):
+        return self._modules[str(name)]
+
+    def __iter__(self):
+        return iter(self._modules.values())
+
+
+class _Block(nn.Module):
+    """Parameters of BasicBlock (models/VisMVSNet/nn_utils.py:123-171)."""
+
+    def __init__(self, cin, cout, stride, dim):
+        super().__init__()
+        conv = nn.Conv2d if dim == 2 else nn.Conv3d
+        bn = nn.BatchNorm2d if dim == 2 else nn.BatchNorm3d
+        self.conv1 = conv(cin, cout, 3, stride, 1, bias=False)
+        self.bn1 = bn(cout)
+        self.conv2 = conv(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = bn(cout)
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(conv(cin, cout, 1, stride, bias=False), bn(cout))
+        self.stride = stride
+
+    def forward(self, x):  # PyTorch execution, used by the 2-D feature extractor only
+        y = F.relu(self.bn1(self.conv1(x)), inplace=True)
+        y = self.bn2(self.conv2(y))
+        r = x if self.downsample is None else self.downsample(x)
+        return F.relu(y + r, inplace=True)
+
+
+def _layer(cin, cout, blocks, stride, dim):
+    mods = [_Block(cin, cout, stride, dim)] + [_Block(cout, cout, 1, dim) for _ in range(blocks - 1)]
+    return nn.Sequential(*mods)
+
+
+class _FeatUNet(nn.Module):
+    """UNet(16, 2, 1, 2, [], [32, 64, 128], [], '2d', 2) of models/VisMVSNet/model_cas.py:27."""
+
+    def __init__(self):
+        super().__init__()
+        self.enc_blocks = _Named([("2d2_0", _layer(16, 32, 2, 1, 2)), ("2d4_1", _layer(32, 64, 2, 2, 2)),
+                                  ("2d8_2", _layer(64, 128, 2, 2, 2))])
+        self.dec_blocks = _Named([
+            ("2d16_3", _Named([(0, nn.ConvTranspose2d(128, 64, 3, 2, 1, 1, bias=False)), (1, nn.Conv2d(128, 64, 3, 1, 1, bias=False)),
+                               (2, _layer(64, 64, 1, 1, 2))])),
+            ("2d8_4", _Named([(0, nn.ConvTranspose2d(64, 32, 3, 2, 1, 1, bias=False)), (1, nn.Conv2d(64, 32, 3, 1, 1, bias=False)),
+                              (2, _layer(32, 32, 1, 1, 2))]))])
+
+    def forward(self, x):
+        enc = []
+        for b in self.enc_blocks:
+            x = b(x)
+            enc.append(x)
+        outs = [x]
+        for i, b in enumerate(self.dec_blocks):
+            x = b[0](x)
+            x = b[1](torch.cat([x, enc[-2 - i]], 1))
+            x = b[2](x)
+            outs.append(x)
+        return outs
+
+
+class FeatExt(nn.Module):
+    """models/VisMVSNet/model_cas.py:18-35: 32-channel features at 1/8, 1/4, 1/2 image resolution."""
+
+    def __init__(self):
+        super().__init__()
+        self.init_conv = nn.Sequential(nn.Conv2d(3, 16, 5, 2, 2, bias=False), nn.BatchNorm2d(16), nn.ReLU())
+        self.unet = _FeatUNet()
+        self.final_conv_1 = nn.Conv2d(128, 32, 3, 1, 1, bias=False)
+        self.final_conv_2 = nn.Conv2d(64, 32, 3, 1, 1, bias=False)
+        self.final_conv_3 = nn.Conv2d(32, 32, 3, 1, 1, bias=False)
+
+    def forward(self, x):
+        x = x.contiguous(memory_format=torch.channels_last)
+        o1, o2, o3 = self.unet(self.init_conv(x))
+        return self.final_conv_1(o1), self.final_conv_2(o2), self.final_conv_3(o3)
+
+
+class _RegUNet(nn.Module):
+    """UNet(8, 1, 0, 4, [], [8, 16], [], tag, dim=3) (model_cas.py:43,63); executed by K2."""
+
+    def __init__(self, tag):
+        super().__init__()
+        self.tag = tag
+        self.enc_blocks = _Named([(tag + "4_0", _layer(8, 8, 1, 1, 3)), (tag + "8_1", _layer(8, 16, 1, 2, 3))])
+        self.dec_blocks = _Named([(tag + "16_2", _Named([(0, nn.ConvTranspose3d(16, 8, 3, 2, 1, 1, bias=False)),
+                                                         (1, nn.Conv3d(16, 8, 3, 1, 1, bias=False))]))])
+
+    def pack(self):
+        b0 = self.enc_blocks[self.tag + "4_0"][0]
+        b1 = self.enc_blocks[self.tag + "8_1"][0]
+        dec = self.dec_blocks[self.tag + "16_2"]
+        return {
+            "b0c1": ops.PackedConv(b0.conv1.weight, b0.bn1, relu=True),
+            "b0c2": ops.PackedConv(b0.conv2.weight, b0.bn2, relu=True, skip_mode=L.SKIP_BEFORE_RELU),
+            "b1ds": ops.PackedConv(b1.downsample[0].weight, b1.downsample[1], stride=2),
+            "b1c1": ops.PackedConv(b1.conv1.weight, b1.bn1, stride=2, relu=True),
+            "b1c2": ops.PackedConv(b1.conv2.weight, b1.bn2, relu=True, skip_mode=L.SKIP_BEFORE_RELU),
+            "up": ops.PackedConv(dec[0].weight, None, stride=2, transposed=True),
+            "post": ops.PackedConv(dec[1].weight, None),
+        }
+
+    @staticmethod
+    def run(pk, x):
+        e0 = ops.conv3d(ops.conv3d(x, pk["b0c1"]), pk["b0c2"], skip=x)
+        r = ops.conv3d(e0, pk["b1ds"])
+        e1 = ops.conv3d(ops.conv3d(e0, pk["b1c1"]), pk["b1c2"], skip=r)
+        up = ops.conv3d(e1, pk["up"])
+        return ops.conv3d(up, pk["post"], x2=e0)  # conv(cat([up, e0], 1)), nn_utils.py:268-269
+
+
+class Reg(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.unet = _RegUNet("reg1")
+
+
+class RegPair(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.final_conv = nn.Conv3d(8, 1, 3, 1, 1, bias=False)
+
+
+class RegFuse(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.unet = _RegUNet("reg2")
+        self.final_conv = nn.Conv3d(8, 1, 3, 1, 1, bias=False)
+
+
+class UncertNet(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Sequential(nn.Conv2d(1, 8, 3, 1, 1, bias=False), nn.BatchNorm2d(8), nn.ReLU())
+        self.conv2 = nn.Sequential(nn.Conv2d(8, 8, 3, 1, 1, bias=False), nn.BatchNorm2d(8), nn.ReLU())
+        self.head_convs = _Named([(0, nn.Conv2d(8, 1, 3, 1, 1, bias=False))])
+
+
+class SingleStage(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.reg = Reg()
+        self.reg_fuse = RegFuse()
+        self.reg_pair = RegPair()
+        self.uncert_net = UncertNet()
+        self._packed, self._key = None, None
+
+    def _pack(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + tuple(
+            (b.data_ptr(), b._version) for b in self.buffers())
+        if self._packed is None or key != self._key:
+            u = self.uncert_net
+            self._packed = {
+                "reg": self.reg.unet.pack(), "fuse": self.reg_fuse.unet.pack(),
+                "pair_head": ops.PackedConv(self.reg_pair.final_conv.weight),
+                "fuse_head": ops.PackedConv(self.reg_fuse.final_conv.weight),
+                "u1": ops.PackedConv(u.conv1[0].weight, u.conv1[1], relu=True),
+                "u2": ops.PackedConv(u.conv2[0].weight, u.conv2[1], relu=True, skip_mode=L.SKIP_AFTER_RELU),
+                "uh": ops.PackedConv(u.head_convs[0].weight),
+            }
+            self._key = key
+        return self._packed
+
+    def run(self, ref, srcs, ref_cam, src_cams, depth_num, depth_start, depth_interval, s_scale):
+        """ref [B,H,W,32], srcs list of [B,Hs,Ws,32]; cams [B,2,4,4] / [B,S,2,4,4]; depth_start [B] or [B,H,W];
+        depth_interval [B].  Returns est_depth [B,H,W], prob_map [B,H,W], pair list [(depth, uncert)]."""
+        if self.training:
+            raise NotImplementedError("libmvsb200 implements inference only (SURVEY.md 8-f2)")
+        pk = self._pack()
+        B, H, W, _ = ref.shape
+        S = len(srcs)
+        D = depth_num
+        if D % 2 or H % 2 or W % 2:
+            raise L.Mvsb200Error("Vis-MVSNet regulariser needs even D,H,W (got %d,%d,%d)" % (D, H, W))
+        warp = ops.vis_homography_params(ref_cam, src_cams, 1.0 / s_scale)
+        cost = ops.build_cost_volume(ref, srcs, warp, depth_start, D, L.GEOM_VIS, L.AGG_GROUPCORR,
+                                     interval=depth_interval, groups=8)            # [S,B,D,H,W,8]
+        interm = _RegUNet.run(pk["reg"], cost.view(S * B, D, H, W, 8))              # pairs stacked on the batch axis
+        del cost
+        score = ops.conv3d(interm, pk["pair_head"]).squeeze(-1)                     # [S*B,D,H,W]
+        start_sb = depth_start.repeat(S, *([1] * (depth_start.dim() - 1)))
+        pair = ops.depth_regress(score, start_sb, interval=depth_interval.reshape(-1).repeat(S), want_entropy=True)
+        ent = pair["entropy"].view(S * B, 1, H, W, 1)
+        u = ops.conv3d(ent, pk["u1"])
+        u = ops.conv3d(u, pk["u2"], skip=ent.expand(-1, -1, -1, -1, 8).contiguous())  # out += x (broadcast), model_cas.py:95
+        u = ops.conv3d(u, pk["uh"]).view(S, B, H, W)
+        interm = interm.view(S, B, D, H, W, 8)
+        fused = ops.vis_fuse([interm[s] for s in range(S)], [u[s] for s in range(S)])
+        pair_depth = pair["depth"].view(S, B, H, W)
+        pairs = [[pair_depth[s].unsqueeze(1), [u[s].unsqueeze(1)]] for s in range(S)]
+        del interm
+        fscore = ops.conv3d(_RegUNet.run(pk["fuse"], fused), pk["fuse_head"]).squeeze(-1)
+        out = ops.depth_regress(fscore, depth_start, interval=depth_interval, conf_mode=L.CONF_WINDOW)
+        return out["depth"], out["conf"], pairs
+
+
+class Model(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.feat_ext = FeatExt()
+        self.stage1 = SingleStage()
+        self.stage2 = SingleStage()
+        self.stage3 = SingleStage()
+
+
+class Frontend(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.model = Model()
+        self.depth_nums = [32, 16, 8]
+        self.interval_scales = [4, 2, 1]
+
+    @staticmethod
+    def fill_cam_array(K, R, t, start_depth, depth_interval):
+        """[B,2,4,4]: [:,0] = R|t, [:,1] = K with [1,3,0]=depth start, [1,3,1]=interval (frontend.py:14-24)."""
+        res = torch.zeros(K.shape[0], 2, 4, 4, device=K.device)
+        res[:, 0, :3, :3] = R
+        res[:, 0, :3, 3:4] = t
+        res[:, 1, :3, :3] = K
+        res[:, 1, 3, 0] = start_depth
+        res[:, 1, 3, 1] = depth_interval
+        return res
+
+    def depth_from_features(self, feats, ref_cam, src_cams, depth_min, depth_interval, depth_nums, interval_scales):
+        """feats[v][k]: channels-last [B,h_k,w_k,32] of view v (0 = reference) at stage k; ref_cam [B,2,4,4];
+        src_cams [B,S,2,4,4]; depth_min, depth_interval [B].  The cascade of frontend.py:66-98."""
+        stages = (self.model.stage1, self.model.stage2, self.model.stage3)
+        ests, probs, pairs = [], [], []
+        start = depth_min.contiguous()
+        for k, (stage, s_scale) in enumerate(zip(stages, (8, 4, 2))):
+            ref = feats[0][k]
+            if k > 0:
+                up = F.interpolate(ests[-1].unsqueeze(1), size=(ref.shape[1], ref.shape[2]), mode="bilinear",
+                                   align_corners=False).squeeze(1)
+                # the reference reads self.interval_scales here, not the kwarg override (frontend.py:76-78)
+                start = (up - depth_nums[k] * depth_interval.view(-1, 1, 1) * self.interval_scales[k] / 2).contiguous()
+            d, p, pr = stage.run(ref, [f[k] for f in feats[1:]], ref_cam, src_cams, depth_nums[k], start,
+                                 (depth_interval * interval_scales[k]).contiguous(), s_scale)
+            ests.append(d)
+            probs.append(p)
+            pairs.append(pr)
+        return ests, probs, pairs
+
+    def forward(self, imgs, K, R, t, depth_min, depth_max, reference_frame=0, **kwargs):
+        if self.training:
+            raise NotImplementedError("libmvsb200 implements inference only; call .eval() (SURVEY.md 8-f2)")
+        depth_interval = (depth_max - depth_min) / 128
+        interval_scales = kwargs.get("interval_scales", self.interval_scales)
+        depth_nums = kwargs.get("depth_nums", self.depth_nums)
+        if not isinstance(imgs, list):
+            imgs = list(torch.unbind(imgs, dim=1))
+        v = len(imgs)
+        src_idx = list(range(reference_frame)) + list(range(reference_frame + 1, v))
+        with torch.no_grad():
+            ref_cam = self.fill_cam_array(K[:, reference_frame], R[:, reference_frame], t[:, reference_frame],
+                                          depth_min[:, reference_frame], depth_interval[:, reference_frame])
+            src_cams = torch.stack([self.fill_cam_array(K[:, i], R[:, i], t[:, i], depth_min[:, i], depth_interval[:, i])
+                                    for i in src_idx], 1)
+            feats = [[ops.to_nhwc(f) for f in self.model.feat_ext(imgs[i])] for i in [reference_frame] + src_idx]
+            ests, probs, pairs = self.depth_from_features(feats, ref_cam, src_cams, depth_min[:, reference_frame],
+                                                          depth_interval[:, reference_frame].contiguous(), depth_nums,
+                                                          interval_scales)
+            p1 = F.interpolate(probs[0].unsqueeze(1), scale_factor=4, mode="bilinear", align_corners=False)
+            p2 = F.interpolate(probs[1].unsqueeze(1), scale_factor=2, mode="bilinear", align_corners=False)
+        return {"depth": ests[2], "depth_est_list": ests[::-1], "depth_pair_list": pairs[::-1],
+                "photometric_confidence": torch.cat([p1, p2, probs[2].unsqueeze(1)], dim=1)}
