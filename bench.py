@@ -192,7 +192,8 @@ def workload_config(n):
     return {"workload": "BASELINE cfg2: MVSNet variance, 1 ref + 4 src views, 640x512 images -> 32ch 160x128 features, D=192, "
                         "features->depth+confidence (K1 warp+variance, K2 3-D U-Net, K3 softmax/regress)",
             "views": CFG["views"], "feature_hw": [CFG["h"], CFG["w"]], "D": CFG["D"], "voxels_per_map": voxels(),
-            "maps_per_step": n, "parallelism": "view-sharded replicas x%d + 1 all-gather of depth maps" % n,
+            "maps_per_step": n, "k2_engine": os.environ.get("MVSB200_K2_ENGINE", "tc") + " (tcgen05 kind::tf32, 3xTF32 split = fp32-equivalent)",
+            "parallelism": "view-sharded replicas x%d + 1 all-gather of depth maps" % n,
             "l2": "flushed between timed steps (512 MiB memset, untimed); intermediate volumes (503 MB) exceed L2"}
 
 

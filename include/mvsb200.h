@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MVSB200_ABI_VERSION 1
+#define MVSB200_ABI_VERSION 2
 
 #define MVSB200_OK 0
 #define MVSB200_E_INVALID (-1)  /* bad argument / unsupported shape */
@@ -131,6 +131,23 @@ MVSB200_API int mvsb200_conv3d_out_shape(const mvsb200_conv3d_desc *desc, int *D
 MVSB200_API int mvsb200_conv3d(const mvsb200_conv3d_desc *desc, const float *x, const float *x2, const float *w,
                    const float *scale, const float *bias, const float *skip, float *y,
                    mvsb200_stream_t stream);
+
+/* K2 on the tcgen05 tensor cores (k=3 layers with Cin % 8 == 0 and Cout in {1, 8, 16, 32, 64, ...}): implicit GEMM,
+ * kind::tf32 MMAs with TMEM accumulators, same fused epilogue as mvsb200_conv3d.
+ *   MVSB200_PRECISION_3XTF32  error-compensated split products, fp32-equivalent (the parity-tested default)
+ *   MVSB200_PRECISION_TF32    single-pass TF32 (10-bit mantissa operands, fp32 accumulate); faster, outside the
+ *                             1e-3 depth parity bar on peaked cost volumes
+ * Weights are packed once per layer: `w` is the tap-major [27][Cin+Cin2][Cout] buffer mvsb200_conv3d takes,
+ * `packed` a device buffer of mvsb200_conv3d_tc_packed_floats(desc) floats. */
+#define MVSB200_PRECISION_3XTF32 0
+#define MVSB200_PRECISION_TF32 1
+MVSB200_API int mvsb200_conv3d_tc_supported(const mvsb200_conv3d_desc *desc);
+MVSB200_API long long mvsb200_conv3d_tc_packed_floats(const mvsb200_conv3d_desc *desc);
+MVSB200_API int mvsb200_conv3d_tc_pack(const mvsb200_conv3d_desc *desc, const float *w, float *packed,
+                                       mvsb200_stream_t stream);
+MVSB200_API int mvsb200_conv3d_tc(const mvsb200_conv3d_desc *desc, const float *x, const float *x2, const float *packed,
+                                  const float *scale, const float *bias, const float *skip, float *y, int precision,
+                                  mvsb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K3: softmax over D + depth regression + confidence (+ entropy, + probability volume).

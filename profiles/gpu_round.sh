@@ -4,7 +4,7 @@
 # Outputs land in gpurun_out/ (scratch); the summaries worth keeping are copied into profiles/ by hand.
 set -u
 TAG=${1:-r1}
-KREGEX=${2:-"k1_cost_volume|k2_conv3d|k2_tc"}
+KREGEX=${2:-"k1_cost_volume|k2_conv3d"}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi_$TAG.txt 2>&1

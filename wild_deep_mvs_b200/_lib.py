@@ -14,6 +14,8 @@ AGG_VARIANCE, AGG_VARIANCE_MEAN, AGG_SOFTMIN, AGG_GROUPCORR = 0, 1, 2, 3
 DEPTH_VALUES, DEPTH_VOLUME, DEPTH_START, DEPTH_START_MAP = 0, 1, 2, 3
 SKIP_NONE, SKIP_BEFORE_RELU, SKIP_AFTER_RELU = 0, 1, 2
 CONF_NONE, CONF_SUM4, CONF_WINDOW = 0, 1, 2
+PRECISION_3XTF32, PRECISION_TF32 = 0, 1
+ABI_VERSION = 2
 
 
 class Mvsb200Error(RuntimeError):
@@ -50,6 +52,10 @@ SIGNATURES = {
     "mvsb200_build_cost_volume": (_i, [ctypes.POINTER(CostVolumeDesc), _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvsb200_conv3d_out_shape": (_i, [ctypes.POINTER(Conv3dDesc)] + [ctypes.POINTER(_i)] * 3),
     "mvsb200_conv3d": (_i, [ctypes.POINTER(Conv3dDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvsb200_conv3d_tc_supported": (_i, [ctypes.POINTER(Conv3dDesc)]),
+    "mvsb200_conv3d_tc_packed_floats": (ctypes.c_longlong, [ctypes.POINTER(Conv3dDesc)]),
+    "mvsb200_conv3d_tc_pack": (_i, [ctypes.POINTER(Conv3dDesc), _vp, _vp, _vp]),
+    "mvsb200_conv3d_tc": (_i, [ctypes.POINTER(Conv3dDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "mvsb200_depth_regress": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "mvsb200_vis_fuse": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
@@ -70,8 +76,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.mvsb200_abi_version() != 1:
-        raise Mvsb200Error("libmvsb200.so ABI version %d, expected 1" % lib.mvsb200_abi_version())
+    if lib.mvsb200_abi_version() != ABI_VERSION:
+        raise Mvsb200Error("libmvsb200.so ABI version %d, expected %d" % (lib.mvsb200_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
 

@@ -6,10 +6,17 @@ Layouts (include/mvsb200.h): feature maps [B,H,W,C], volumes [B,D,H,W,C], single
 copy when the tensor is already channels-last in memory.
 """
 import ctypes
+import os
 
 import torch
 
 from . import _lib as L
+
+# K2 engine: "tc" = tcgen05 tensor cores with 3xTF32 split products (fp32-equivalent, the parity-tested default),
+# "tc_tf32" = tensor cores, single-pass TF32, "fp32" = the CUDA-core kernel.  Layers the tensor-core engine does not
+# cover (1x1x1, 2-D, Cin % 8 != 0) always run on the fp32 kernel.
+ENGINES = ("tc", "tc_tf32", "fp32")
+DEFAULT_ENGINE = os.environ.get("MVSB200_K2_ENGINE", "tc")
 
 
 def _stream():
@@ -156,11 +163,25 @@ class PackedConv:
         else:
             self.scale = None
             self.bias = conv_bias.detach().float().contiguous() if conv_bias is not None else None
+        self._tc_packed = None
+
+    def tc_packed(self, desc):
+        """Weights split into tf32 hi/lo and laid out as tcgen05 B operands (packed once, on the device)."""
+        if self._tc_packed is None:
+            lib = L.load()
+            n = lib.mvsb200_conv3d_tc_packed_floats(ctypes.byref(desc))
+            buf = torch.empty(n, device=self.w.device, dtype=torch.float32)
+            L.check(lib.mvsb200_conv3d_tc_pack(ctypes.byref(desc), _ptr(self.w), _ptr(buf), _stream()), "mvsb200_conv3d_tc_pack")
+            self._tc_packed = buf
+        return self._tc_packed
 
 
-def conv3d(x, layer, x2=None, skip=None):
+def conv3d(x, layer, x2=None, skip=None, engine=None):
     """x [B,D,H,W,Cin] (+ x2 [B,D,H,W,Cin2] concatenated on channels) -> [B,Do,Ho,Wo,Cout]."""
     lib = L.load()
+    engine = engine or DEFAULT_ENGINE
+    if engine not in ENGINES:
+        raise L.Mvsb200Error("conv3d: unknown engine %r (expected one of %s)" % (engine, ", ".join(ENGINES)))
     x = _dev_f32(x, "x")
     B, D, H, W, C1 = x.shape
     C2 = 0
@@ -185,6 +206,11 @@ def conv3d(x, layer, x2=None, skip=None):
     if skip is not None:
         _dev_f32(skip, "skip")
         assert skip.shape == y.shape, (skip.shape, y.shape)
+    if engine != "fp32" and x.device == layer.w.device and lib.mvsb200_conv3d_tc_supported(ctypes.byref(desc)):
+        prec = L.PRECISION_3XTF32 if engine == "tc" else L.PRECISION_TF32
+        L.check(lib.mvsb200_conv3d_tc(ctypes.byref(desc), _ptr(x), _ptr(x2), _ptr(layer.tc_packed(desc)), _ptr(layer.scale),
+                                      _ptr(layer.bias), _ptr(skip), _ptr(y), prec, _stream()), "mvsb200_conv3d_tc")
+        return y
     L.check(lib.mvsb200_conv3d(ctypes.byref(desc), _ptr(x), _ptr(x2), _ptr(layer.w), _ptr(layer.scale), _ptr(layer.bias),
                                _ptr(skip), _ptr(y), _stream()), "mvsb200_conv3d")
     return y
