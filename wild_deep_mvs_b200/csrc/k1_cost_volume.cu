@@ -5,7 +5,9 @@
 // 32/LPV adjacent pixels and every tap is a 16-byte load per lane, fully coalesced per pixel.
 // The depth axis is walked in chunks of DCH hypotheses whose running aggregates stay in registers while
 // the source views are visited one after the other (view-outer, depth-inner), so nothing C-wide except
-// the final cost volume is ever written.
+// the final cost volume is ever written.  The projection / tap geometry of a (pixel, hypothesis, view) does not
+// depend on the channel, so the LPV lanes of a pixel split the chunk's hypotheses between them and exchange the
+// packed taps by warp shuffle; the four taps are re-loaded only when the 2x2 cell changes between hypotheses.
 //
 // Sampling semantics follow the reference bit for bit in structure (see oracle/mvs_oracle.c):
 //   MVS geometry  models/MVSNet/module.py:138-155   (integer pixel grid, z<=0 -> (-10,-10), clamp +-10)
@@ -65,28 +67,28 @@ __device__ __forceinline__ Taps make_taps(float gx, float gy, int Hs, int Ws)
     return t;
 }
 
-template <int C>
-__device__ __forceinline__ float4 sample(const float *__restrict__ map, const Taps &t, int Ws, int sub)
+// Packed taps as they travel between lanes: cell = clamped north-west pixel index with the east/south steps in the
+// two top bits (maps are far below 2^29 pixels), plus the four zero-padding-folded weights.
+struct PackedTaps {
+    int cell;
+    float w00, w01, w10, w11;
+};
+
+__device__ __forceinline__ PackedTaps pack_taps(const Taps &t)
 {
-    const float *p = map + t.o00 * C + sub * 4;
-    float4 a = ldg4(p);
-    float4 b = ldg4(p + (long long)t.dx * C);
-    float4 c = ldg4(p + (long long)t.dy * Ws * C);
-    float4 d = ldg4(p + ((long long)t.dy * Ws + t.dx) * C);
-    float4 r;
-    // accumulation order nw, ne, sw, se (ATen grid_sampler_2d)
-    r.x = a.x * t.w00; r.y = a.y * t.w00; r.z = a.z * t.w00; r.w = a.w * t.w00;
-    r.x += b.x * t.w01; r.y += b.y * t.w01; r.z += b.z * t.w01; r.w += b.w * t.w01;
-    r.x += c.x * t.w10; r.y += c.y * t.w10; r.z += c.z * t.w10; r.w += c.w * t.w10;
-    r.x += d.x * t.w11; r.y += d.y * t.w11; r.z += d.z * t.w11; r.w += d.w * t.w11;
-    return r;
+    PackedTaps q;
+    q.cell = (int)t.o00 | (t.dx << 29) | (t.dy << 30);
+    q.w00 = t.w00; q.w01 = t.w01; q.w10 = t.w10; q.w11 = t.w11;
+    return q;
 }
 
 template <int C, int GEOM, int AGG>
 __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Params p)
 {
-    constexpr int LPV = C / 4;        // lanes per voxel
-    constexpr int VPB = K1_THREADS / LPV;  // pixels per block
+    constexpr int LPV = C / 4;              // lanes per voxel
+    constexpr int VPB = K1_THREADS / LPV;   // pixels per block
+    constexpr int KPL = K1_DCH / LPV;       // hypotheses whose geometry each lane of a pixel group computes
+    static_assert(K1_DCH % LPV == 0, "depth chunk must split evenly over the lanes of a pixel group");
     __shared__ float s_warp[MVSB200_MAX_SRC * 16];
 
     const int b = blockIdx.z;
@@ -96,18 +98,21 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
     __syncthreads();
 
     const int sub = threadIdx.x % LPV;
-    const long long pix = (long long)blockIdx.x * VPB + threadIdx.x / LPV;
-    if (pix >= HW) return;  // whole LPV-lane groups leave together; shuffles below use group masks
+    const long long pix_raw = (long long)blockIdx.x * VPB + threadIdx.x / LPV;
+    const bool active = pix_raw < HW;                 // inactive groups shadow the last pixel and store nothing,
+    const long long pix = active ? pix_raw : HW - 1;  // so every shuffle below runs with the full warp
     const int y = (int)(pix / p.W), x = (int)(pix % p.W);
 
     const float4 r = ldg4(p.ref + ((long long)b * HW + pix) * C + sub * 4);
     const float interval = (p.depth_mode >= MVSB200_DEPTH_START) ? __ldg(p.interval + b) : 0.f;
 
-    float dv[K1_DCH];
+    // The projection of a (pixel, hypothesis, view) is the same for every channel: lane `sub` of the pixel group
+    // computes it for hypotheses sub, sub+LPV, ... of the chunk and the group shares the taps by shuffle.
+    float dv[KPL];
 #pragma unroll
-    for (int k = 0; k < K1_DCH; k++) {
-        int d = min(d0 + k, p.D - 1);
-        dv[k] = hypothesis(p.depth_mode, p.depth, interval, b, d, p.D, HW, pix);
+    for (int j = 0; j < KPL; j++) {
+        int d = min(d0 + j * LPV + sub, p.D - 1);
+        dv[j] = hypothesis(p.depth_mode, p.depth, interval, b, d, p.D, HW, pix);
     }
 
     float4 acc1[K1_DCH], acc2[K1_DCH];
@@ -124,12 +129,11 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
         sum_exp[k] = 0.f;
     }
     const float temp = (AGG == MVSB200_AGG_SOFTMIN) ? __ldg(p.temp) : 0.f;
-    const unsigned gmask = (LPV == 32) ? 0xffffffffu : (((1u << LPV) - 1u) << ((threadIdx.x % 32) / LPV * LPV));
 
     for (int s = 0; s < p.S; s++) {
         const float *wp = s_warp + s * 16;
         const int Hs = p.src_h[s], Ws = p.src_w[s];
-        const float *map = p.src[s] + (long long)b * Hs * Ws * C;
+        const float *map = p.src[s] + (long long)b * Hs * Ws * C + sub * 4;
         float ax, ay, az, np_ = 0.f;
         if (GEOM == MVSB200_GEOM_MVS) {
             const float fx = (float)x, fy = (float)y;
@@ -144,17 +148,18 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
             np_ = wp[12] * fx + wp[13] * fy + wp[14];
         }
         const float bx = wp[9], by = wp[10], bz = wp[11];
+        PackedTaps own[KPL];
 #pragma unroll
-        for (int k = 0; k < K1_DCH; k++) {
+        for (int j = 0; j < KPL; j++) {
             float gx, gy;
             if (GEOM == MVSB200_GEOM_MVS) {
-                float qx = ax * dv[k] + bx, qy = ay * dv[k] + by, qz = az * dv[k] + bz;
+                float qx = ax * dv[j] + bx, qy = ay * dv[j] + by, qz = az * dv[j] + bz;
                 float px = qx / qz, py = qy / qz;
                 if (qz <= 0.f) px = -10.f, py = -10.f;
                 gx = clampf(px / ((float)(Ws - 1) / 2.f) - 1.f, -10.f, 10.f);
                 gy = clampf(py / ((float)(Hs - 1) / 2.f) - 1.f, -10.f, 10.f);
             } else {
-                float f = np_ / (dv[k] + 1e-9f);
+                float f = np_ / (dv[j] + 1e-9f);
                 float qx = ax - bx * f, qy = ay - by * f, qz = az - bz * f;
                 float zc = fmaxf(qz, 1e-9f);
                 float u = qx / zc, v = qy / zc;
@@ -164,8 +169,36 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
             }
             // NaN coordinates (degenerate cameras) sample nothing
             if (!(gx == gx) || !(gy == gy)) gx = gy = -10.f;
-            const Taps t = make_taps(gx, gy, Hs, Ws);
-            const float4 w = sample<C>(map, t, Ws, sub);
+            own[j] = pack_taps(make_taps(gx, gy, Hs, Ws));
+        }
+
+        // Consecutive hypotheses of a pixel move along the epipolar line by a fraction of a pixel, so they mostly
+        // fall into the same 2x2 tap cell: the four 16-byte taps stay in registers until the cell changes.
+        int cur_cell = -1;
+        float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta, tc = ta, td = ta;
+#pragma unroll
+        for (int k = 0; k < K1_DCH; k++) {
+            const int owner = k % LPV, j = k / LPV;
+            const int cell = __shfl_sync(0xffffffffu, own[j].cell, owner, LPV);
+            const float w00 = __shfl_sync(0xffffffffu, own[j].w00, owner, LPV);
+            const float w01 = __shfl_sync(0xffffffffu, own[j].w01, owner, LPV);
+            const float w10 = __shfl_sync(0xffffffffu, own[j].w10, owner, LPV);
+            const float w11 = __shfl_sync(0xffffffffu, own[j].w11, owner, LPV);
+            if (cell != cur_cell) {
+                cur_cell = cell;
+                const int o00 = cell & 0x1fffffff, dx = (cell >> 29) & 1, dy = (cell >> 30) & 1;
+                const float *q = map + (long long)o00 * C;
+                ta = ldg4(q);
+                tb = ldg4(q + dx * C);
+                tc = ldg4(q + (long long)dy * Ws * C);
+                td = ldg4(q + ((long long)dy * Ws + dx) * C);
+            }
+            float4 w;
+            // accumulation order nw, ne, sw, se (ATen grid_sampler_2d)
+            w.x = ta.x * w00; w.y = ta.y * w00; w.z = ta.z * w00; w.w = ta.w * w00;
+            w.x += tb.x * w01; w.y += tb.y * w01; w.z += tb.z * w01; w.w += tb.w * w01;
+            w.x += tc.x * w10; w.y += tc.y * w10; w.z += tc.z * w10; w.w += tc.w * w10;
+            w.x += td.x * w11; w.y += td.y * w11; w.z += td.z * w11; w.w += td.w * w11;
             if (AGG == MVSB200_AGG_VARIANCE || AGG == MVSB200_AGG_VARIANCE_MEAN) {
                 acc1[k].x += w.x; acc1[k].y += w.y; acc1[k].z += w.z; acc1[k].w += w.w;
                 acc2[k].x += w.x * w.x; acc2[k].y += w.y * w.y; acc2[k].z += w.z * w.z; acc2[k].w += w.w * w.w;
@@ -174,7 +207,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
                 df.x *= df.x; df.y *= df.y; df.z *= df.z; df.w *= df.w;
                 float ssd = (df.x + df.y) + (df.z + df.w);
 #pragma unroll
-                for (int m = LPV / 2; m >= 1; m >>= 1) ssd += __shfl_xor_sync(gmask, ssd, m);
+                for (int m = LPV / 2; m >= 1; m >>= 1) ssd += __shfl_xor_sync(0xffffffffu, ssd, m);
                 float e = expf(-temp * ssd);
                 sum_exp[k] += e;
                 acc1[k].x += df.x * e; acc1[k].y += df.y * e; acc1[k].z += df.z * e; acc1[k].w += df.w * e;
@@ -183,13 +216,13 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
                 g += r.y * w.y;
                 g += r.z * w.z;
                 g += r.w * w.w;
-                if (d0 + k < p.D)
+                if (active && d0 + k < p.D)
                     __stcs(p.out + s * p.out_view_stride + (((long long)b * p.D + d0 + k) * HW + pix) * LPV + sub, g);
             }
         }
     }
 
-    if (AGG == MVSB200_AGG_GROUPCORR) return;
+    if (AGG == MVSB200_AGG_GROUPCORR || !active) return;
     const float V = (float)(p.S + 1);
 #pragma unroll
     for (int k = 0; k < K1_DCH; k++) {
