@@ -137,3 +137,21 @@ def test_full_size_properties():
     # (5) permuting the source views leaves the variance volume unchanged up to fp32 re-association
     vol_p = net.cost_volume_cl(nh[0], nh[:0:-1], projs[0], projs[:0:-1], depth)
     assert rel_linf(vol_p.cpu().numpy(), vol.cpu().numpy()) < 1e-5
+
+
+def test_cuda_graph_replay_equals_eager_launches(golden):
+    """GraphedHotPath captures the ~14 launches of a step once; replays on new inputs must equal eager calls bit for bit."""
+    g = golden("mvsnet_variance")
+    net = _load(g, "variance")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    feats = [ops.to_nhwc(t(g["feat%d" % i])) for i in range(3)]
+    projs = [t(g["proj"][:, i]) for i in range(3)]
+    dv = t(g["depth_values"])
+    graphed = net.graphed(feats, projs, dv)
+    d_eager, c_eager = net.depth_from_features(feats, projs, dv)
+    d_graph, c_graph = graphed()
+    assert torch.equal(d_graph, d_eager) and torch.equal(c_graph, c_eager)
+    feats2 = [f.flip(1).contiguous() for f in feats]          # new inputs through the same graph
+    d2_eager, _ = net.depth_from_features(feats2, projs, dv)
+    d2_graph, _ = graphed(feats2, projs, dv)
+    assert torch.equal(d2_graph, d2_eager) and not torch.equal(d2_graph, d_eager)

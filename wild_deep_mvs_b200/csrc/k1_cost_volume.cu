@@ -67,6 +67,15 @@ __device__ __forceinline__ Taps make_taps(float gx, float gy, int Hs, int Ws)
     return t;
 }
 
+// x / d for a divisor whose correctly rounded reciprocal r is known: one residual correction of x*r gives the
+// correctly rounded quotient for normal operands (the fast path of the IEEE division sequence, without its range
+// check and slow-path call -- the epilogue divides 64 values per thread by V and V^2).
+__device__ __forceinline__ float div_by(float x, float d, float r)
+{
+    const float q = x * r;
+    return fmaf(fmaf(-q, d, x), r, q);
+}
+
 // Packed taps as they travel between lanes: cell = clamped north-west pixel index with the east/south steps in the
 // two top bits (maps are far below 2^29 pixels), plus the four zero-padding-folded weights.
 struct PackedTaps {
@@ -133,7 +142,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
     for (int s = 0; s < p.S; s++) {
         const float *wp = s_warp + s * 16;
         const int Hs = p.src_h[s], Ws = p.src_w[s];
-        const float *map = p.src[s] + (long long)b * Hs * Ws * C + sub * 4;
+        const float *map = p.src[s] + (long long)b * Hs * Ws * C;   // warp-uniform base, 32-bit element offsets below
         float ax, ay, az, np_ = 0.f;
         if (GEOM == MVSB200_GEOM_MVS) {
             const float fx = (float)x, fy = (float)y;
@@ -186,12 +195,12 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
             const float w11 = __shfl_sync(0xffffffffu, own[j].w11, owner, LPV);
             if (cell != cur_cell) {
                 cur_cell = cell;
-                const int o00 = cell & 0x1fffffff, dx = (cell >> 29) & 1, dy = (cell >> 30) & 1;
-                const float *q = map + (long long)o00 * C;
-                ta = ldg4(q);
-                tb = ldg4(q + dx * C);
-                tc = ldg4(q + (long long)dy * Ws * C);
-                td = ldg4(q + ((long long)dy * Ws + dx) * C);
+                const unsigned o00 = (unsigned)(cell & 0x1fffffff) * C + sub * 4;
+                const unsigned ox = ((cell >> 29) & 1) * C, oy = ((cell >> 30) & 1) * (unsigned)(Ws * C);
+                ta = ldg4(map + o00);
+                tb = ldg4(map + (o00 + ox));
+                tc = ldg4(map + (o00 + oy));
+                td = ldg4(map + (o00 + oy + ox));
             }
             float4 w;
             // accumulation order nw, ne, sw, se (ATen grid_sampler_2d)
@@ -223,26 +232,28 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
     }
 
     if (AGG == MVSB200_AGG_GROUPCORR || !active) return;
-    const float V = (float)(p.S + 1);
+    const float V = (float)(p.S + 1), V2 = V * V;
+    const float rV = 1.f / V, rV2 = 1.f / V2;
 #pragma unroll
     for (int k = 0; k < K1_DCH; k++) {
         if (d0 + k >= p.D) break;
         float4 o;
         if (AGG == MVSB200_AGG_VARIANCE) {
-            const float V2 = V * V;
-            o.x = acc2[k].x / V - (acc1[k].x * acc1[k].x) / V2;
-            o.y = acc2[k].y / V - (acc1[k].y * acc1[k].y) / V2;
-            o.z = acc2[k].z / V - (acc1[k].z * acc1[k].z) / V2;
-            o.w = acc2[k].w / V - (acc1[k].w * acc1[k].w) / V2;
+            o.x = div_by(acc2[k].x, V, rV) - div_by(acc1[k].x * acc1[k].x, V2, rV2);
+            o.y = div_by(acc2[k].y, V, rV) - div_by(acc1[k].y * acc1[k].y, V2, rV2);
+            o.z = div_by(acc2[k].z, V, rV) - div_by(acc1[k].z * acc1[k].z, V2, rV2);
+            o.w = div_by(acc2[k].w, V, rV) - div_by(acc1[k].w * acc1[k].w, V2, rV2);
         } else if (AGG == MVSB200_AGG_VARIANCE_MEAN) {
-            float mx = acc1[k].x / V, my = acc1[k].y / V, mz = acc1[k].z / V, mw = acc1[k].w / V;
-            o.x = acc2[k].x / V - mx * mx;
-            o.y = acc2[k].y / V - my * my;
-            o.z = acc2[k].z / V - mz * mz;
-            o.w = acc2[k].w / V - mw * mw;
+            const float mx = div_by(acc1[k].x, V, rV), my = div_by(acc1[k].y, V, rV), mz = div_by(acc1[k].z, V, rV),
+                        mw = div_by(acc1[k].w, V, rV);
+            o.x = div_by(acc2[k].x, V, rV) - mx * mx;
+            o.y = div_by(acc2[k].y, V, rV) - my * my;
+            o.z = div_by(acc2[k].z, V, rV) - mz * mz;
+            o.w = div_by(acc2[k].w, V, rV) - mw * mw;
         } else {
-            float den = sum_exp[k] + 1e-6f;
-            o.x = acc1[k].x / den; o.y = acc1[k].y / den; o.z = acc1[k].z / den; o.w = acc1[k].w / den;
+            const float den = sum_exp[k] + 1e-6f, rden = 1.f / den;
+            o.x = div_by(acc1[k].x, den, rden); o.y = div_by(acc1[k].y, den, rden);
+            o.z = div_by(acc1[k].z, den, rden); o.w = div_by(acc1[k].w, den, rden);
         }
         st4_stream(p.out + (((long long)b * p.D + d0 + k) * HW + pix) * C + sub * 4, o);
     }
@@ -294,6 +305,8 @@ extern "C" int mvsb200_build_cost_volume(const mvsb200_cost_volume_desc *d, cons
     p.ref = ref;
     for (int s = 0; s < d->S; s++) {
         MVSB200_REQUIRE(src[s] && d->src_h[s] > 0 && d->src_w[s] > 0, "build_cost_volume: source %d invalid", s);
+        MVSB200_REQUIRE((long long)d->src_h[s] * d->src_w[s] < (1ll << 29) && (long long)d->src_h[s] * d->src_w[s] * d->C < (1ll << 31),
+                        "build_cost_volume: source %d too large (%dx%d)", s, d->src_h[s], d->src_w[s]);
         p.src[s] = src[s];
         p.src_h[s] = d->src_h[s];
         p.src_w[s] = d->src_w[s];

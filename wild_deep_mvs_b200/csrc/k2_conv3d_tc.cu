@@ -99,7 +99,7 @@ struct TcParams {
 };
 
 template <int MODE, int CT, int NPROD>
-__global__ void __launch_bounds__(TC_THREADS, 2) k2_conv3d_tc_kernel(const TcParams p)
+__global__ void __launch_bounds__(TC_THREADS, (TcTile<MODE, CT, NPROD>::TMEM_COLS > 256) ? 1 : 2) k2_conv3d_tc_kernel(const TcParams p)
 {
     using T = TcTile<MODE, CT, NPROD>;
     constexpr int NHL = T::NHL, RA = T::R_ALLOC, NC = T::NCOLS;
@@ -134,35 +134,62 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k2_conv3d_tc_kernel(const TcPar
 
     const float *wp_nb = p.wp + (size_t)nb * windows_per_chunk(MODE) * nch * (8 * NC);
     uint32_t phase = 0;
-    bool first_stage = true;
 
-    for (int c = 0; c < nch; c++) {
+    // Software pipeline: the global loads of stage st+1 are issued into registers right after the MMAs of stage st
+    // have been launched, so their latency overlaps the tensor-core work; the registers are split into tf32 hi/lo
+    // and stored to shared memory once the MMAs (which read that memory) have completed.
+    // Lane pairs share a voxel: even lanes fetch channels [0,4) of the chunk, odd lanes [4,8), so a warp-level
+    // LDG.128 covers 16 voxels x 32 contiguous bytes (one sector each).
+    constexpr int NPF = (T::SUBR + TC_THREADS / 2 - 1) / (TC_THREADS / 2);   // staged voxels per lane pair
+    constexpr int NPB = (T::MAX_WIN * 2 * NC + TC_THREADS - 1) / TC_THREADS;  // weight float4s per thread
+    const int half = tid & 1;
+    float4 preA[NPF], preB[NPB];
+    const int nstages = nch * T::NSUB;
+
+    auto prefetch = [&](int st) {
+        const int c = st / T::NSUB, s = st % T::NSUB;
         const float *src;
         int cs, cstride;
         if (c * 8 < p.Cin1) { src = p.x; cs = c * 8; cstride = p.Cin1; }
         else { src = p.x2; cs = c * 8 - p.Cin1; cstride = p.Cin2; }
+        const int pz = (s >> 2) & 1, py = (s >> 1) & 1, px = s & 1;
+#pragma unroll
+        for (int k = 0; k < NPF; k++) {
+            const int i = (tid >> 1) + k * (TC_THREADS / 2);
+            const int lx = i % T::EX, r = i / T::EX;
+            const int ly = r % T::EY, lz = r / T::EY;
+            int gz, gy, gx;
+            if (MODE == TC_S1) { gz = z0 - 1 + lz; gy = y0 - 1 + ly; gx = x0 - 1 + lx; }
+            else if (MODE == TC_S2) { gz = 2 * (z0 + lz) - 1 + pz; gy = 2 * (y0 + ly) - 1 + py; gx = 2 * (x0 + lx) - 1 + px; }
+            else { gz = z0 + lz; gy = y0 + ly; gx = x0 + lx; }
+            preA[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < T::SUBR && (unsigned)gz < (unsigned)p.D && (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W)
+                preA[k] = ldg4(src + ((((long long)b * p.D + gz) * p.H + gy) * p.W + gx) * cstride + cs + half * 4);
+        }
+        // weights of this (class, chunk, sub-grid): contiguous in the packed buffer
+        const int nwin = windows_of(MODE, (MODE == TC_S2) ? s : cl);
+        const float4 *wsrc = reinterpret_cast<const float4 *>(wp_nb) + (size_t)pack_block_offset(MODE, cl, c, s, nch) * (2 * NC);
+#pragma unroll
+        for (int k = 0; k < NPB; k++) {
+            const int i = tid + k * TC_THREADS;
+            if (i < nwin * 2 * NC) preB[k] = __ldg(wsrc + i);
+        }
+    };
+
+    prefetch(0);
 #pragma unroll 1
-        for (int s = 0; s < T::NSUB; s++) {
-            if (!first_stage) {   // the previous stage's MMAs still read sA / sB
-                mbar_wait(bar, phase);
-                phase ^= 1;
-            }
-            // ---- stage the input block: global (fp32, channels-last) -> hi/lo tf32 planes in shared memory ----
-            const int pz = (s >> 2) & 1, py = (s >> 1) & 1, px = s & 1;
-            // lane pairs share a voxel: even lanes fetch channels [0,4) of the chunk, odd lanes [4,8), so a warp-level
-            // LDG.128 covers 16 voxels x 32 contiguous bytes (one sector each) instead of 32 half-used sectors
-            const int half = tid & 1;
-#pragma unroll 4
-            for (int i = tid >> 1; i < T::SUBR; i += TC_THREADS / 2) {
-                const int lx = i % T::EX, r = i / T::EX;
-                const int ly = r % T::EY, lz = r / T::EY;
-                int gz, gy, gx;
-                if (MODE == TC_S1) { gz = z0 - 1 + lz; gy = y0 - 1 + ly; gx = x0 - 1 + lx; }
-                else if (MODE == TC_S2) { gz = 2 * (z0 + lz) - 1 + pz; gy = 2 * (y0 + ly) - 1 + py; gx = 2 * (x0 + lx) - 1 + px; }
-                else { gz = z0 + lz; gy = y0 + ly; gx = x0 + lx; }
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((unsigned)gz < (unsigned)p.D && (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W)
-                    v = ldg4(src + ((((long long)b * p.D + gz) * p.H + gy) * p.W + gx) * cstride + cs + half * 4);
+    for (int st = 0; st < nstages; st++) {
+        const int s = st % T::NSUB;
+        if (st > 0) {   // the previous stage's MMAs still read sA / sB
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        }
+        // ---- registers -> hi/lo tf32 planes in shared memory ----
+#pragma unroll
+        for (int k = 0; k < NPF; k++) {
+            const int i = (tid >> 1) + k * (TC_THREADS / 2);
+            if (i < T::SUBR) {
+                const float4 v = preA[k];
                 if (NPROD == 3) {
                     float4 h, l;
                     split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
@@ -171,46 +198,46 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k2_conv3d_tc_kernel(const TcPar
                     sA[half * RA + i] = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
                 }
             }
-            // ---- stage the weights of this (class, chunk, sub-grid): contiguous in the packed buffer ----
-            const int v3 = (MODE == TC_S2) ? s : cl;
-            const int vz = (v3 >> 2) & 1, vy = (v3 >> 1) & 1;
-            const int nz = dim_opts(MODE, vz), ny = dim_opts(MODE, vy);
-            {
-                const float4 *wsrc = reinterpret_cast<const float4 *>(wp_nb) + (size_t)pack_block_offset(MODE, cl, c, s, nch) * (2 * NC);
-                for (int i = tid; i < nz * ny * 2 * NC; i += TC_THREADS) sB[i] = __ldg(wsrc + i);
-            }
-            fence_proxy_async_smem();
-            __syncthreads();
-            // ---- one thread issues every MMA of the stage ----
-            if (warp == 0) {
-                if (lane == 0) {
-                    tc_fence_after_sync();
-                    constexpr uint32_t idesc = idesc_tf32(128, NC);
-                    const uint64_t adesc = smem_desc(smem_u32(sA), RA * 16, 128);
-                    const uint64_t bdesc = smem_desc(smem_u32(sB), NC * 16, 128);
-                    int win = 0;
-#pragma unroll 1
-                    for (int jz = 0; jz < nz; jz++)
-#pragma unroll 1
-                        for (int jy = 0; jy < ny; jy++, win++) {
-                            const int shift = (dim_shift(MODE, vz, jz) * T::EY + dim_shift(MODE, vy, jy)) * T::EX;
-                            const uint64_t bd = bdesc + (uint64_t)(win * 2 * NC);
-                            const uint32_t acc0 = (first_stage && win == 0) ? 0u : 1u;
-#pragma unroll
-                            for (int mt = 0; mt < T::NMT; mt++) {
-                                const int row0 = (mt / T::MT_PLANE) * T::P + (mt % T::MT_PLANE) * 128 + shift;
-                                const uint64_t a_hi = adesc + (uint64_t)row0;
-                                const uint32_t d = tmem + mt * NC;
-                                mma_tf32(d, a_hi, bd, idesc, acc0);
-                                if (NPROD == 3) mma_tf32(d, a_hi + 2 * RA, bd, idesc, 1u);
-                            }
-                        }
-                    mma_commit(bar);
-                }
-                __syncwarp();
-            }
-            first_stage = false;
         }
+        const int v3 = (MODE == TC_S2) ? s : cl;
+        const int vz = (v3 >> 2) & 1, vy = (v3 >> 1) & 1;
+        const int nz = dim_opts(MODE, vz), ny = dim_opts(MODE, vy);
+#pragma unroll
+        for (int k = 0; k < NPB; k++) {
+            const int i = tid + k * TC_THREADS;
+            if (i < nz * ny * 2 * NC) sB[i] = preB[k];
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        // ---- one thread issues every MMA of the stage ----
+        if (warp == 0) {
+            if (lane == 0) {
+                tc_fence_after_sync();
+                constexpr uint32_t idesc = idesc_tf32(128, NC);
+                const uint64_t adesc = smem_desc(smem_u32(sA), RA * 16, 128);
+                const uint64_t bdesc = smem_desc(smem_u32(sB), NC * 16, 128);
+                int win = 0;
+#pragma unroll 1
+                for (int jz = 0; jz < nz; jz++)
+#pragma unroll 1
+                    for (int jy = 0; jy < ny; jy++, win++) {
+                        const int shift = (dim_shift(MODE, vz, jz) * T::EY + dim_shift(MODE, vy, jy)) * T::EX;
+                        const uint64_t bd = bdesc + (uint64_t)(win * 2 * NC);
+                        const uint32_t acc0 = (st == 0 && win == 0) ? 0u : 1u;
+#pragma unroll
+                        for (int mt = 0; mt < T::NMT; mt++) {
+                            const int row0 = (mt / T::MT_PLANE) * T::P + (mt % T::MT_PLANE) * 128 + shift;
+                            const uint64_t a_hi = adesc + (uint64_t)row0;
+                            const uint32_t d = tmem + mt * NC;
+                            mma_tf32(d, a_hi, bd, idesc, acc0);
+                            if (NPROD == 3) mma_tf32(d, a_hi + 2 * RA, bd, idesc, 1u);
+                        }
+                    }
+                mma_commit(bar);
+            }
+            __syncwarp();
+        }
+        if (st + 1 < nstages) prefetch(st + 1);
     }
     mbar_wait(bar, phase);
     tc_fence_after_sync();
