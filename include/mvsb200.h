@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MVSB200_ABI_VERSION 2
+#define MVSB200_ABI_VERSION 3
 
 #define MVSB200_OK 0
 #define MVSB200_E_INVALID (-1)  /* bad argument / unsupported shape */
@@ -96,10 +96,12 @@ typedef struct {
 /* ref [B,H,W,C]; src: HOST array of S device pointers, src[s] is [B,src_h[s],src_w[s],C];
  * warp [B,S,16] from one of the geometry prologues; depth/interval per depth_mode; temp: device scalar
  * (SOFTMIN only, models/MVSNet/model.py:94-95).
- * out: [B,D,H,W,C] (VARIANCE*, SOFTMIN) or S volumes [B,D,H,W,groups] (GROUPCORR). */
+ * out: [B,D,H,W,C] (VARIANCE*, SOFTMIN) or S volumes [B,D,H,W,groups] (GROUPCORR).
+ * out_amax: optional device scalar, atomically max-ed with max|out| (zero it before the launch); the z-march conv
+ * engine takes it as x_amax so the volume is not read a second time. */
 MVSB200_API int mvsb200_build_cost_volume(const mvsb200_cost_volume_desc *desc, const float *ref, const float *const *src,
                               const float *warp, const float *depth, const float *interval, const float *temp,
-                              float *out, mvsb200_stream_t stream);
+                              float *out, float *out_amax, mvsb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K2: 3-D convolution / transposed convolution with fused BN (scale,bias) + ReLU + skip.
@@ -148,6 +150,26 @@ MVSB200_API int mvsb200_conv3d_tc_pack(const mvsb200_conv3d_desc *desc, const fl
 MVSB200_API int mvsb200_conv3d_tc(const mvsb200_conv3d_desc *desc, const float *x, const float *x2, const float *packed,
                                   const float *scale, const float *bias, const float *skip, float *y, int precision,
                                   mvsb200_stream_t stream);
+
+/* K2 "z-march" engine (k=3 layers, Cin % 8 == 0, Cout == 8 or Cout % 16 == 0, packed weights resident in shared
+ * memory): persistent warp-specialised tcgen05 kernel (kind::f16) that stages every input plane once and keeps the
+ * accumulators of the output planes in flight in TMEM.  Operands are split into two fp16 pieces after a power-of-two
+ * scaling taken from the tensor's abs-max (error-compensated products, fp32-equivalent to ~1e-6; the reference is
+ * fp32: models/MVSNet/module.py:41-48, VisMVSNet/nn_utils.py:123-278, CVP_MVSNet/models/net.py:50-85).
+ *   x_amax / x2_amax : device scalars holding max|x| (max|x2|) -- produced by mvsb200_absmax or by the y_amax output
+ *                      of the kernel that wrote the tensor; they must bound the tensor (a too-small value overflows
+ *                      fp16), a larger value only costs precision;
+ *   y_amax           : optional device scalar, atomically max-ed with max|y| (zero it before the launch).
+ * `packed` holds mvsb200_conv3d_zm_packed_bytes(desc) bytes (16-byte aligned) filled by mvsb200_conv3d_zm_pack from
+ * the tap-major [27][Cin+Cin2][Cout] weights mvsb200_conv3d takes. */
+MVSB200_API int mvsb200_absmax(const float *x, long long n, float *amax, mvsb200_stream_t stream);
+MVSB200_API int mvsb200_conv3d_zm_supported(const mvsb200_conv3d_desc *desc);
+MVSB200_API long long mvsb200_conv3d_zm_packed_bytes(const mvsb200_conv3d_desc *desc);
+MVSB200_API int mvsb200_conv3d_zm_pack(const mvsb200_conv3d_desc *desc, const float *w, void *packed,
+                                       mvsb200_stream_t stream);
+MVSB200_API int mvsb200_conv3d_zm(const mvsb200_conv3d_desc *desc, const float *x, const float *x2, const void *packed,
+                                  const float *scale, const float *bias, const float *skip, float *y,
+                                  const float *x_amax, const float *x2_amax, float *y_amax, mvsb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K3: softmax over D + depth regression + confidence (+ entropy, + probability volume).

@@ -175,8 +175,21 @@ TC_CASES = [
 ]
 
 
-@pytest.mark.parametrize("engine", ["fp32", "tc", "tc_tf32"])
-@pytest.mark.parametrize("cin,cout,k,stride,transposed,dims", CONV_CASES + TC_CASES)
+# shapes that exercise the z-march engine: several (y,x) tiles (7 x 32 / 7 x 16 outputs), several depth segments per
+# tile column and more tiles than CTAs (persistent loop), odd sizes at every edge
+ZM_CASES = [
+    (32, 8, (3, 3, 3), 1, False, (19, 30, 70)),
+    (8, 8, (3, 3, 3), 1, False, (40, 50, 131)),
+    (16, 16, (3, 3, 3), 1, False, (21, 23, 37)),
+    (8, 16, (3, 3, 3), 2, False, (22, 30, 66)),
+    (16, 32, (3, 3, 3), 2, False, (9, 15, 35)),
+    (16, 8, (3, 3, 3), 2, True, (11, 16, 40)),
+    (32, 16, (3, 3, 3), 2, True, (7, 9, 19)),
+]
+
+
+@pytest.mark.parametrize("engine", ["fp32", "zm", "tc", "tc_tf32"])
+@pytest.mark.parametrize("cin,cout,k,stride,transposed,dims", CONV_CASES + TC_CASES + ZM_CASES)
 def test_k2_conv_against_oracle(cin, cout, k, stride, transposed, dims, engine):
     rng = np.random.default_rng(cin * 131 + cout)
     x = rng.standard_normal((cin,) + dims).astype(np.float32)
@@ -189,8 +202,37 @@ def test_k2_conv_against_oracle(cin, cout, k, stride, transposed, dims, engine):
     layer = ops.PackedConv(cu(w), None, stride=stride, transposed=transposed)
     got = from_ndhwc(ops.conv3d(ndhwc(x), layer, engine=engine))
     assert got.shape == want.shape
-    # fp32 FMA chains and the 3xTF32 split agree with the oracle to ~1e-6; plain TF32 rounds operands to 11 bits
+    # fp32 FMA chains, the fp16x2 split (zm) and the 3xTF32 split (tc) agree with the oracle to ~1e-6; plain TF32
+    # rounds operands to 11 bits
     assert rel_linf(got, want) < (3e-3 if engine == "tc_tf32" else 1e-5)
+
+
+@pytest.mark.parametrize("gain", [1e-6, 1.0, 3e5])
+def test_k2_zm_scaling_is_range_safe(gain):
+    """The fp16 split of the z-march engine works on x * 2^k with k from the tracked abs-max: tiny and huge tensors,
+    and tensors with a few large outliers, keep fp32-equivalent accuracy."""
+    rng = np.random.default_rng(11)
+    dims = (6, 16, 40)
+    x = (rng.standard_normal((32,) + dims) * gain).astype(np.float32)
+    x[3, 2, 5, 7] = 4000.0 * gain   # outlier: sets the scale, everything else sits 2^-12 below it
+    w = (rng.standard_normal((8, 32, 3, 3, 3)) / np.sqrt(32 * 27)).astype(np.float32)
+    want = orc.conv3d(x, w, None, 1)
+    got = from_ndhwc(ops.conv3d(ndhwc(x), ops.PackedConv(cu(w), None), engine="zm"))
+    assert rel_linf(got, want) < 1e-5
+    # away from the outlier the error relative to the typical magnitude stays small too
+    err = np.abs(got - want)
+    err[:, 0:5, 2:9, 4:11] = 0
+    assert err.max() < 1e-5 * np.abs(want[:, :, :2]).max()
+
+
+def test_absmax_and_tracked_amax():
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((1, 5, 9, 33, 8)).astype(np.float32)
+    t = cu(x)
+    assert float(ops.absmax(t)) == float(np.abs(x).max())
+    w = (rng.standard_normal((8, 8, 3, 3, 3)) / 15).astype(np.float32)
+    y = ops.conv3d(t, ops.PackedConv(cu(w), None), engine="zm")
+    assert float(y._mvs_amax) == float(y.abs().max())       # the epilogue tracks max|y| for the next layer
 
 
 def test_k2_fused_epilogue_and_concat():
@@ -208,7 +250,7 @@ def test_k2_fused_epilogue_and_concat():
     npy = lambda t: t.detach().cpu().numpy()
     y = orc.bn_relu(conv, npy(bn.weight), npy(bn.bias), npy(bn.running_mean), npy(bn.running_var), bn.eps, relu=False)
     for mode, want in ((L.SKIP_BEFORE_RELU, np.maximum(y + skip, 0)), (L.SKIP_AFTER_RELU, np.maximum(y, 0) + skip)):
-        for engine in ("fp32", "tc"):
+        for engine in ("fp32", "tc", "zm"):
             layer = ops.PackedConv(cu(w), bn, relu=True, skip_mode=mode)
             got = from_ndhwc(ops.conv3d(ndhwc(xa), layer, x2=ndhwc(xb), skip=ndhwc(skip), engine=engine))
             assert rel_linf(got, want) < 1e-5, engine
@@ -219,7 +261,7 @@ def test_k2_stride1_transposed_conv_is_packed_as_flipped_conv():
     x = rng.standard_normal((64, 3, 4, 6)).astype(np.float32)
     w = (rng.standard_normal((64, 32, 3, 3, 3)) / 40).astype(np.float32)
     want = orc.deconv3d(x, w, None, 1, 1, 0)
-    for engine in ("fp32", "tc"):
+    for engine in ("fp32", "tc", "zm"):
         got = from_ndhwc(ops.conv3d(ndhwc(x), ops.PackedConv(cu(w), None, stride=1, transposed=True), engine=engine))
         assert rel_linf(got, want) < 2e-5, engine   # K = 64*27 = 1728 products per output
 

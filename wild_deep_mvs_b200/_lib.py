@@ -15,7 +15,7 @@ DEPTH_VALUES, DEPTH_VOLUME, DEPTH_START, DEPTH_START_MAP = 0, 1, 2, 3
 SKIP_NONE, SKIP_BEFORE_RELU, SKIP_AFTER_RELU = 0, 1, 2
 CONF_NONE, CONF_SUM4, CONF_WINDOW = 0, 1, 2
 PRECISION_3XTF32, PRECISION_TF32 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Mvsb200Error(RuntimeError):
@@ -49,13 +49,18 @@ SIGNATURES = {
     "mvsb200_device_info": (_i, [ctypes.POINTER(_i)] * 3),
     "mvsb200_mvs_relative_proj": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "mvsb200_vis_homography_params": (_i, [_vp, _vp, ctypes.c_float, _vp, _i, _i, _vp]),
-    "mvsb200_build_cost_volume": (_i, [ctypes.POINTER(CostVolumeDesc), _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvsb200_build_cost_volume": (_i, [ctypes.POINTER(CostVolumeDesc), _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvsb200_conv3d_out_shape": (_i, [ctypes.POINTER(Conv3dDesc)] + [ctypes.POINTER(_i)] * 3),
     "mvsb200_conv3d": (_i, [ctypes.POINTER(Conv3dDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvsb200_conv3d_tc_supported": (_i, [ctypes.POINTER(Conv3dDesc)]),
     "mvsb200_conv3d_tc_packed_floats": (ctypes.c_longlong, [ctypes.POINTER(Conv3dDesc)]),
     "mvsb200_conv3d_tc_pack": (_i, [ctypes.POINTER(Conv3dDesc), _vp, _vp, _vp]),
     "mvsb200_conv3d_tc": (_i, [ctypes.POINTER(Conv3dDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "mvsb200_absmax": (_i, [_vp, ctypes.c_longlong, _vp, _vp]),
+    "mvsb200_conv3d_zm_supported": (_i, [ctypes.POINTER(Conv3dDesc)]),
+    "mvsb200_conv3d_zm_packed_bytes": (ctypes.c_longlong, [ctypes.POINTER(Conv3dDesc)]),
+    "mvsb200_conv3d_zm_pack": (_i, [ctypes.POINTER(Conv3dDesc), _vp, _vp, _vp]),
+    "mvsb200_conv3d_zm": (_i, [ctypes.POINTER(Conv3dDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvsb200_depth_regress": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "mvsb200_vis_fuse": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }

@@ -29,6 +29,7 @@ struct K1Params {
     const float *interval;
     const float *temp;
     float *out;
+    float *out_amax;
     long long out_view_stride;
     int B, S, D, H, W, depth_mode;
 };
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
         sum_exp[k] = 0.f;
     }
     const float temp = (AGG == MVSB200_AGG_SOFTMIN) ? __ldg(p.temp) : 0.f;
+    float vmax = 0.f;   // max |stored value| of this thread (abs-max tracking for the z-march conv engine)
 
     for (int s = 0; s < p.S; s++) {
         const float *wp = s_warp + s * 16;
@@ -225,18 +227,19 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
                 g += r.y * w.y;
                 g += r.z * w.z;
                 g += r.w * w.w;
-                if (active && d0 + k < p.D)
+                if (active && d0 + k < p.D) {
+                    vmax = fmaxf(vmax, fabsf(g));
                     __stcs(p.out + s * p.out_view_stride + (((long long)b * p.D + d0 + k) * HW + pix) * LPV + sub, g);
+                }
             }
         }
     }
 
-    if (AGG == MVSB200_AGG_GROUPCORR || !active) return;
     const float V = (float)(p.S + 1), V2 = V * V;
     const float rV = 1.f / V, rV2 = 1.f / V2;
 #pragma unroll
     for (int k = 0; k < K1_DCH; k++) {
-        if (d0 + k >= p.D) break;
+        if (AGG == MVSB200_AGG_GROUPCORR || !active || d0 + k >= p.D) break;
         float4 o;
         if (AGG == MVSB200_AGG_VARIANCE) {
             o.x = div_by(acc2[k].x, V, rV) - div_by(acc1[k].x * acc1[k].x, V2, rV2);
@@ -255,7 +258,13 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
             o.x = div_by(acc1[k].x, den, rden); o.y = div_by(acc1[k].y, den, rden);
             o.z = div_by(acc1[k].z, den, rden); o.w = div_by(acc1[k].w, den, rden);
         }
+        vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
         st4_stream(p.out + (((long long)b * p.D + d0 + k) * HW + pix) * C + sub * 4, o);
+    }
+    if (p.out_amax) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, m));
+        if ((threadIdx.x & 31) == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned int *>(p.out_amax), __float_as_uint(vmax));
     }
 }
 
@@ -287,7 +296,7 @@ using namespace mvsb200;
 
 extern "C" int mvsb200_build_cost_volume(const mvsb200_cost_volume_desc *d, const float *ref,
                                          const float *const *src, const float *warp, const float *depth,
-                                         const float *interval, const float *temp, float *out,
+                                         const float *interval, const float *temp, float *out, float *out_amax,
                                          mvsb200_stream_t stream)
 {
     MVSB200_REQUIRE(d && ref && src && warp && depth && out, "build_cost_volume: null pointer");
@@ -311,7 +320,7 @@ extern "C" int mvsb200_build_cost_volume(const mvsb200_cost_volume_desc *d, cons
         p.src_h[s] = d->src_h[s];
         p.src_w[s] = d->src_w[s];
     }
-    p.warp = warp; p.depth = depth; p.interval = interval; p.temp = temp; p.out = out;
+    p.warp = warp; p.depth = depth; p.interval = interval; p.temp = temp; p.out = out; p.out_amax = out_amax;
     p.out_view_stride = d->out_view_stride;
     p.B = d->B; p.S = d->S; p.D = d->D; p.H = d->H; p.W = d->W; p.depth_mode = d->depth_mode;
     const long long HW = (long long)d->H * d->W;

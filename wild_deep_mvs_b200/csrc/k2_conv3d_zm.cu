@@ -1,0 +1,703 @@
+// K2 "z-march" engine: 3x3x3 convolution / stride-2 convolution / stride-2 transposed convolution over
+// channels-last volumes on the 5th-generation tensor cores (tcgen05.mma kind::f16, TMEM accumulators), as a
+// persistent, warp-specialised kernel that walks a (y,x) tile column along the depth axis.
+//
+// Why another engine (see profiles/ncu_r1f.md): the tile-at-a-time kernel of k2_conv3d_tc.cu is bound by the shared
+// memory pipe -- tensor-core operand reads (62 % of peak) plus the staging stores (18 %) -- not by math or HBM.
+// This engine attacks exactly those bytes:
+//   * every input plane of a tile column is staged ONCE and feeds the three output planes it touches (the old
+//     kernel re-staged each plane twice as z halo), accumulators of the planes in flight live in TMEM;
+//   * operands are split into two fp16 pieces instead of two tf32 pieces (x*s = h + l, |l| <= 2^-11 |h|, s a power
+//     of two taken from the tensor's tracked abs-max so h never overflows): half the operand bytes per element and
+//     twice the MMA rate.  The two pieces of the activation are the two K core matrices of ONE kind::f16 MMA
+//     (K = 16 = 8 channels x {h, l}); the weight pieces sit on the N axis:
+//         k-plane 0 (x_h):  [ w_h | w_l ]        k-plane 1 (x_l):  [ w_h | 0 ]
+//     so one MMA yields x_h*w_h + x_l*w_h (columns "hl=0") and x_h*w_l (columns "hl=1"); the dropped x_l*w_l term is
+//     2^-22 relative.  Products are exact in the fp32 accumulator: the result is fp32-equivalent (~1e-6).
+//   * producer warps (global -> registers -> fp16 split -> shared), one MMA-issuing thread and epilogue warps
+//     (TMEM -> registers -> BN/ReLU/skip -> global) run concurrently through mbarrier pipelines; the packed weights
+//     of the layer stay resident in shared memory for the lifetime of the CTA.
+// As in k2_conv3d_tc.cu a (dz,dy) tap is a shifted 128-row window of the staged plane (descriptor start address) and
+// the dx taps are folded into the MMA N dimension, re-aligned in the epilogue.
+//
+// Accumulator columns of one 128-row tile: ((xs * 2) + hl) * CT + co.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace mvsb200 {
+
+using namespace umma;
+
+constexpr int ZM_S1 = 0, ZM_S2 = 1, ZM_DECONV = 2;
+constexpr int ZM_EPI_WARPS = 4, ZM_PROD_WARPS = 8;
+constexpr int ZM_THREADS = (ZM_EPI_WARPS + ZM_PROD_WARPS + 1) * 32;   // 416
+constexpr int ZM_PROD_GROUP = 128;                                     // producer threads working on one stage
+constexpr int ZM_HEADER_HALVES = 8;                                    // 16-byte header in front of the packed weights
+
+template <int MODE, int CT> struct ZmCfg {
+    static constexpr int NXS = (MODE == ZM_S1) ? 3 : 2;       // x taps folded into N
+    static constexpr int NC = NXS * 2 * CT;                   // accumulator columns per 128-row tile (MMA N)
+    static constexpr int HALO = (MODE == ZM_S1) ? 2 : 1;
+    static constexpr int MT = (CT == 8) ? 2 : 1;              // 128-row MMA tiles per plane
+    static constexpr int TY = 7, TX = (CT == 8) ? 32 : 16;
+    static constexpr int EY = TY + HALO, EX = TX + HALO;
+    static constexpr int ROWS = EY * EX;                      // staged rows per (plane, chunk, sub-grid)
+    static constexpr int R_NEED = MT * 128 + HALO * EX;       // rows the shifted windows may touch
+    static constexpr int RA = ((R_NEED > ROWS ? R_NEED : ROWS) + 7) / 8 * 8;
+    static constexpr int NPF = (ROWS + ZM_PROD_GROUP - 1) / ZM_PROD_GROUP;   // rows per producer thread per stage
+    static constexpr int NSUB = (MODE == ZM_S2) ? 4 : 1;      // (py,px) parity sub-grids staged per plane
+    static constexpr int NPXL = (MODE == ZM_S2) ? 2 : 1;      // x-parity weight variants resident per CTA
+    static constexpr int NACC = (512 / (MT * NC) >= 8) ? 8 : 4;   // accumulator planes in TMEM
+    static constexpr int ACC_COLS = MT * NC;
+    static constexpr int XROWS = MT * 128 + 8;
+    static constexpr int STAGE_BYTES = 2 * RA * 16;
+    static constexpr int WBLOCK_BYTES = 2 * NC * 16;          // one (chunk, px, kz, ky) weight block
+    static constexpr int X_BYTES = (NXS - 1) * (CT / 4) * XROWS * 16;
+    static_assert(TY * EX <= MT * 128, "plane tile does not fit the MMA row tiles");
+    static_assert(NACC * ACC_COLS <= 512, "accumulators exceed TMEM");
+    static_assert(NC % 16 == 0 && NC <= 256, "invalid MMA N");
+};
+
+struct ZmParams {
+    const float *x, *x2, *scale, *bias, *skip;
+    const __half *wp;            // packed weights of this layer (header + blocks)
+    float *y;
+    const float *x_amax, *x2_amax;
+    float *y_amax;
+    int B, D, H, W, Do, Ho, Wo;
+    int Cin1, Cin2, Cout;
+    int relu, skip_mode;
+    int tiles_x, tiles_y, nseg, zseg, ntiles, nstages;
+};
+
+// ---- small PTX helpers local to this engine -------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N)
+{
+    // kind::f16: [4,6) D format 1 = f32 | [7,10) A format 0 = f16 | [10,13) B format 0 = f16 | N >> 3 | M >> 4
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Power-of-two scale that maps a tensor with the given abs-max into [2^13, 2^14): h = fp16(x*s) cannot overflow and
+// the absolute rounding floor of the l piece (2^-25) is 2^-38 of the abs-max.  Returns s; *inv = 1/s.
+__device__ __forceinline__ float pow2_scale(float amax, float *inv)
+{
+    if (!(amax > 0.f) || !(amax < 3.0e38f)) {
+        *inv = 1.f;
+        return 1.f;
+    }
+    int e = (int)((__float_as_uint(amax) >> 23) & 0xffu) - 127;   // floor(log2(amax)) for normal numbers
+    e = max(-100, min(100, e));
+    *inv = __uint_as_float((uint32_t)(127 + e - 13) << 23);
+    return __uint_as_float((uint32_t)(127 + 13 - e) << 23);
+}
+
+// z-march tables.  Local input plane p of a segment -> (local output plane q, z tap kz) contributions.
+//   S1      z_in = zb - 1 + p      q = p - kz                       kz = 0,1,2
+//   S2      z_in = 2 zb - 1 + p    p even: (q = p/2, kz 0), (q = p/2 - 1, kz 2);  p odd: (q = (p-1)/2, kz 1)
+//   DECONV  z_in = zb + p          (q = 2p - 1, kz 0), (q = 2p, kz 1), (q = 2p + 1, kz 2)     [gather form]
+template <int MODE> __device__ __forceinline__ int zm_zin(int zb, int p)
+{
+    return MODE == ZM_S1 ? zb - 1 + p : (MODE == ZM_S2 ? 2 * zb - 1 + p : zb + p);
+}
+template <int MODE> __device__ __forceinline__ int zm_ncontrib(int p) { return MODE == ZM_S2 ? ((p & 1) ? 1 : 2) : 3; }
+template <int MODE> __device__ __forceinline__ void zm_contrib(int p, int j, int &q, int &kz)
+{
+    if (MODE == ZM_S1) { kz = 2 - j; q = p - kz; }                    // finishing plane first
+    else if (MODE == ZM_S2) {
+        if (p & 1) { kz = 1; q = (p - 1) >> 1; }
+        else if (j == 0) { kz = 2; q = (p >> 1) - 1; }
+        else { kz = 0; q = p >> 1; }
+    } else { kz = j; q = 2 * p - 1 + j; }
+}
+// planes of one segment: nq output planes -> number of input planes walked
+template <int MODE> __device__ __forceinline__ int zm_nplanes(int nq) { return MODE == ZM_S1 ? nq + 2 : (MODE == ZM_S2 ? 2 * nq + 1 : nq / 2 + 1); }
+// output planes that are complete once input plane p has been consumed: [qlo, qhi)
+template <int MODE> __device__ __forceinline__ void zm_complete(int p, int nq, int &qlo, int &qhi)
+{
+    if (MODE == ZM_S1) { qlo = p - 2; qhi = p - 1; }
+    else if (MODE == ZM_S2) { if (p & 1) { qlo = qhi = 0; } else { qlo = (p >> 1) - 1; qhi = p >> 1; } }
+    else { qlo = 2 * p - 1; qhi = 2 * p + 1; }
+    qlo = max(qlo, 0);
+    qhi = min(qhi, nq);
+}
+// y-dimension tap options of a staged block: variant v (S1: 0; S2: parity of the staged sub-grid; DECONV: parity of the
+// output class) -> option j = (filter index, row shift)
+__host__ __device__ constexpr int zm_dim_opts(int mode, int v) { return mode == ZM_S1 ? 3 : (mode == ZM_S2 ? (v == 0 ? 2 : 1) : (v == 0 ? 1 : 2)); }
+__host__ __device__ constexpr int zm_dim_k(int mode, int v, int j)
+{
+    return mode == ZM_S1 ? j : (mode == ZM_S2 ? (v == 0 ? 2 * j : 1) : (v == 0 ? 1 : (j == 0 ? 2 : 0)));
+}
+__host__ __device__ constexpr int zm_dim_shift(int mode, int v, int j) { return mode == ZM_S1 ? j : (mode == ZM_S2 ? (v == 0 ? j : 0) : (v == 0 ? 0 : j)); }
+
+struct ZmTile {
+    int b, zb, nq, y0, x0, cls;
+};
+
+template <int MODE, int CT> __device__ __forceinline__ ZmTile zm_decode(const ZmParams &p, int tile)
+{
+    using T = ZmCfg<MODE, CT>;
+    ZmTile t;
+    t.cls = 0;
+    if (MODE == ZM_DECONV) { t.cls = tile & 3; tile >>= 2; }
+    const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+    const int ty = tile % p.tiles_y; tile /= p.tiles_y;
+    const int sg = tile % p.nseg;
+    t.b = tile / p.nseg;
+    t.x0 = tx * T::TX;
+    t.y0 = ty * T::TY;
+    // segments are counted in output planes (S1, S2) or input planes (DECONV)
+    const int ztot = (MODE == ZM_DECONV) ? p.D : p.Do;
+    t.zb = sg * p.zseg;
+    const int n = min(p.zseg, ztot - t.zb);
+    t.nq = (MODE == ZM_DECONV) ? 2 * n : n;
+    return t;
+}
+
+template <int MODE, int CT>
+__global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmParams p)
+{
+    using T = ZmCfg<MODE, CT>;
+    constexpr int NC = T::NC, RA = T::RA, MT = T::MT, NACC = T::NACC, EX = T::EX;
+    constexpr int MAXST = 8;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_full[MAXST], s_empty[MAXST], s_accfull[8], s_accempty[8], s_wbar;
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nb = blockIdx.y;
+    const int nch = (p.Cin1 + p.Cin2) >> 3;
+    const int NST = p.nstages;
+    const int wblocks = T::NPXL * nch * 9;
+    unsigned char *sW = smem_raw;
+    unsigned char *sA = sW + (size_t)wblocks * T::WBLOCK_BYTES;
+    float4 *sX = reinterpret_cast<float4 *>(sA + (size_t)NST * T::STAGE_BYTES);
+
+    if (tid == 0) {
+        for (int i = 0; i < NST; i++) { mbar_init(smem_u32(&s_full[i]), 4); mbar_init(smem_u32(&s_empty[i]), 1); }
+        for (int i = 0; i < NACC; i++) { mbar_init(smem_u32(&s_accfull[i]), 1); mbar_init(smem_u32(&s_accempty[i]), ZM_EPI_WARPS); }
+        mbar_init(smem_u32(&s_wbar), ZM_PROD_WARPS);
+        fence_mbar_init();
+    }
+    if (warp == ZM_EPI_WARPS + ZM_PROD_WARPS) tmem_alloc(smem_u32(&s_tmem), 512);
+    // staged rows beyond the plane tile are only ever read by discarded GEMM rows; give them a defined value once
+    for (int i = tid; i < NST * T::STAGE_BYTES / 16; i += ZM_THREADS) reinterpret_cast<uint4 *>(sA)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = s_tmem;
+
+    // operand scales
+    float amax = __ldg(p.x_amax);
+    if (p.x2) amax = fmaxf(amax, __ldg(p.x2_amax));
+    float inv_sx;
+    const float sx = pow2_scale(amax, &inv_sx);
+
+    if (warp < ZM_EPI_WARPS) {
+        // =================================== epilogue warps ===================================
+        const float w_inv = __ldg(reinterpret_cast<const float *>(p.wp) + 1);   // header: {w_scale, w_inv_scale, -, -}
+        const float unscale = inv_sx * w_inv;
+        constexpr int C4 = CT / 4;
+        const int ncol = min(CT, p.Cout - nb * CT), co0 = nb * CT;
+        float4 sc[C4], bi[C4];
+#pragma unroll
+        for (int c4 = 0; c4 < C4; c4++) {
+            sc[c4] = make_float4(unscale, unscale, unscale, unscale);
+            bi[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c4 * 4 < ncol) {
+                if (p.scale) { const float4 s4 = ldg4(p.scale + co0 + c4 * 4); sc[c4].x *= s4.x; sc[c4].y *= s4.y; sc[c4].z *= s4.z; sc[c4].w *= s4.w; }
+                if (p.bias) bi[c4] = ldg4(p.bias + co0 + c4 * 4);
+            }
+        }
+        float vmax = 0.f;
+        int qg = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            const ZmTile t = zm_decode<MODE, CT>(p, tile);
+            const int ry = (t.cls >> 1) & 1, rx = t.cls & 1;
+            for (int q = 0; q < t.nq; q++, qg++) {
+                const int slot = qg % NACC;
+                mbar_wait(smem_u32(&s_accfull[slot]), (uint32_t)(qg / NACC) & 1u);
+                tc_fence_after_sync();
+                float r0[MT][CT];
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const int xrow = mt * 128 + warp * 32 + lane;
+#pragma unroll
+                    for (int xs = 0; xs < T::NXS; xs++) {
+                        float v[2 * CT];
+                        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + slot * T::ACC_COLS + mt * NC + xs * 2 * CT;
+#pragma unroll
+                        for (int j = 0; j < 2 * CT; j += 16) tmem_ld16(taddr + j, v + j);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < CT; k++) v[k] += v[CT + k];
+                        if (xs == 0) {
+#pragma unroll
+                            for (int k = 0; k < CT; k++) r0[mt][k] = v[k];
+                        } else {
+#pragma unroll
+                            for (int c4 = 0; c4 < C4; c4++)
+                                sX[((xs - 1) * C4 + c4) * T::XROWS + xrow] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+                        }
+                    }
+                }
+                // the accumulator plane is in registers / shared memory: hand the TMEM slot back to the MMA thread
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&s_accempty[slot]));
+                named_bar_sync(1, ZM_EPI_WARPS * 32);
+                int oz = t.zb + q;
+                if (MODE == ZM_DECONV) oz = 2 * t.zb + q;
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const int pr = mt * 128 + warp * 32 + lane;
+                    const int oy_l = pr / EX, ox_l = pr % EX;
+                    int oy = t.y0 + oy_l, ox = t.x0 + ox_l;
+                    bool ok = oy_l < T::TY && ox_l < T::TX;
+                    if (MODE == ZM_DECONV) {
+                        ok = ok && oy < p.H && ox < p.W;
+                        oy = 2 * oy + ry; ox = 2 * ox + rx;
+                    }
+                    ok = ok && oz < p.Do && oy < p.Ho && ox < p.Wo;
+                    if (!ok) continue;
+                    const long long o = ((((long long)t.b * p.Do + oz) * p.Ho + oy) * p.Wo + ox) * p.Cout + co0;
+#pragma unroll
+                    for (int c4 = 0; c4 < C4; c4++) {
+                        if (c4 * 4 >= ncol) break;
+                        float r[4] = {r0[mt][c4 * 4], r0[mt][c4 * 4 + 1], r0[mt][c4 * 4 + 2], r0[mt][c4 * 4 + 3]};
+#pragma unroll
+                        for (int xs = 1; xs < T::NXS; xs++) {
+                            const float4 nbv = sX[((xs - 1) * C4 + c4) * T::XROWS + pr + xs];
+                            r[0] += nbv.x; r[1] += nbv.y; r[2] += nbv.z; r[3] += nbv.w;
+                        }
+                        r[0] = fmaf(r[0], sc[c4].x, bi[c4].x); r[1] = fmaf(r[1], sc[c4].y, bi[c4].y);
+                        r[2] = fmaf(r[2], sc[c4].z, bi[c4].z); r[3] = fmaf(r[3], sc[c4].w, bi[c4].w);
+                        float4 sk = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.skip_mode != MVSB200_SKIP_NONE) sk = ldg4(p.skip + o + c4 * 4);
+                        if (p.skip_mode == MVSB200_SKIP_BEFORE_RELU) { r[0] += sk.x; r[1] += sk.y; r[2] += sk.z; r[3] += sk.w; }
+                        if (p.relu) { r[0] = fmaxf(r[0], 0.f); r[1] = fmaxf(r[1], 0.f); r[2] = fmaxf(r[2], 0.f); r[3] = fmaxf(r[3], 0.f); }
+                        if (p.skip_mode == MVSB200_SKIP_AFTER_RELU) { r[0] += sk.x; r[1] += sk.y; r[2] += sk.z; r[3] += sk.w; }
+                        vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(r[0]), fabsf(r[1]))), fmaxf(fabsf(r[2]), fabsf(r[3])));
+                        st4(p.y + o + c4 * 4, make_float4(r[0], r[1], r[2], r[3]));
+                    }
+                }
+                named_bar_sync(1, ZM_EPI_WARPS * 32);   // sX is rewritten by the next plane
+            }
+        }
+        if (p.y_amax) {
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, m));
+            if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned int *>(p.y_amax), __float_as_uint(vmax));
+        }
+    } else if (warp < ZM_EPI_WARPS + ZM_PROD_WARPS) {
+        // =================================== producer warps ===================================
+        const int ptid = tid - ZM_EPI_WARPS * 32;
+        const int group = ptid / ZM_PROD_GROUP, gt = ptid % ZM_PROD_GROUP;
+        // resident weights of this CTA: S1 one variant, S2 both x-parity variants, DECONV the variant of the CTA's
+        // output class (the grid is a multiple of 4 wide and the class is the fastest tile index, so every tile of a
+        // CTA has class blockIdx.x % 4)
+        const size_t wblock_halves = T::WBLOCK_BYTES / 2;
+        const __half *wsrc = p.wp + ZM_HEADER_HALVES + (size_t)nb * ((MODE == ZM_S1 ? 1 : 2) * nch * 9) * wblock_halves;
+        if (MODE == ZM_DECONV) wsrc += (size_t)(blockIdx.x & 1) * (nch * 9) * wblock_halves;
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(wsrc);
+            uint4 *dst = reinterpret_cast<uint4 *>(sW);
+            const int n16 = wblocks * T::WBLOCK_BYTES / 16;
+            for (int i = ptid; i < n16; i += ZM_PROD_WARPS * 32) dst[i] = __ldg(src + i);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_wbar));
+        }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            const ZmTile t = zm_decode<MODE, CT>(p, tile);
+            const int np = zm_nplanes<MODE>(t.nq);
+            for (int pl = 0; pl < np; pl++) {
+                const int gz = zm_zin<MODE>(t.zb, pl);
+                if ((unsigned)gz >= (unsigned)p.D) continue;   // an all-zero plane contributes nothing: no stage at all
+                for (int c = 0; c < nch; c++) {
+                    const float *src;
+                    int cs, cstride;
+                    if (c * 8 < p.Cin1) { src = p.x; cs = c * 8; cstride = p.Cin1; }
+                    else { src = p.x2; cs = c * 8 - p.Cin1; cstride = p.Cin2; }
+                    const float *plane = src + ((long long)t.b * p.D + gz) * p.H * p.W * cstride + cs;
+                    for (int s = 0; s < T::NSUB; s++, it++) {
+                        if ((it & 1) != group) continue;
+                        const int py = (s >> 1) & 1, px = s & 1;
+                        float4 va[T::NPF], vb[T::NPF];
+#pragma unroll
+                        for (int k = 0; k < T::NPF; k++) {
+                            const int i = gt + k * ZM_PROD_GROUP;
+                            const int ly = i / EX, lx = i % EX;
+                            int gy, gx;
+                            if (MODE == ZM_S1) { gy = t.y0 - 1 + ly; gx = t.x0 - 1 + lx; }
+                            else if (MODE == ZM_S2) { gy = 2 * (t.y0 + ly) - 1 + py; gx = 2 * (t.x0 + lx) - 1 + px; }
+                            else { gy = t.y0 + ly; gx = t.x0 + lx; }
+                            va[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            vb[k] = va[k];
+                            if (i < T::ROWS && (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W) {
+                                const float *q = plane + ((long long)gy * p.W + gx) * cstride;
+                                va[k] = ldg4(q);
+                                vb[k] = ldg4(q + 4);
+                            }
+                        }
+                        const int slot = it % NST;
+                        mbar_wait(smem_u32(&s_empty[slot]), ((uint32_t)(it / NST) & 1u) ^ 1u);
+                        uint4 *dst = reinterpret_cast<uint4 *>(sA + (size_t)slot * T::STAGE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < T::NPF; k++) {
+                            const int i = gt + k * ZM_PROD_GROUP;
+                            if (i < T::ROWS) {
+                                const float f[8] = {va[k].x * sx, va[k].y * sx, va[k].z * sx, va[k].w * sx,
+                                                    vb[k].x * sx, vb[k].y * sx, vb[k].z * sx, vb[k].w * sx};
+                                uint32_t hw[4], lw[4];
+#pragma unroll
+                                for (int e = 0; e < 4; e++) {
+                                    const __half2 h = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+                                    const float2 hf = __half22float2(h);
+                                    const __half2 l = __floats2half2_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+                                    hw[e] = *reinterpret_cast<const uint32_t *>(&h);
+                                    lw[e] = *reinterpret_cast<const uint32_t *>(&l);
+                                }
+                                dst[i] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                                dst[RA + i] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                            }
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&s_full[slot]));
+                    }
+                }
+            }
+        }
+    } else {
+        // =================================== MMA issuer ===================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_f16(128, NC);
+            mbar_wait(smem_u32(&s_wbar), 0);
+            tc_fence_after_sync();
+            const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
+            int it = 0, qbase = 0;
+            uint32_t started = 0;   // bit per accumulator slot: the plane in it has received its first MMA
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                const ZmTile t = zm_decode<MODE, CT>(p, tile);
+                const int np = zm_nplanes<MODE>(t.nq);
+                const int vy_cls = (t.cls >> 1) & 1;
+                for (int pl = 0; pl < np; pl++) {
+                    const int gz = zm_zin<MODE>(t.zb, pl);
+                    if ((unsigned)gz < (unsigned)p.D) {
+                        for (int c = 0; c < nch; c++) {
+                            for (int s = 0; s < T::NSUB; s++, it++) {
+                                const int slot = it % NST;
+                                mbar_wait(smem_u32(&s_full[slot]), (uint32_t)(it / NST) & 1u);
+                                tc_fence_after_sync();
+                                const int py = (s >> 1) & 1, px = s & 1;
+                                const int vy = (MODE == ZM_S2) ? py : vy_cls;
+                                const int ny = zm_dim_opts(MODE, vy);
+                                const uint64_t adesc = smem_desc(sA_u + slot * T::STAGE_BYTES, RA * 16, 128);
+                                const int ncn = zm_ncontrib<MODE>(pl);
+                                for (int j = 0; j < ncn; j++) {
+                                    int q, kz;
+                                    zm_contrib<MODE>(pl, j, q, kz);
+                                    if (q < 0 || q >= t.nq) continue;
+                                    const int qg = qbase + q, aslot = qg % NACC;
+                                    if (!(started >> aslot & 1u)) {
+                                        mbar_wait(smem_u32(&s_accempty[aslot]), ((uint32_t)(qg / NACC) & 1u) ^ 1u);
+                                        tc_fence_after_sync();
+                                    }
+                                    for (int jy = 0; jy < ny; jy++) {
+                                        const int ky = zm_dim_k(MODE, vy, jy);
+                                        const int shift = zm_dim_shift(MODE, vy, jy) * EX;
+                                        const int wb = (((MODE == ZM_S2 ? px : 0) * nch + c) * 3 + kz) * 3 + ky;
+                                        const uint64_t bdesc = smem_desc(sW_u + wb * T::WBLOCK_BYTES, NC * 16, 128);
+                                        const uint32_t acc = (started >> aslot & 1u) ? 1u : 0u;
+#pragma unroll
+                                        for (int mt = 0; mt < MT; mt++)
+                                            mma_f16(tmem + aslot * T::ACC_COLS + mt * NC, adesc + (uint64_t)(mt * 128 + shift), bdesc, idesc, acc);
+                                        started |= 1u << aslot;
+                                    }
+                                }
+                                mma_commit(smem_u32(&s_empty[slot]));
+                            }
+                        }
+                    }
+                    int qlo, qhi;
+                    zm_complete<MODE>(pl, t.nq, qlo, qhi);
+                    for (int q = qlo; q < qhi; q++) {
+                        const int aslot = (qbase + q) % NACC;
+                        mma_commit(smem_u32(&s_accfull[aslot]));
+                        started &= ~(1u << aslot);
+                    }
+                }
+                qbase += t.nq;
+            }
+        }
+        __syncwarp();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == ZM_EPI_WARPS + ZM_PROD_WARPS) tmem_dealloc(tmem, 512);
+}
+
+// ---- weight packing ----------------------------------------------------------------------------------------------
+// layout: header {w_scale, w_inv_scale, 0, 0} (fp32, 16 bytes) then
+//   [N block][x-parity variant (S2: px, DECONV: rx; S1: single)][chunk][kz][ky][k-plane 2][NC][8 halves]
+struct ZmPackParams {
+    const float *w;
+    __half *wp;
+    int Cin, Cout, nch, mode, CT, NC, nvar;
+};
+
+__global__ void k2_zm_absmax_kernel(const float *x, long long n, float *out)
+{
+    float m = 0.f;
+    const long long n4 = n >> 2;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x4 + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(__ldg(x + i)));
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int *>(out), __float_as_uint(m));
+}
+
+__global__ void k2_zm_header_kernel(float *hdr)
+{
+    // hdr[0] holds the abs-max of the weights on entry
+    float inv;
+    const float s = pow2_scale(hdr[0], &inv);
+    hdr[0] = s; hdr[1] = inv; hdr[2] = 0.f; hdr[3] = 0.f;
+}
+
+__host__ __device__ constexpr int zm_kx_of(int mode, int var, int xs)
+{
+    // filter x index multiplied with the rows shifted by xs, or -1
+    return mode == ZM_S1 ? xs
+         : mode == ZM_S2 ? (var == 0 ? (xs == 0 ? 0 : 2) : (xs == 0 ? 1 : -1))
+                         : (var == 0 ? (xs == 0 ? 1 : -1) : (xs == 0 ? 2 : 0));
+}
+
+__global__ void k2_zm_pack_kernel(const ZmPackParams p)
+{
+    // one block per (nb, var, c, kz, ky); threads over (k-plane, column, element)
+    int id = blockIdx.x;
+    const int ky = id % 3; id /= 3;
+    const int kz = id % 3; id /= 3;
+    const int c = id % p.nch; id /= p.nch;
+    const int var = id % p.nvar;
+    const int nb = id / p.nvar;
+    const float s = reinterpret_cast<const float *>(p.wp)[0];
+    __half *dst = p.wp + ZM_HEADER_HALVES + (size_t)blockIdx.x * (2 * p.NC * 8);
+    for (int i = threadIdx.x; i < 2 * p.NC * 8; i += blockDim.x) {
+        const int e = i & 7;
+        int r = i >> 3;
+        const int col = r % p.NC;
+        const int kp = r / p.NC;
+        const int co_l = col % p.CT, g = col / p.CT;
+        const int hl = g & 1, xs = g >> 1;
+        const int kx = zm_kx_of(p.mode, var, xs);
+        const int ci = c * 8 + e, co = nb * p.CT + co_l;
+        float val = 0.f;
+        if (kx >= 0 && co < p.Cout) val = p.w[((size_t)((kz * 3 + ky) * 3 + kx) * p.Cin + ci) * p.Cout + co] * s;
+        const __half h = __float2half_rn(val);
+        const __half l = __float2half_rn(val - __half2float(h));
+        dst[i] = (kp == 0) ? (hl ? l : h) : (hl ? __float2half_rn(0.f) : h);
+    }
+}
+
+static int zm_mode(const mvsb200_conv3d_desc *d) { return d->transposed ? ZM_DECONV : (d->stride == 2 ? ZM_S2 : ZM_S1); }
+static int zm_ct(const mvsb200_conv3d_desc *d) { return d->Cout == 8 ? 8 : 16; }
+static int zm_nvar(int mode) { return mode == ZM_S1 ? 1 : 2; }
+
+template <int MODE, int CT> static size_t zm_smem_bytes(int nch, int nst)
+{
+    using T = ZmCfg<MODE, CT>;
+    return (size_t)T::NPXL * nch * 9 * T::WBLOCK_BYTES + (size_t)nst * T::STAGE_BYTES + T::X_BYTES;
+}
+
+// number of pipeline stages that fit next to the resident weights (0: the layer does not fit this engine)
+template <int MODE, int CT> static int zm_stages(int nch)
+{
+    for (int nst = 8; nst >= 3; nst--)
+        if (zm_smem_bytes<MODE, CT>(nch, nst) + 2048 <= 227 * 1024) return nst;
+    return 0;
+}
+
+static int zm_stages_for(int mode, int ct, int nch)
+{
+    if (mode == ZM_S1) return ct == 8 ? zm_stages<ZM_S1, 8>(nch) : zm_stages<ZM_S1, 16>(nch);
+    if (mode == ZM_S2) return ct == 8 ? zm_stages<ZM_S2, 8>(nch) : zm_stages<ZM_S2, 16>(nch);
+    return ct == 8 ? zm_stages<ZM_DECONV, 8>(nch) : zm_stages<ZM_DECONV, 16>(nch);
+}
+
+static bool zm_shape_ok(const mvsb200_conv3d_desc *d)
+{
+    const int cin = d->Cin + d->Cin2;
+    if (!(d->kd == 3 && d->kh == 3 && d->kw == 3 && d->Cin % 8 == 0 && d->Cin2 % 8 == 0 && cin >= 8)) return false;
+    if (!(d->Cout == 8 || (d->Cout % 16 == 0 && d->Cout <= 256))) return false;
+    if (!((d->stride == 1 && !d->transposed) || d->stride == 2)) return false;
+    return zm_stages_for(zm_mode(d), zm_ct(d), cin / 8) > 0;
+}
+
+template <int MODE, int CT>
+static int launch_zm(ZmParams p, int sm_count, cudaStream_t st)
+{
+    using T = ZmCfg<MODE, CT>;
+    const int nch = (p.Cin1 + p.Cin2) / 8;
+    p.nstages = zm_stages<MODE, CT>(nch);
+    const size_t smem = zm_smem_bytes<MODE, CT>(nch, p.nstages);
+    const int nzt = (MODE == ZM_DECONV) ? p.D : p.Do, ny = (MODE == ZM_DECONV) ? p.H : p.Ho, nx = (MODE == ZM_DECONV) ? p.W : p.Wo;
+    p.tiles_y = (ny + T::TY - 1) / T::TY;
+    p.tiles_x = (nx + T::TX - 1) / T::TX;
+    const int nblocks = (p.Cout + CT - 1) / CT;
+    const int classes = (MODE == ZM_DECONV) ? 4 : 1;
+    const long long base = (long long)p.tiles_x * p.tiles_y * p.B * classes;
+    int ctas = sm_count / nblocks;
+    if (ctas < 1) ctas = 1;
+    if (MODE == ZM_DECONV) ctas = ctas / 4 * 4 > 0 ? ctas / 4 * 4 : 4;   // tile % 4 (the class) must be constant per CTA
+    // segment length: trade the z halo of a segment against filling all CTAs for a whole number of rounds
+    const int halo = (MODE == ZM_S1) ? 2 : 1;
+    double best = -1.0;
+    int best_nseg = 1;
+    for (int nseg = 1; nseg <= nzt; nseg++) {
+        const int zseg = (nzt + nseg - 1) / nseg;
+        if ((long long)(nseg - 1) * zseg >= nzt) continue;
+        const long long tiles = base * nseg;
+        const long long rounds = (tiles + ctas - 1) / ctas;
+        const double eff = (double)tiles / (double)(rounds * ctas) * (double)zseg / (double)(zseg + halo) *
+                           (1.0 - 0.02 * (double)rounds / (double)(rounds + 8));
+        if (eff > best) { best = eff; best_nseg = nseg; }
+        if (tiles > 64ll * ctas) break;
+    }
+    p.nseg = best_nseg;
+    p.zseg = (nzt + best_nseg - 1) / best_nseg;
+    const long long tiles = base * p.nseg;
+    if (tiles >= (1ll << 30)) {
+        set_error("conv3d_zm: volume too large");
+        return MVSB200_E_INVALID;
+    }
+    p.ntiles = (int)tiles;
+    static size_t attr_smem = 0;  // per template instantiation
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(k2_conv3d_zm_kernel<MODE, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("conv3d_zm: cudaFuncSetAttribute(%zu bytes): %s", smem, cudaGetErrorString(e));
+            return MVSB200_E_CUDA;
+        }
+        attr_smem = smem;
+    }
+    dim3 grid((unsigned)(tiles < ctas ? tiles : ctas), (unsigned)nblocks, 1);
+    if (MODE == ZM_DECONV && grid.x % 4) grid.x = (grid.x + 3) / 4 * 4;   // ntiles is a multiple of 4
+    k2_conv3d_zm_kernel<MODE, CT><<<grid, ZM_THREADS, smem, st>>>(p);
+    return check_launch("k2_conv3d_zm_kernel");
+}
+
+}  // namespace mvsb200
+
+using namespace mvsb200;
+
+extern "C" int mvsb200_absmax(const float *x, long long n, float *amax, mvsb200_stream_t stream)
+{
+    MVSB200_REQUIRE(x && amax && n >= 0, "absmax: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(amax, 0, sizeof(float), st);
+    if (e != cudaSuccess) {
+        set_error("absmax: cudaMemsetAsync: %s", cudaGetErrorString(e));
+        return MVSB200_E_CUDA;
+    }
+    if (n == 0) return MVSB200_OK;
+    MVSB200_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "absmax: x must be 16-byte aligned");
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    k2_zm_absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, amax);
+    return check_launch("k2_zm_absmax_kernel");
+}
+
+extern "C" int mvsb200_conv3d_zm_supported(const mvsb200_conv3d_desc *d)
+{
+    return d && zm_shape_ok(d) ? 1 : 0;
+}
+
+extern "C" long long mvsb200_conv3d_zm_packed_bytes(const mvsb200_conv3d_desc *d)
+{
+    if (!d || !zm_shape_ok(d)) return 0;
+    const int ct = zm_ct(d), nblocks = (d->Cout + ct - 1) / ct, nch = (d->Cin + d->Cin2) / 8, mode = zm_mode(d);
+    const int nc = (mode == ZM_S1 ? 3 : 2) * 2 * ct;
+    return 16 + (long long)nblocks * zm_nvar(mode) * nch * 9 * (2 * nc * 16);
+}
+
+extern "C" int mvsb200_conv3d_zm_pack(const mvsb200_conv3d_desc *d, const float *w, void *packed, mvsb200_stream_t stream)
+{
+    MVSB200_REQUIRE(d && w && packed, "conv3d_zm_pack: null pointer");
+    MVSB200_REQUIRE(zm_shape_ok(d), "conv3d_zm_pack: layer not supported by the z-march engine");
+    MVSB200_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "conv3d_zm_pack: packed must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    ZmPackParams p;
+    p.w = w; p.wp = reinterpret_cast<__half *>(packed);
+    p.Cin = d->Cin + d->Cin2; p.Cout = d->Cout; p.nch = p.Cin / 8;
+    p.mode = zm_mode(d); p.CT = zm_ct(d); p.nvar = zm_nvar(p.mode);
+    p.NC = (p.mode == ZM_S1 ? 3 : 2) * 2 * p.CT;
+    const int nblocks = (d->Cout + p.CT - 1) / p.CT;
+    int rc = mvsb200_absmax(w, 27ll * p.Cin * p.Cout, reinterpret_cast<float *>(packed), stream);
+    if (rc) return rc;
+    k2_zm_header_kernel<<<1, 1, 0, st>>>(reinterpret_cast<float *>(packed));
+    k2_zm_pack_kernel<<<nblocks * p.nvar * p.nch * 9, 256, 0, st>>>(p);
+    return check_launch("k2_zm_pack_kernel");
+}
+
+extern "C" int mvsb200_conv3d_zm(const mvsb200_conv3d_desc *d, const float *x, const float *x2, const void *packed,
+                                 const float *scale, const float *bias, const float *skip, float *y,
+                                 const float *x_amax, const float *x2_amax, float *y_amax, mvsb200_stream_t stream)
+{
+    MVSB200_REQUIRE(d && x && packed && y && x_amax, "conv3d_zm: null pointer");
+    MVSB200_REQUIRE(zm_shape_ok(d), "conv3d_zm: layer not supported by the z-march engine");
+    MVSB200_REQUIRE(d->B > 0 && d->D > 0 && d->H > 0 && d->W > 0, "conv3d_zm: bad shape B=%d D=%d H=%d W=%d", d->B, d->D, d->H, d->W);
+    MVSB200_REQUIRE(d->Cin2 == 0 || (x2 && x2_amax), "conv3d_zm: Cin2=%d but x2 / x2_amax is null", d->Cin2);
+    MVSB200_REQUIRE(d->skip_mode >= 0 && d->skip_mode <= 2, "conv3d_zm: skip_mode=%d", d->skip_mode);
+    MVSB200_REQUIRE(d->skip_mode == MVSB200_SKIP_NONE || skip, "conv3d_zm: skip_mode=%d but skip is null", d->skip_mode);
+    ZmParams p;
+    int rc = mvsb200_conv3d_out_shape(d, &p.Do, &p.Ho, &p.Wo);
+    if (rc) return rc;
+    MVSB200_REQUIRE(p.Do > 0 && p.Ho > 0 && p.Wo > 0, "conv3d_zm: empty output");
+    p.x = x; p.x2 = d->Cin2 ? x2 : nullptr; p.wp = reinterpret_cast<const __half *>(packed);
+    p.scale = scale; p.bias = bias; p.skip = skip; p.y = y;
+    p.x_amax = x_amax; p.x2_amax = x2_amax; p.y_amax = y_amax;
+    p.B = d->B; p.D = d->D; p.H = d->H; p.W = d->W;
+    p.Cin1 = d->Cin; p.Cin2 = d->Cin2; p.Cout = d->Cout;
+    p.relu = d->relu; p.skip_mode = d->skip_mode;
+    p.tiles_x = p.tiles_y = p.nseg = p.zseg = p.ntiles = p.nstages = 0;
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int mode = zm_mode(d), ct = zm_ct(d);
+    if (mode == ZM_S1) return ct == 8 ? launch_zm<ZM_S1, 8>(p, sm_count, st) : launch_zm<ZM_S1, 16>(p, sm_count, st);
+    if (mode == ZM_S2) return ct == 8 ? launch_zm<ZM_S2, 8>(p, sm_count, st) : launch_zm<ZM_S2, 16>(p, sm_count, st);
+    return ct == 8 ? launch_zm<ZM_DECONV, 8>(p, sm_count, st) : launch_zm<ZM_DECONV, 16>(p, sm_count, st);
+}

@@ -12,11 +12,14 @@ import torch
 
 from . import _lib as L
 
-# K2 engine: "tc" = tcgen05 tensor cores with 3xTF32 split products (fp32-equivalent, the parity-tested default),
-# "tc_tf32" = tensor cores, single-pass TF32, "fp32" = the CUDA-core kernel.  Layers the tensor-core engine does not
-# cover (1x1x1, 2-D, Cin % 8 != 0) always run on the fp32 kernel.
-ENGINES = ("tc", "tc_tf32", "fp32")
-DEFAULT_ENGINE = os.environ.get("MVSB200_K2_ENGINE", "tc")
+# K2 engine:
+#   "zm"      = z-march tcgen05 kernel (kind::f16, error-compensated fp16 split after abs-max scaling: fp32-equivalent),
+#               the parity-tested default; layers it does not cover fall through to "tc", then to "fp32";
+#   "tc"      = tile-at-a-time tcgen05 kernel with 3xTF32 split products (fp32-equivalent);
+#   "tc_tf32" = the same kernel, single-pass TF32 (outside the parity bar);
+#   "fp32"    = the CUDA-core kernel (also runs every 1x1x1 / 2-D / Cin % 8 != 0 layer).
+ENGINES = ("zm", "tc", "tc_tf32", "fp32")
+DEFAULT_ENGINE = os.environ.get("MVSB200_K2_ENGINE", "zm")
 
 
 def _stream():
@@ -31,6 +34,35 @@ def _dev_f32(t, name):
     if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
         raise L.Mvsb200Error("%s must be a contiguous float32 CUDA tensor" % name)
     return t
+
+
+class AmaxPool:
+    """Zero-initialised device scalars for the abs-max tracking of the z-march engine: ONE fill per pool instead of
+    one per layer.  take() hands out the next 1-element view."""
+
+    def __init__(self, device, n=32):
+        self.buf = torch.zeros(n, device=device, dtype=torch.float32)
+        self.next = 0
+
+    def take(self):
+        if self.next >= self.buf.numel():
+            self.buf = torch.zeros_like(self.buf)
+            self.next = 0
+        v = self.buf[self.next:self.next + 1]
+        self.next += 1
+        return v
+
+
+def absmax(t):
+    """max|t| as a 1-element device tensor: the value its producer tracked (attribute `_mvs_amax`, set by
+    build_cost_volume / conv3d / vis_fuse) or, for tensors from elsewhere, one reduction pass (mvsb200_absmax)."""
+    a = getattr(t, "_mvs_amax", None)
+    if a is not None:
+        return a
+    a = torch.empty(1, device=t.device, dtype=torch.float32)
+    L.check(L.load().mvsb200_absmax(_ptr(t), t.numel(), _ptr(a), _stream()), "mvsb200_absmax")
+    t._mvs_amax = a
+    return a
 
 
 def to_nhwc(x):
@@ -90,9 +122,10 @@ def _depth_mode(depth, interval, B, D, H, W):
     return L.DEPTH_START_MAP
 
 
-def build_cost_volume(ref, srcs, warp, depth, D, geom, agg, interval=None, temp=None, groups=8):
+def build_cost_volume(ref, srcs, warp, depth, D, geom, agg, interval=None, temp=None, groups=8, out=None, amax=None):
     """ref [B,H,W,C]; srcs list of [B,Hs,Ws,C]; warp [B,S,16]; depth/interval see mvsb200.h.
-    Returns [B,D,H,W,C] or, for AGG_GROUPCORR, [S,B,D,H,W,groups]."""
+    Returns [B,D,H,W,C] or, for AGG_GROUPCORR, [S,B,D,H,W,groups].  `amax` (zeroed device scalar, optional) receives
+    max|out| for the z-march conv engine; `out` lets the caller own the output buffer."""
     lib = L.load()
     ref = _dev_f32(ref, "ref")
     B, H, W, C = ref.shape
@@ -114,17 +147,20 @@ def build_cost_volume(ref, srcs, warp, depth, D, geom, agg, interval=None, temp=
             raise L.Mvsb200Error("src[%d] has shape %s, expected [%d,*,*,%d]" % (i, tuple(s.shape), B, C))
         ptrs[i] = s.data_ptr()
         desc.src_h[i], desc.src_w[i] = s.shape[1], s.shape[2]
-    if agg == L.AGG_GROUPCORR:
-        out = torch.empty(S, B, D, H, W, groups, device=ref.device, dtype=torch.float32)
-        desc.out_view_stride = B * D * H * W * groups
-    else:
-        out = torch.empty(B, D, H, W, C, device=ref.device, dtype=torch.float32)
-        desc.out_view_stride = 0
+    shape = (S, B, D, H, W, groups) if agg == L.AGG_GROUPCORR else (B, D, H, W, C)
+    desc.out_view_stride = B * D * H * W * groups if agg == L.AGG_GROUPCORR else 0
+    if out is None:
+        out = torch.empty(shape, device=ref.device, dtype=torch.float32)
+    elif tuple(_dev_f32(out, "out").shape) != shape:
+        raise L.Mvsb200Error("build_cost_volume: out has shape %s, expected %s" % (tuple(out.shape), shape))
     if temp is not None:
         temp = _dev_f32(temp.detach().contiguous(), "temp")
+    if amax is None:
+        amax = torch.zeros(1, device=ref.device, dtype=torch.float32)
     L.check(lib.mvsb200_build_cost_volume(ctypes.byref(desc), _ptr(ref), ptrs, _ptr(_dev_f32(warp, "warp")), _ptr(depth),
-                                          _ptr(interval), _ptr(temp), _ptr(out), _stream()),
+                                          _ptr(interval), _ptr(temp), _ptr(out), _ptr(amax), _stream()),
             "mvsb200_build_cost_volume")
+    out._mvs_amax = amax
     return out
 
 
@@ -164,6 +200,18 @@ class PackedConv:
             self.scale = None
             self.bias = conv_bias.detach().float().contiguous() if conv_bias is not None else None
         self._tc_packed = None
+        self._zm_packed = None
+
+    def zm_packed(self, desc):
+        """Weights scaled by a power of two, split into two fp16 pieces and laid out as kind::f16 B operands for the
+        z-march engine (packed once, on the device)."""
+        if self._zm_packed is None:
+            lib = L.load()
+            n = lib.mvsb200_conv3d_zm_packed_bytes(ctypes.byref(desc))
+            buf = torch.empty((n + 3) // 4, device=self.w.device, dtype=torch.float32)
+            L.check(lib.mvsb200_conv3d_zm_pack(ctypes.byref(desc), _ptr(self.w), _ptr(buf), _stream()), "mvsb200_conv3d_zm_pack")
+            self._zm_packed = buf
+        return self._zm_packed
 
     def tc_packed(self, desc):
         """Weights split into tf32 hi/lo and laid out as tcgen05 B operands (packed once, on the device)."""
@@ -176,8 +224,9 @@ class PackedConv:
         return self._tc_packed
 
 
-def conv3d(x, layer, x2=None, skip=None, engine=None):
-    """x [B,D,H,W,Cin] (+ x2 [B,D,H,W,Cin2] concatenated on channels) -> [B,Do,Ho,Wo,Cout]."""
+def conv3d(x, layer, x2=None, skip=None, engine=None, out=None, amax=None):
+    """x [B,D,H,W,Cin] (+ x2 [B,D,H,W,Cin2] concatenated on channels) -> [B,Do,Ho,Wo,Cout].
+    `out`: caller-owned output buffer; `amax`: zeroed device scalar that receives max|y| (z-march engine)."""
     lib = L.load()
     engine = engine or DEFAULT_ENGINE
     if engine not in ENGINES:
@@ -202,12 +251,26 @@ def conv3d(x, layer, x2=None, skip=None, engine=None):
     do, ho, wo = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     L.check(lib.mvsb200_conv3d_out_shape(ctypes.byref(desc), ctypes.byref(do), ctypes.byref(ho), ctypes.byref(wo)),
             "mvsb200_conv3d_out_shape")
-    y = torch.empty(B, do.value, ho.value, wo.value, layer.cout, device=x.device, dtype=torch.float32)
+    yshape = (B, do.value, ho.value, wo.value, layer.cout)
+    if out is None:
+        y = torch.empty(yshape, device=x.device, dtype=torch.float32)
+    else:
+        y = _dev_f32(out, "out")
+        if tuple(y.shape) != yshape:
+            raise L.Mvsb200Error("conv3d: out has shape %s, expected %s" % (tuple(y.shape), yshape))
     if skip is not None:
         _dev_f32(skip, "skip")
         assert skip.shape == y.shape, (skip.shape, y.shape)
+    if engine == "zm" and x.device == layer.w.device and lib.mvsb200_conv3d_zm_supported(ctypes.byref(desc)):
+        if amax is None:
+            amax = torch.zeros(1, device=x.device, dtype=torch.float32)
+        L.check(lib.mvsb200_conv3d_zm(ctypes.byref(desc), _ptr(x), _ptr(x2), _ptr(layer.zm_packed(desc)), _ptr(layer.scale),
+                                      _ptr(layer.bias), _ptr(skip), _ptr(y), _ptr(absmax(x)),
+                                      _ptr(absmax(x2)) if x2 is not None else None, _ptr(amax), _stream()), "mvsb200_conv3d_zm")
+        y._mvs_amax = amax
+        return y
     if engine != "fp32" and x.device == layer.w.device and lib.mvsb200_conv3d_tc_supported(ctypes.byref(desc)):
-        prec = L.PRECISION_3XTF32 if engine == "tc" else L.PRECISION_TF32
+        prec = L.PRECISION_TF32 if engine == "tc_tf32" else L.PRECISION_3XTF32
         L.check(lib.mvsb200_conv3d_tc(ctypes.byref(desc), _ptr(x), _ptr(x2), _ptr(layer.tc_packed(desc)), _ptr(layer.scale),
                                       _ptr(layer.bias), _ptr(skip), _ptr(y), prec, _stream()), "mvsb200_conv3d_tc")
         return y
