@@ -4,7 +4,7 @@
 # Outputs land in gpurun_out/ (scratch); the summaries worth keeping are copied into profiles/ by hand.
 set -u
 TAG=${1:-r1}
-KREGEX=${2:-"k1_cost_volume|k2_conv3d"}
+KREGEX=${2:-"k1_cost_volume|k2_conv3d|k3_depth"}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi_$TAG.txt 2>&1
@@ -23,7 +23,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 echo "ncu list rc=$?"
 
 # full capture of the first launches of the top kernels
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$KREGEX" -c 3 -f -o $OUT/prof_$TAG \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$KREGEX" -c 13 -f -o $OUT/prof_$TAG \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_full_$TAG.log 2>&1
 echo "ncu full rc=$?"
 ls -la $OUT

@@ -93,6 +93,10 @@ def full(tag):
     hdr, units = rows[0], rows[1]
     traffic_path = os.path.join(PROF, "traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+    # the capture holds the kernels of ONE cfg2 step in launch order: name them by layer for bench.py
+    step_layers = ["k1_cost_volume", "conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv9",
+                   "conv11", "prob", "k3_regress"]
+    layers, nth = {}, 0
     with open(os.path.join(PROF, "ncu_%s.md" % tag), "w") as f:
         f.write("# ncu --set full `%s` (--clock-control none, one pass of cfg2 under the profiler; not a bench value)\n\n" % tag)
         for r in rows[2:]:
@@ -113,7 +117,12 @@ def full(tag):
                 f.write("| **dram traffic per launch** | %.1f MB |\n" % ((rd + wr) / 1e6))
                 key = name + "#" + r[hdr.index("ID")]
                 traffic[key] = rd + wr
+                if nth < len(step_layers):
+                    layers[step_layers[nth]] = {"kernel": name, "dram_bytes": rd + wr, "tag": tag}
+            nth += 1
             f.write("\n")
+    if len(layers) >= 2:
+        traffic["layers"] = layers
     json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
     print("wrote profiles/ncu_%s.md, profiles/traffic.json" % tag)
 

@@ -31,8 +31,8 @@ namespace mvsb200 {
 using namespace umma;
 
 constexpr int ZM_S1 = 0, ZM_S2 = 1, ZM_DECONV = 2;
-constexpr int ZM_EPI_WARPS = 4, ZM_PROD_WARPS = 8;
-constexpr int ZM_THREADS = (ZM_EPI_WARPS + ZM_PROD_WARPS + 1) * 32;   // 416
+constexpr int ZM_EPI_WARPS = 8, ZM_PROD_WARPS = 8;
+constexpr int ZM_THREADS = (ZM_EPI_WARPS + ZM_PROD_WARPS + 1) * 32;   // 544
 constexpr int ZM_PROD_GROUP = 128;                                     // producer threads working on one stage
 constexpr int ZM_HEADER_HALVES = 8;                                    // 16-byte header in front of the packed weights
 
@@ -45,8 +45,9 @@ template <int MODE, int CT> struct ZmCfg {
     static constexpr int EY = TY + HALO, EX = TX + HALO;
     static constexpr int ROWS = EY * EX;                      // staged rows per (plane, chunk, sub-grid)
     static constexpr int R_NEED = MT * 128 + HALO * EX;       // rows the shifted windows may touch
-    static constexpr int RA = ((R_NEED > ROWS ? R_NEED : ROWS) + 7) / 8 * 8;
-    static constexpr int NPF = (ROWS + ZM_PROD_GROUP - 1) / ZM_PROD_GROUP;   // rows per producer thread per stage
+    // rounded up to 2 mod 4: consecutive stage buffers (2*RA*16 bytes) then start 64 bytes apart modulo 128, so the
+    // 8-byte stores of a producer warp, which fan out over the stage buffers of a unit, are bank-conflict free
+    static constexpr int RA = ((R_NEED > ROWS ? R_NEED : ROWS) + 1) / 4 * 4 + 2;
     static constexpr int NSUB = (MODE == ZM_S2) ? 4 : 1;      // (py,px) parity sub-grids staged per plane
     static constexpr int NPXL = (MODE == ZM_S2) ? 2 : 1;      // x-parity weight variants resident per CTA
     static constexpr int NACC = (512 / (MT * NC) >= 8) ? 8 : 4;   // accumulator planes in TMEM
@@ -54,7 +55,8 @@ template <int MODE, int CT> struct ZmCfg {
     static constexpr int XROWS = MT * 128 + 8;
     static constexpr int STAGE_BYTES = 2 * RA * 16;
     static constexpr int WBLOCK_BYTES = 2 * NC * 16;          // one (chunk, px, kz, ky) weight block
-    static constexpr int X_BYTES = (NXS - 1) * (CT / 4) * XROWS * 16;
+    static constexpr int X_BYTES = (NXS - 1) * (CT / 4) * XROWS * 16;   // x-shift exchange buffer of one epilogue team
+    static constexpr int NTEAMS = (MT == 2) ? 1 : 2;
     static_assert(TY * EX <= MT * 128, "plane tile does not fit the MMA row tiles");
     static_assert(NACC * ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(NC % 16 == 0 && NC <= 256, "invalid MMA N");
@@ -76,6 +78,16 @@ struct ZmParams {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Waiters that are not on the critical path back off between polls so that their spinning does not take issue slots
+// from the MMA-issuing thread (bounded like umma::mbar_wait: a pipeline bug must trap, not hang the GPU).
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
+{
+    for (uint32_t i = 0; i < (1u << 24); i++) {
+        if (mbar_try_wait(bar, parity)) return;
+        __nanosleep(64);
+    }
+    __trap();
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
@@ -172,28 +184,42 @@ template <int MODE, int CT> __device__ __forceinline__ ZmTile zm_decode(const Zm
     return t;
 }
 
+
+// Pipeline stages of one input plane, in issue order:  for py: for chunk c: for px  (py, px: parity sub-grids of S2).
+// The producers fill them in UNITS of G chunks x NPX sub-grids = one contiguous run of G*32 bytes per voxel (the
+// whole 128-byte voxel record when Cin >= 32), so that a warp-level 16-byte load covers whole cache lines.
+__device__ __forceinline__ int zm_unit_chunks(int c, int nch1, int nch, int gmax)
+{
+    const int rem = (c < nch1 ? nch1 : nch) - c;   // chunks left in the tensor this chunk belongs to
+    int g = 1;
+    while (g * 2 <= gmax && g * 2 <= rem) g *= 2;
+    return g;
+}
+
 template <int MODE, int CT>
 __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmParams p)
 {
     using T = ZmCfg<MODE, CT>;
     constexpr int NC = T::NC, RA = T::RA, MT = T::MT, NACC = T::NACC, EX = T::EX;
     constexpr int MAXST = 8;
+    constexpr int NPY = (MODE == ZM_S2) ? 2 : 1, NPX = NPY;
+    constexpr int TEAM_WARPS = 4 * MT, NTEAMS = ZM_EPI_WARPS / TEAM_WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_full[MAXST], s_empty[MAXST], s_accfull[8], s_accempty[8], s_wbar;
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nb = blockIdx.y;
-    const int nch = (p.Cin1 + p.Cin2) >> 3;
+    const int nch = (p.Cin1 + p.Cin2) >> 3, nch1 = p.Cin1 >> 3;
     const int NST = p.nstages;
     const int wblocks = T::NPXL * nch * 9;
     unsigned char *sW = smem_raw;
     unsigned char *sA = sW + (size_t)wblocks * T::WBLOCK_BYTES;
-    float4 *sX = reinterpret_cast<float4 *>(sA + (size_t)NST * T::STAGE_BYTES);
+    float4 *sXall = reinterpret_cast<float4 *>(sA + (size_t)NST * T::STAGE_BYTES);
 
     if (tid == 0) {
-        for (int i = 0; i < NST; i++) { mbar_init(smem_u32(&s_full[i]), 4); mbar_init(smem_u32(&s_empty[i]), 1); }
-        for (int i = 0; i < NACC; i++) { mbar_init(smem_u32(&s_accfull[i]), 1); mbar_init(smem_u32(&s_accempty[i]), ZM_EPI_WARPS); }
+        for (int i = 0; i < NST; i++) { mbar_init(smem_u32(&s_full[i]), ZM_PROD_GROUP / 32); mbar_init(smem_u32(&s_empty[i]), 1); }
+        for (int i = 0; i < NACC; i++) { mbar_init(smem_u32(&s_accfull[i]), 1); mbar_init(smem_u32(&s_accempty[i]), TEAM_WARPS); }
         mbar_init(smem_u32(&s_wbar), ZM_PROD_WARPS);
         fence_mbar_init();
     }
@@ -214,93 +240,92 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
 
     if (warp < ZM_EPI_WARPS) {
         // =================================== epilogue warps ===================================
+        // MT == 2: one team of 8 warps, warps 0-3 take row tile 0 and warps 4-7 row tile 1 of every plane;
+        // MT == 1: two teams of 4 warps taking alternate planes.  A warp reads the TMEM lanes of quadrant warp % 4.
+        const int quad = warp & 3, team = (MT == 2) ? 0 : (warp >> 2), mt = (MT == 2) ? (warp >> 2) : 0;
+        float4 *sX = sXall + (size_t)team * (T::X_BYTES / 16);
         const float w_inv = __ldg(reinterpret_cast<const float *>(p.wp) + 1);   // header: {w_scale, w_inv_scale, -, -}
         const float unscale = inv_sx * w_inv;
         constexpr int C4 = CT / 4;
         const int ncol = min(CT, p.Cout - nb * CT), co0 = nb * CT;
-        float4 sc[C4], bi[C4];
-#pragma unroll
-        for (int c4 = 0; c4 < C4; c4++) {
-            sc[c4] = make_float4(unscale, unscale, unscale, unscale);
-            bi[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c4 * 4 < ncol) {
-                if (p.scale) { const float4 s4 = ldg4(p.scale + co0 + c4 * 4); sc[c4].x *= s4.x; sc[c4].y *= s4.y; sc[c4].z *= s4.z; sc[c4].w *= s4.w; }
-                if (p.bias) bi[c4] = ldg4(p.bias + co0 + c4 * 4);
-            }
-        }
+        const int pr = mt * 128 + quad * 32 + lane;           // GEMM row of this thread within the plane tile
+        const int oy_l = pr / EX, ox_l = pr % EX;
         float vmax = 0.f;
         int qg = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             const ZmTile t = zm_decode<MODE, CT>(p, tile);
             const int ry = (t.cls >> 1) & 1, rx = t.cls & 1;
+            int oy = t.y0 + oy_l, ox = t.x0 + ox_l;
+            bool ok_yx = oy_l < T::TY && ox_l < T::TX;
+            if (MODE == ZM_DECONV) {
+                ok_yx = ok_yx && oy < p.H && ox < p.W;
+                oy = 2 * oy + ry; ox = 2 * ox + rx;
+            }
+            ok_yx = ok_yx && oy < p.Ho && ox < p.Wo;
             for (int q = 0; q < t.nq; q++, qg++) {
+                if (NTEAMS == 2 && (qg & 1) != team) continue;
                 const int slot = qg % NACC;
-                mbar_wait(smem_u32(&s_accfull[slot]), (uint32_t)(qg / NACC) & 1u);
+                const int oz = (MODE == ZM_DECONV ? 2 * t.zb : t.zb) + q;
+                const bool ok = ok_yx && oz < p.Do;
+                const long long o = ((((long long)t.b * p.Do + oz) * p.Ho + oy) * p.Wo + ox) * p.Cout + co0;
+                // the skip operand does not depend on the accumulator: fetch it while the MMAs are still running
+                float4 sk[C4];
+#pragma unroll
+                for (int c4 = 0; c4 < C4; c4++) {
+                    sk[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok && p.skip_mode != MVSB200_SKIP_NONE && c4 * 4 < ncol) sk[c4] = ldg4(p.skip + o + c4 * 4);
+                }
+                mbar_wait_relaxed(smem_u32(&s_accfull[slot]), (uint32_t)(qg / NACC) & 1u);
                 tc_fence_after_sync();
-                float r0[MT][CT];
+                float r0[CT];
 #pragma unroll
-                for (int mt = 0; mt < MT; mt++) {
-                    const int xrow = mt * 128 + warp * 32 + lane;
+                for (int xs = 0; xs < T::NXS; xs++) {
+                    float v[2 * CT];
+                    const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + slot * T::ACC_COLS + mt * NC + xs * 2 * CT;
 #pragma unroll
-                    for (int xs = 0; xs < T::NXS; xs++) {
-                        float v[2 * CT];
-                        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + slot * T::ACC_COLS + mt * NC + xs * 2 * CT;
+                    for (int j = 0; j < 2 * CT; j += 16) tmem_ld16(taddr + j, v + j);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 2 * CT; j += 16) tmem_ld16(taddr + j, v + j);
-                        tmem_ld_wait();
+                    for (int k = 0; k < CT; k++) v[k] += v[CT + k];
+                    if (xs == 0) {
 #pragma unroll
-                        for (int k = 0; k < CT; k++) v[k] += v[CT + k];
-                        if (xs == 0) {
+                        for (int k = 0; k < CT; k++) r0[k] = v[k];
+                    } else {
 #pragma unroll
-                            for (int k = 0; k < CT; k++) r0[mt][k] = v[k];
-                        } else {
-#pragma unroll
-                            for (int c4 = 0; c4 < C4; c4++)
-                                sX[((xs - 1) * C4 + c4) * T::XROWS + xrow] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
-                        }
+                        for (int c4 = 0; c4 < C4; c4++)
+                            sX[((xs - 1) * C4 + c4) * T::XROWS + pr] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
                     }
                 }
                 // the accumulator plane is in registers / shared memory: hand the TMEM slot back to the MMA thread
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&s_accempty[slot]));
-                named_bar_sync(1, ZM_EPI_WARPS * 32);
-                int oz = t.zb + q;
-                if (MODE == ZM_DECONV) oz = 2 * t.zb + q;
-#pragma unroll
-                for (int mt = 0; mt < MT; mt++) {
-                    const int pr = mt * 128 + warp * 32 + lane;
-                    const int oy_l = pr / EX, ox_l = pr % EX;
-                    int oy = t.y0 + oy_l, ox = t.x0 + ox_l;
-                    bool ok = oy_l < T::TY && ox_l < T::TX;
-                    if (MODE == ZM_DECONV) {
-                        ok = ok && oy < p.H && ox < p.W;
-                        oy = 2 * oy + ry; ox = 2 * ox + rx;
-                    }
-                    ok = ok && oz < p.Do && oy < p.Ho && ox < p.Wo;
-                    if (!ok) continue;
-                    const long long o = ((((long long)t.b * p.Do + oz) * p.Ho + oy) * p.Wo + ox) * p.Cout + co0;
+                if (team == 0) named_bar_sync(1, TEAM_WARPS * 32); else named_bar_sync(2, TEAM_WARPS * 32);
+                if (ok) {
 #pragma unroll
                     for (int c4 = 0; c4 < C4; c4++) {
                         if (c4 * 4 >= ncol) break;
-                        float r[4] = {r0[mt][c4 * 4], r0[mt][c4 * 4 + 1], r0[mt][c4 * 4 + 2], r0[mt][c4 * 4 + 3]};
+                        float r[4] = {r0[c4 * 4], r0[c4 * 4 + 1], r0[c4 * 4 + 2], r0[c4 * 4 + 3]};
 #pragma unroll
                         for (int xs = 1; xs < T::NXS; xs++) {
                             const float4 nbv = sX[((xs - 1) * C4 + c4) * T::XROWS + pr + xs];
                             r[0] += nbv.x; r[1] += nbv.y; r[2] += nbv.z; r[3] += nbv.w;
                         }
-                        r[0] = fmaf(r[0], sc[c4].x, bi[c4].x); r[1] = fmaf(r[1], sc[c4].y, bi[c4].y);
-                        r[2] = fmaf(r[2], sc[c4].z, bi[c4].z); r[3] = fmaf(r[3], sc[c4].w, bi[c4].w);
-                        float4 sk = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.skip_mode != MVSB200_SKIP_NONE) sk = ldg4(p.skip + o + c4 * 4);
-                        if (p.skip_mode == MVSB200_SKIP_BEFORE_RELU) { r[0] += sk.x; r[1] += sk.y; r[2] += sk.z; r[3] += sk.w; }
+                        // BN scale / bias: 16-byte loads that stay in L1 (keeping them in registers spills at CT = 16)
+                        float4 sc = make_float4(unscale, unscale, unscale, unscale), bi = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.scale) { const float4 s4 = ldg4(p.scale + co0 + c4 * 4); sc.x *= s4.x; sc.y *= s4.y; sc.z *= s4.z; sc.w *= s4.w; }
+                        if (p.bias) bi = ldg4(p.bias + co0 + c4 * 4);
+                        r[0] = fmaf(r[0], sc.x, bi.x); r[1] = fmaf(r[1], sc.y, bi.y);
+                        r[2] = fmaf(r[2], sc.z, bi.z); r[3] = fmaf(r[3], sc.w, bi.w);
+                        if (p.skip_mode == MVSB200_SKIP_BEFORE_RELU) { r[0] += sk[c4].x; r[1] += sk[c4].y; r[2] += sk[c4].z; r[3] += sk[c4].w; }
                         if (p.relu) { r[0] = fmaxf(r[0], 0.f); r[1] = fmaxf(r[1], 0.f); r[2] = fmaxf(r[2], 0.f); r[3] = fmaxf(r[3], 0.f); }
-                        if (p.skip_mode == MVSB200_SKIP_AFTER_RELU) { r[0] += sk.x; r[1] += sk.y; r[2] += sk.z; r[3] += sk.w; }
+                        if (p.skip_mode == MVSB200_SKIP_AFTER_RELU) { r[0] += sk[c4].x; r[1] += sk[c4].y; r[2] += sk[c4].z; r[3] += sk[c4].w; }
                         vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(r[0]), fabsf(r[1]))), fmaxf(fabsf(r[2]), fabsf(r[3])));
                         st4(p.y + o + c4 * 4, make_float4(r[0], r[1], r[2], r[3]));
                     }
                 }
-                named_bar_sync(1, ZM_EPI_WARPS * 32);   // sX is rewritten by the next plane
+                // sX is rewritten by the team's next plane
+                if (team == 0) named_bar_sync(1, TEAM_WARPS * 32); else named_bar_sync(2, TEAM_WARPS * 32);
             }
         }
         if (p.y_amax) {
@@ -315,10 +340,10 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
         // resident weights of this CTA: S1 one variant, S2 both x-parity variants, DECONV the variant of the CTA's
         // output class (the grid is a multiple of 4 wide and the class is the fastest tile index, so every tile of a
         // CTA has class blockIdx.x % 4)
-        const size_t wblock_halves = T::WBLOCK_BYTES / 2;
-        const __half *wsrc = p.wp + ZM_HEADER_HALVES + (size_t)nb * ((MODE == ZM_S1 ? 1 : 2) * nch * 9) * wblock_halves;
-        if (MODE == ZM_DECONV) wsrc += (size_t)(blockIdx.x & 1) * (nch * 9) * wblock_halves;
         {
+            const size_t wblock_halves = T::WBLOCK_BYTES / 2;
+            const __half *wsrc = p.wp + ZM_HEADER_HALVES + (size_t)nb * ((MODE == ZM_S1 ? 1 : 2) * nch * 9) * wblock_halves;
+            if (MODE == ZM_DECONV) wsrc += (size_t)(blockIdx.x & 1) * (nch * 9) * wblock_halves;
             const uint4 *src = reinterpret_cast<const uint4 *>(wsrc);
             uint4 *dst = reinterpret_cast<uint4 *>(sW);
             const int n16 = wblocks * T::WBLOCK_BYTES / 16;
@@ -327,77 +352,92 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_wbar));
         }
-        int it = 0;
+        constexpr int XV = EX * NPX;          // voxels of one staged row run (contiguous in x)
+        constexpr int BATCH = 5;              // 16-byte loads in flight per thread
+        int it = 0, un = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             const ZmTile t = zm_decode<MODE, CT>(p, tile);
             const int np = zm_nplanes<MODE>(t.nq);
             for (int pl = 0; pl < np; pl++) {
                 const int gz = zm_zin<MODE>(t.zb, pl);
                 if ((unsigned)gz >= (unsigned)p.D) continue;   // an all-zero plane contributes nothing: no stage at all
-                for (int c = 0; c < nch; c++) {
-                    const float *src;
-                    int cs, cstride;
-                    if (c * 8 < p.Cin1) { src = p.x; cs = c * 8; cstride = p.Cin1; }
-                    else { src = p.x2; cs = c * 8 - p.Cin1; cstride = p.Cin2; }
-                    const float *plane = src + ((long long)t.b * p.D + gz) * p.H * p.W * cstride + cs;
-                    for (int s = 0; s < T::NSUB; s++, it++) {
-                        if ((it & 1) != group) continue;
-                        const int py = (s >> 1) & 1, px = s & 1;
-                        float4 va[T::NPF], vb[T::NPF];
+                for (int py = 0; py < NPY; py++) {
+                    for (int c0 = 0; c0 < nch;) {
+                        const int G = zm_unit_chunks(c0, nch1, nch, 4 / NPX);
+                        const int nst_unit = G * NPX;
+                        if ((un++ & 1) != group) { c0 += G; it += nst_unit; continue; }
+                        const float *src;
+                        int cs, cstride;
+                        if (c0 < nch1) { src = p.x; cs = c0 * 8; cstride = p.Cin1; }
+                        else { src = p.x2; cs = (c0 - nch1) * 8; cstride = p.Cin2; }
+                        const float *plane = src + ((long long)t.b * p.D + gz) * p.H * p.W * cstride + cs;
+                        const int lgp = (G == 4) ? 3 : (G == 2 ? 2 : 1);     // log2(16-byte pieces per voxel)
+                        const int npieces = (T::EY * XV) << lgp;
+                        bool waited = false;
+                        for (int k0 = gt; k0 < npieces; k0 += BATCH * ZM_PROD_GROUP) {
+                            float4 v[BATCH];
 #pragma unroll
-                        for (int k = 0; k < T::NPF; k++) {
-                            const int i = gt + k * ZM_PROD_GROUP;
-                            const int ly = i / EX, lx = i % EX;
-                            int gy, gx;
-                            if (MODE == ZM_S1) { gy = t.y0 - 1 + ly; gx = t.x0 - 1 + lx; }
-                            else if (MODE == ZM_S2) { gy = 2 * (t.y0 + ly) - 1 + py; gx = 2 * (t.x0 + lx) - 1 + px; }
-                            else { gy = t.y0 + ly; gx = t.x0 + lx; }
-                            va[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            vb[k] = va[k];
-                            if (i < T::ROWS && (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W) {
-                                const float *q = plane + ((long long)gy * p.W + gx) * cstride;
-                                va[k] = ldg4(q);
-                                vb[k] = ldg4(q + 4);
+                            for (int k = 0; k < BATCH; k++) {
+                                const int idx = k0 + k * ZM_PROD_GROUP;
+                                const int piece = idx & ((1 << lgp) - 1), vx = idx >> lgp;
+                                const int lxv = vx % XV, ly = vx / XV;
+                                int gy, gx;
+                                if (MODE == ZM_S1) { gy = t.y0 - 1 + ly; gx = t.x0 - 1 + lxv; }
+                                else if (MODE == ZM_S2) { gy = 2 * (t.y0 + ly) - 1 + py; gx = 2 * t.x0 - 1 + lxv; }
+                                else { gy = t.y0 + ly; gx = t.x0 + lxv; }
+                                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (idx < npieces && (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W)
+                                    v[k] = ldg4(plane + ((long long)gy * p.W + gx) * cstride + piece * 4);
                             }
-                        }
-                        const int slot = it % NST;
-                        mbar_wait(smem_u32(&s_empty[slot]), ((uint32_t)(it / NST) & 1u) ^ 1u);
-                        uint4 *dst = reinterpret_cast<uint4 *>(sA + (size_t)slot * T::STAGE_BYTES);
+                            if (!waited) {   // the unit's stage buffers must have been released by the MMAs that read them
+                                for (int j = 0; j < nst_unit; j++)
+                                    mbar_wait_relaxed(smem_u32(&s_empty[(it + j) % NST]), ((uint32_t)((it + j) / NST) & 1u) ^ 1u);
+                                waited = true;
+                            }
 #pragma unroll
-                        for (int k = 0; k < T::NPF; k++) {
-                            const int i = gt + k * ZM_PROD_GROUP;
-                            if (i < T::ROWS) {
-                                const float f[8] = {va[k].x * sx, va[k].y * sx, va[k].z * sx, va[k].w * sx,
-                                                    vb[k].x * sx, vb[k].y * sx, vb[k].z * sx, vb[k].w * sx};
-                                uint32_t hw[4], lw[4];
-#pragma unroll
-                                for (int e = 0; e < 4; e++) {
-                                    const __half2 h = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
-                                    const float2 hf = __half22float2(h);
-                                    const __half2 l = __floats2half2_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
-                                    hw[e] = *reinterpret_cast<const uint32_t *>(&h);
-                                    lw[e] = *reinterpret_cast<const uint32_t *>(&l);
-                                }
-                                dst[i] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                                dst[RA + i] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                            for (int k = 0; k < BATCH; k++) {
+                                const int idx = k0 + k * ZM_PROD_GROUP;
+                                if (idx >= npieces) break;
+                                const int piece = idx & ((1 << lgp) - 1), vx = idx >> lgp;
+                                const int lxv = vx % XV, ly = vx / XV;
+                                const int px = (NPX == 2) ? (lxv & 1) : 0, lx = (NPX == 2) ? (lxv >> 1) : lxv;
+                                const int j = (piece >> 1) * NPX + px;          // stage of the unit this piece belongs to
+                                const float f0 = v[k].x * sx, f1 = v[k].y * sx, f2 = v[k].z * sx, f3 = v[k].w * sx;
+                                const __half2 h01 = __floats2half2_rn(f0, f1), h23 = __floats2half2_rn(f2, f3);
+                                const float2 g01 = __half22float2(h01), g23 = __half22float2(h23);
+                                const __half2 l01 = __floats2half2_rn(f0 - g01.x, f1 - g01.y), l23 = __floats2half2_rn(f2 - g23.x, f3 - g23.y);
+                                unsigned char *dst = sA + (size_t)((it + j) % NST) * T::STAGE_BYTES + (size_t)(ly * EX + lx) * 16 + (piece & 1) * 8;
+                                *reinterpret_cast<uint2 *>(dst) = make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
+                                *reinterpret_cast<uint2 *>(dst + RA * 16) = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
                             }
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&s_full[slot]));
+                        if (lane == 0)
+                            for (int j = 0; j < nst_unit; j++) mbar_arrive(smem_u32(&s_full[(it + j) % NST]));
+                        c0 += G;
+                        it += nst_unit;
                     }
                 }
             }
         }
     } else {
         // =================================== MMA issuer ===================================
+        // ONE thread issues every MMA of the CTA, so its instruction stream is the pacing item of the whole pipeline:
+        // ring positions and phases are carried incrementally (no division), the tap loops are fully unrolled and a
+        // descriptor is the 32-bit low word (start address | LBO) plus a constant high word.
         if (lane == 0) {
             constexpr uint32_t idesc = idesc_f16(128, NC);
             mbar_wait(smem_u32(&s_wbar), 0);
             tc_fence_after_sync();
-            const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
-            int it = 0, qbase = 0;
-            uint32_t started = 0;   // bit per accumulator slot: the plane in it has received its first MMA
+            const uint32_t a_hi = (uint32_t)(smem_desc(0, RA * 16, 128) >> 32), b_hi = (uint32_t)(smem_desc(0, NC * 16, 128) >> 32);
+            const uint32_t a_lo0 = (uint32_t)smem_desc(smem_u32(sA), RA * 16, 128), b_lo0 = (uint32_t)smem_desc(smem_u32(sW), NC * 16, 128);
+            const uint32_t full0 = smem_u32(&s_full[0]), empty0 = smem_u32(&s_empty[0]);
+            const uint32_t accfull0 = smem_u32(&s_accfull[0]), accempty0 = smem_u32(&s_accempty[0]);
+            int slot = 0;            // stage ring position
+            uint32_t sphase = 0;     // parity of the current pass over the stage ring
+            int qbase = 0;           // output planes of the tiles already issued (accumulator ring position = qbase + q)
+            uint32_t started = 0;    // bit per accumulator slot: the plane in it has received its first MMA
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 const ZmTile t = zm_decode<MODE, CT>(p, tile);
                 const int np = zm_nplanes<MODE>(t.nq);
@@ -405,46 +445,62 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                 for (int pl = 0; pl < np; pl++) {
                     const int gz = zm_zin<MODE>(t.zb, pl);
                     if ((unsigned)gz < (unsigned)p.D) {
-                        for (int c = 0; c < nch; c++) {
-                            for (int s = 0; s < T::NSUB; s++, it++) {
-                                const int slot = it % NST;
-                                mbar_wait(smem_u32(&s_full[slot]), (uint32_t)(it / NST) & 1u);
-                                tc_fence_after_sync();
-                                const int py = (s >> 1) & 1, px = s & 1;
-                                const int vy = (MODE == ZM_S2) ? py : vy_cls;
-                                const int ny = zm_dim_opts(MODE, vy);
-                                const uint64_t adesc = smem_desc(sA_u + slot * T::STAGE_BYTES, RA * 16, 128);
-                                const int ncn = zm_ncontrib<MODE>(pl);
-                                for (int j = 0; j < ncn; j++) {
-                                    int q, kz;
-                                    zm_contrib<MODE>(pl, j, q, kz);
-                                    if (q < 0 || q >= t.nq) continue;
-                                    const int qg = qbase + q, aslot = qg % NACC;
-                                    if (!(started >> aslot & 1u)) {
-                                        mbar_wait(smem_u32(&s_accempty[aslot]), ((uint32_t)(qg / NACC) & 1u) ^ 1u);
-                                        tc_fence_after_sync();
-                                    }
-                                    for (int jy = 0; jy < ny; jy++) {
-                                        const int ky = zm_dim_k(MODE, vy, jy);
-                                        const int shift = zm_dim_shift(MODE, vy, jy) * EX;
-                                        const int wb = (((MODE == ZM_S2 ? px : 0) * nch + c) * 3 + kz) * 3 + ky;
-                                        const uint64_t bdesc = smem_desc(sW_u + wb * T::WBLOCK_BYTES, NC * 16, 128);
-                                        const uint32_t acc = (started >> aslot & 1u) ? 1u : 0u;
+                        // accumulator slots of the (up to 3) output planes this input plane contributes to
+                        int cq[3], ckz[3];
+                        uint32_t cd[3];
+                        int ncn = 0;
 #pragma unroll
-                                        for (int mt = 0; mt < MT; mt++)
-                                            mma_f16(tmem + aslot * T::ACC_COLS + mt * NC, adesc + (uint64_t)(mt * 128 + shift), bdesc, idesc, acc);
-                                        started |= 1u << aslot;
+                        for (int j = 0; j < 3; j++) {
+                            if (j >= zm_ncontrib<MODE>(pl)) continue;
+                            int q, kz;
+                            zm_contrib<MODE>(pl, j, q, kz);
+                            if (q < 0 || q >= t.nq) continue;
+                            const int qg = qbase + q, aslot = qg & (NACC - 1);
+                            if (!(started >> aslot & 1u)) {   // first touch: the epilogue must have drained the slot
+                                mbar_wait(accempty0 + aslot * 8, ((uint32_t)(qg / NACC) & 1u) ^ 1u);
+                            }
+                            cq[ncn] = aslot; ckz[ncn] = kz; cd[ncn] = tmem + aslot * T::ACC_COLS;
+                            ncn++;
+                        }
+                        tc_fence_after_sync();
+                        for (int py = 0; py < NPY; py++) {
+                            const int vy = (MODE == ZM_S2) ? py : vy_cls;
+                            for (int c = 0; c < nch; c++) {
+#pragma unroll
+                                for (int px = 0; px < NPX; px++) {
+                                    mbar_wait(full0 + slot * 8, sphase);
+                                    tc_fence_after_sync();
+                                    const uint32_t a_lo = a_lo0 + slot * (T::STAGE_BYTES / 16);
+                                    const uint32_t b_c = b_lo0 + ((px * nch + c) * 9) * (T::WBLOCK_BYTES / 16);
+#pragma unroll
+                                    for (int j = 0; j < 3; j++) {
+                                        if (j >= ncn) continue;
+                                        const uint32_t b_z = b_c + ckz[j] * 3 * (T::WBLOCK_BYTES / 16);
+                                        uint32_t acc = (started >> cq[j]) & 1u;
+#pragma unroll
+                                        for (int jy = 0; jy < 3; jy++) {
+                                            if (jy >= zm_dim_opts(MODE, vy)) continue;
+                                            const int ky = zm_dim_k(MODE, vy, jy);
+                                            const uint32_t shift = zm_dim_shift(MODE, vy, jy) * EX;
+                                            const uint64_t bdesc = ((uint64_t)b_hi << 32) | (b_z + ky * (T::WBLOCK_BYTES / 16));
+#pragma unroll
+                                            for (int m = 0; m < MT; m++)
+                                                mma_f16(cd[j] + m * NC, ((uint64_t)a_hi << 32) | (a_lo + m * 128 + shift), bdesc, idesc, acc);
+                                            acc = 1u;
+                                        }
+                                        started |= 1u << cq[j];
                                     }
+                                    mma_commit(empty0 + slot * 8);
+                                    if (++slot == NST) { slot = 0; sphase ^= 1u; }
                                 }
-                                mma_commit(smem_u32(&s_empty[slot]));
                             }
                         }
                     }
                     int qlo, qhi;
                     zm_complete<MODE>(pl, t.nq, qlo, qhi);
                     for (int q = qlo; q < qhi; q++) {
-                        const int aslot = (qbase + q) % NACC;
-                        mma_commit(smem_u32(&s_accfull[aslot]));
+                        const int aslot = (qbase + q) & (NACC - 1);
+                        mma_commit(accfull0 + aslot * 8);
                         started &= ~(1u << aslot);
                     }
                 }
@@ -534,13 +590,13 @@ static int zm_nvar(int mode) { return mode == ZM_S1 ? 1 : 2; }
 template <int MODE, int CT> static size_t zm_smem_bytes(int nch, int nst)
 {
     using T = ZmCfg<MODE, CT>;
-    return (size_t)T::NPXL * nch * 9 * T::WBLOCK_BYTES + (size_t)nst * T::STAGE_BYTES + T::X_BYTES;
+    return (size_t)T::NPXL * nch * 9 * T::WBLOCK_BYTES + (size_t)nst * T::STAGE_BYTES + (size_t)T::NTEAMS * T::X_BYTES;
 }
 
 // number of pipeline stages that fit next to the resident weights (0: the layer does not fit this engine)
 template <int MODE, int CT> static int zm_stages(int nch)
 {
-    for (int nst = 8; nst >= 3; nst--)
+    for (int nst = 8; nst >= 4; nst--)
         if (zm_smem_bytes<MODE, CT>(nch, nst) + 2048 <= 227 * 1024) return nst;
     return 0;
 }

@@ -99,14 +99,16 @@ class CostRegNet(nn.Module):
         if D % 8 or H % 8 or W % 8:
             raise L.Mvsb200Error("CostRegNet needs D,H,W divisible by 8 (got %d,%d,%d)" % (D, H, W))
         pk = self._pack()
-        c0 = ops.conv3d(vol, pk["conv0"])
-        c2 = ops.conv3d(ops.conv3d(c0, pk["conv1"]), pk["conv2"])
-        c4 = ops.conv3d(ops.conv3d(c2, pk["conv3"]), pk["conv4"])
-        x = ops.conv3d(ops.conv3d(c4, pk["conv5"]), pk["conv6"])
-        x = ops.conv3d(x, pk["conv7"], skip=c4)
-        x = ops.conv3d(x, pk["conv9"], skip=c2)
-        x = ops.conv3d(x, pk["conv11"], skip=c0)
-        return ops.conv3d(x, pk["prob"]).squeeze(-1)
+        am = ops.AmaxPool(vol.device, 16)   # abs-max scalars of the layer outputs: one fill for the whole net
+        conv = lambda x, name, skip=None: ops.conv3d(x, pk[name], skip=skip, amax=am.take())
+        c0 = conv(vol, "conv0")
+        c2 = conv(conv(c0, "conv1"), "conv2")
+        c4 = conv(conv(c2, "conv3"), "conv4")
+        x = conv(conv(c4, "conv5"), "conv6")
+        x = conv(x, "conv7", c4)
+        x = conv(x, "conv9", c2)
+        x = conv(x, "conv11", c0)
+        return conv(x, "prob").squeeze(-1)
 
     def forward(self, x, down_ft=None):
         """Reference signature: x [B,32,D,H,W] -> [B,1,D,H,W] (models/MVSNet/model.py:74-84)."""
