@@ -89,6 +89,16 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
     }
     __trap();
 }
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -425,8 +435,10 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
         // =================================== MMA issuer ===================================
         // ONE thread issues every MMA of the CTA, so its instruction stream is the pacing item of the whole pipeline:
         // ring positions and phases are carried incrementally (no division), the tap loops are fully unrolled and a
-        // descriptor is the 32-bit low word (start address | LBO) plus a constant high word.
-        if (lane == 0) {
+        // descriptor is the 32-bit low word (start address | LBO) plus a constant high word.  The whole warp runs the
+        // (warp-uniform) control flow and waits; only the tcgen05 instructions are predicated on the elected lane, which
+        // keeps descriptors in uniform registers instead of a per-instruction leader-election loop.
+        {
             constexpr uint32_t idesc = idesc_f16(128, NC);
             mbar_wait(smem_u32(&s_wbar), 0);
             tc_fence_after_sync();
@@ -472,25 +484,30 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                                     tc_fence_after_sync();
                                     const uint32_t a_lo = a_lo0 + slot * (T::STAGE_BYTES / 16);
                                     const uint32_t b_c = b_lo0 + ((px * nch + c) * 9) * (T::WBLOCK_BYTES / 16);
+                                    if (elect_one_sync()) {
 #pragma unroll
-                                    for (int j = 0; j < 3; j++) {
-                                        if (j >= ncn) continue;
-                                        const uint32_t b_z = b_c + ckz[j] * 3 * (T::WBLOCK_BYTES / 16);
-                                        uint32_t acc = (started >> cq[j]) & 1u;
+                                        for (int j = 0; j < 3; j++) {
+                                            if (j >= ncn) continue;
+                                            const uint32_t b_z = b_c + ckz[j] * 3 * (T::WBLOCK_BYTES / 16);
+                                            uint32_t acc = (started >> cq[j]) & 1u;
 #pragma unroll
-                                        for (int jy = 0; jy < 3; jy++) {
-                                            if (jy >= zm_dim_opts(MODE, vy)) continue;
-                                            const int ky = zm_dim_k(MODE, vy, jy);
-                                            const uint32_t shift = zm_dim_shift(MODE, vy, jy) * EX;
-                                            const uint64_t bdesc = ((uint64_t)b_hi << 32) | (b_z + ky * (T::WBLOCK_BYTES / 16));
+                                            for (int jy = 0; jy < 3; jy++) {
+                                                if (jy >= zm_dim_opts(MODE, vy)) continue;
+                                                const int ky = zm_dim_k(MODE, vy, jy);
+                                                const uint32_t shift = zm_dim_shift(MODE, vy, jy) * EX;
+                                                const uint64_t bdesc = ((uint64_t)b_hi << 32) | (b_z + ky * (T::WBLOCK_BYTES / 16));
 #pragma unroll
-                                            for (int m = 0; m < MT; m++)
-                                                mma_f16(cd[j] + m * NC, ((uint64_t)a_hi << 32) | (a_lo + m * 128 + shift), bdesc, idesc, acc);
-                                            acc = 1u;
+                                                for (int m = 0; m < MT; m++)
+                                                    mma_f16(cd[j] + m * NC, ((uint64_t)a_hi << 32) | (a_lo + m * 128 + shift), bdesc, idesc, acc);
+                                                acc = 1u;
+                                            }
                                         }
-                                        started |= 1u << cq[j];
+                                        mma_commit(empty0 + slot * 8);
                                     }
-                                    mma_commit(empty0 + slot * 8);
+#pragma unroll
+                                    for (int j = 0; j < 3; j++)
+                                        if (j < ncn) started |= 1u << cq[j];
+                                    __syncwarp();
                                     if (++slot == NST) { slot = 0; sphase ^= 1u; }
                                 }
                             }
@@ -500,7 +517,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                     zm_complete<MODE>(pl, t.nq, qlo, qhi);
                     for (int q = qlo; q < qhi; q++) {
                         const int aslot = (qbase + q) & (NACC - 1);
-                        mma_commit(accfull0 + aslot * 8);
+                        if (elect_one_sync()) mma_commit(accfull0 + aslot * 8);
                         started &= ~(1u << aslot);
                     }
                 }
