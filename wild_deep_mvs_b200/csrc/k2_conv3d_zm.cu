@@ -31,9 +31,10 @@ namespace mvsb200 {
 using namespace umma;
 
 constexpr int ZM_S1 = 0, ZM_S2 = 1, ZM_DECONV = 2;
-constexpr int ZM_EPI_WARPS = 8, ZM_PROD_WARPS = 8;
-constexpr int ZM_THREADS = (ZM_EPI_WARPS + ZM_PROD_WARPS + 1) * 32;   // 544
-constexpr int ZM_PROD_GROUP = 128;                                     // producer threads working on one stage
+constexpr int ZM_EPI_WARPS = 8, ZM_PROD_WARPS = 9;   // 18 warps with the MMA warp: at most 5 per scheduler, 96 registers each
+constexpr int ZM_THREADS = (ZM_EPI_WARPS + ZM_PROD_WARPS + 1) * 32;   // 576
+constexpr int ZM_PROD_GROUP = 96;                                      // producer threads working on one unit
+constexpr int ZM_NGROUPS = ZM_PROD_WARPS * 32 / ZM_PROD_GROUP;         // units being filled concurrently
 constexpr int ZM_HEADER_HALVES = 8;                                    // 16-byte header in front of the packed weights
 
 template <int MODE, int CT> struct ZmCfg {
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
 {
     using T = ZmCfg<MODE, CT>;
     constexpr int NC = T::NC, RA = T::RA, MT = T::MT, NACC = T::NACC, EX = T::EX;
-    constexpr int MAXST = 8;
+    constexpr int MAXST = 12;
     constexpr int NPY = (MODE == ZM_S2) ? 2 : 1, NPX = NPY;
     constexpr int TEAM_WARPS = 4 * MT, NTEAMS = ZM_EPI_WARPS / TEAM_WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                     for (int c0 = 0; c0 < nch;) {
                         const int G = zm_unit_chunks(c0, nch1, nch, 4 / NPX);
                         const int nst_unit = G * NPX;
-                        if ((un++ & 1) != group) { c0 += G; it += nst_unit; continue; }
+                        if ((un++ % ZM_NGROUPS) != group) { c0 += G; it += nst_unit; continue; }
                         const float *src;
                         int cs, cstride;
                         if (c0 < nch1) { src = p.x; cs = c0 * 8; cstride = p.Cin1; }
@@ -383,9 +384,8 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                         const float *plane = src + ((long long)t.b * p.D + gz) * p.H * p.W * cstride + cs;
                         const int lgp = (G == 4) ? 3 : (G == 2 ? 2 : 1);     // log2(16-byte pieces per voxel)
                         const int npieces = (T::EY * XV) << lgp;
-                        bool waited = false;
-                        for (int k0 = gt; k0 < npieces; k0 += BATCH * ZM_PROD_GROUP) {
-                            float4 v[BATCH];
+                        // batch of BATCH 16-byte pieces per thread: global -> registers
+                        auto load_batch = [&](int k0, float4 (&v)[BATCH]) {
 #pragma unroll
                             for (int k = 0; k < BATCH; k++) {
                                 const int idx = k0 + k * ZM_PROD_GROUP;
@@ -399,11 +399,9 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                                 if (idx < npieces && (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W)
                                     v[k] = ldg4(plane + ((long long)gy * p.W + gx) * cstride + piece * 4);
                             }
-                            if (!waited) {   // the unit's stage buffers must have been released by the MMAs that read them
-                                for (int j = 0; j < nst_unit; j++)
-                                    mbar_wait_relaxed(smem_u32(&s_empty[(it + j) % NST]), ((uint32_t)((it + j) / NST) & 1u) ^ 1u);
-                                waited = true;
-                            }
+                        };
+                        // registers -> scaled fp16 h / l pieces -> the stage buffers of the unit
+                        auto store_batch = [&](int k0, const float4 (&v)[BATCH]) {
 #pragma unroll
                             for (int k = 0; k < BATCH; k++) {
                                 const int idx = k0 + k * ZM_PROD_GROUP;
@@ -419,6 +417,22 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                                 unsigned char *dst = sA + (size_t)((it + j) % NST) * T::STAGE_BYTES + (size_t)(ly * EX + lx) * 16 + (piece & 1) * 8;
                                 *reinterpret_cast<uint2 *>(dst) = make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
                                 *reinterpret_cast<uint2 *>(dst + RA * 16) = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+                            }
+                        };
+                        // two register batches in flight: the loads of batch b+1 are issued before batch b is converted
+                        constexpr int STEP = BATCH * ZM_PROD_GROUP;
+                        float4 va[BATCH], vb[BATCH];
+                        load_batch(gt, va);
+                        if (gt + STEP < npieces) load_batch(gt + STEP, vb);
+                        // the unit's stage buffers must have been released by the MMAs that read them
+                        for (int j = 0; j < nst_unit; j++)
+                            mbar_wait_relaxed(smem_u32(&s_empty[(it + j) % NST]), ((uint32_t)((it + j) / NST) & 1u) ^ 1u);
+                        for (int k0 = gt; k0 < npieces; k0 += 2 * STEP) {
+                            store_batch(k0, va);
+                            if (k0 + 2 * STEP < npieces) load_batch(k0 + 2 * STEP, va);
+                            if (k0 + STEP < npieces) {
+                                store_batch(k0 + STEP, vb);
+                                if (k0 + 3 * STEP < npieces) load_batch(k0 + 3 * STEP, vb);
                             }
                         }
                         fence_proxy_async_smem();
@@ -613,7 +627,7 @@ template <int MODE, int CT> static size_t zm_smem_bytes(int nch, int nst)
 // number of pipeline stages that fit next to the resident weights (0: the layer does not fit this engine)
 template <int MODE, int CT> static int zm_stages(int nch)
 {
-    for (int nst = 8; nst >= 4; nst--)
+    for (int nst = 12; nst >= 4; nst--)
         if (zm_smem_bytes<MODE, CT>(nch, nst) + 2048 <= 227 * 1024) return nst;
     return 0;
 }
