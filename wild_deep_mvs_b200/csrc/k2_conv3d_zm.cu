@@ -20,7 +20,14 @@
 // As in k2_conv3d_tc.cu a (dz,dy) tap is a shifted 128-row window of the staged plane (descriptor start address) and
 // the dx taps are folded into the MMA N dimension, re-aligned in the epilogue.
 //
-// Accumulator columns of one 128-row tile: ((xs * 2) + hl) * CT + co.
+// Accumulator columns of one 128-row tile and output plane: ((xs * 2) + hl) * CT + co.
+//
+// z fold: the weight blocks of the z taps an input plane uses are concatenated on N in the order of the output planes
+// they feed (S1: kz = 2,1,0 -> planes p-2, p-1, p), and the TMEM slots of consecutive output planes are adjacent, so
+// one MMA per (dy window, row tile) updates all of them: A is read from shared memory once instead of three times and
+// the instruction count drops 3x (an N = 48 MMA costs ~80 cycles of issue/operand latency for 24 cycles of math).
+// The MMA is split only where the slot ring wraps and, in the first window of a plane, between the planes that
+// accumulate and the plane that starts (overwrite).
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -51,15 +58,20 @@ template <int MODE, int CT> struct ZmCfg {
     static constexpr int RA = ((R_NEED > ROWS ? R_NEED : ROWS) + 1) / 4 * 4 + 2;
     static constexpr int NSUB = (MODE == ZM_S2) ? 4 : 1;      // (py,px) parity sub-grids staged per plane
     static constexpr int NPXL = (MODE == ZM_S2) ? 2 : 1;      // x-parity weight variants resident per CTA
-    static constexpr int NACC = (512 / (MT * NC) >= 8) ? 8 : 4;   // accumulator planes in TMEM
-    static constexpr int ACC_COLS = MT * NC;
+    static constexpr int NACC = (512 / (MT * NC) >= 8) ? 8 : 5;   // accumulator planes in TMEM
+    // TMEM column of (row tile mt, accumulator slot s): mt * NACC * NC + s * NC -- the slots of consecutive output
+    // planes are adjacent, so ONE MMA of N = 3 * NC accumulates into all three planes an input plane contributes to
+    static constexpr int MT_COLS = NACC * NC;
     static constexpr int XROWS = MT * 128 + 8;
     static constexpr int STAGE_BYTES = 2 * RA * 16;
+    static constexpr int UNIT_STAGES = 4;                     // stage buffers of one pipeline slot (= one producer unit)
+    static constexpr int UNIT_BYTES = UNIT_STAGES * STAGE_BYTES;
     static constexpr int WBLOCK_BYTES = 2 * NC * 16;          // one (chunk, px, kz, ky) weight block
+    static constexpr int WREGION16 = 9 * WBLOCK_BYTES / 16;   // 16-byte units of one (variant, chunk) weight region
     static constexpr int X_BYTES = (NXS - 1) * (CT / 4) * XROWS * 16;   // x-shift exchange buffer of one epilogue team
     static constexpr int NTEAMS = (MT == 2) ? 1 : 2;
     static_assert(TY * EX <= MT * 128, "plane tile does not fit the MMA row tiles");
-    static_assert(NACC * ACC_COLS <= 512, "accumulators exceed TMEM");
+    static_assert(MT * MT_COLS <= 512, "accumulators exceed TMEM");
     static_assert(NC % 16 == 0 && NC <= 256, "invalid MMA N");
 };
 
@@ -73,6 +85,7 @@ struct ZmParams {
     int Cin1, Cin2, Cout;
     int relu, skip_mode;
     int tiles_x, tiles_y, nseg, zseg, ntiles, nstages;
+    int profile;
 };
 
 // ---- small PTX helpers local to this engine -------------------------------------------------------------------
@@ -162,6 +175,24 @@ template <int MODE> __device__ __forceinline__ void zm_complete(int p, int nq, i
     qlo = max(qlo, 0);
     qhi = min(qhi, nq);
 }
+// z fold tables: the output planes plane p contributes to are consecutive, q = zm_qfirst(p) + i, i < zm_nblk(p), and
+// block i of the packed weights of plane type zm_ztype(p) holds filter z index zm_zblock_kz(type, i).
+template <int MODE> __host__ __device__ constexpr int zm_ztype(int p) { return MODE == ZM_S2 ? (p & 1) : 0; }
+__host__ __device__ constexpr int zm_type_nblk(int mode, int type) { return mode == ZM_S2 ? (type ? 1 : 2) : 3; }
+__host__ __device__ constexpr int zm_zblock_kz(int mode, int type, int i)
+{
+    return mode == ZM_S1 ? 2 - i : (mode == ZM_S2 ? (type ? 1 : (i == 0 ? 2 : 0)) : i);
+}
+template <int MODE> __device__ __forceinline__ int zm_qfirst(int p)
+{
+    return MODE == ZM_S1 ? p - 2 : (MODE == ZM_S2 ? ((p & 1) ? (p - 1) >> 1 : (p >> 1) - 1) : 2 * p - 1);
+}
+// 16-byte units from the start of a (variant, chunk) weight region to the [k-plane][nblk * NC][16 B] matrix of (type, ky)
+__host__ __device__ constexpr int zm_wmat_off16(int mode, int type, int ky, int nc)
+{
+    return mode == ZM_S2 ? (type ? 12 * nc + ky * 2 * nc : ky * 4 * nc) : ky * 6 * nc;
+}
+
 // y-dimension tap options of a staged block: variant v (S1: 0; S2: parity of the staged sub-grid; DECONV: parity of the
 // output class) -> option j = (filter index, row shift)
 __host__ __device__ constexpr int zm_dim_opts(int mode, int v) { return mode == ZM_S1 ? 3 : (mode == ZM_S2 ? (v == 0 ? 2 : 1) : (v == 0 ? 1 : 2)); }
@@ -170,6 +201,14 @@ __host__ __device__ constexpr int zm_dim_k(int mode, int v, int j)
     return mode == ZM_S1 ? j : (mode == ZM_S2 ? (v == 0 ? 2 * j : 1) : (v == 0 ? 1 : (j == 0 ? 2 : 0)));
 }
 __host__ __device__ constexpr int zm_dim_shift(int mode, int v, int j) { return mode == ZM_S1 ? j : (mode == ZM_S2 ? (v == 0 ? j : 0) : (v == 0 ? 0 : j)); }
+
+// Optional in-kernel cycle accounting (debug aid, enabled by mvsb200_debug_zm_profile): CTA (0,0) adds the cycles
+// its MMA warp, first producer warp and first epilogue warp spend in each kind of wait to this buffer.
+//   [0] mma total  [1] mma wait full  [2] mma wait acc-empty  [3] mma issue   [4] stages
+//   [8] prod total [9] prod wait empty [10] prod units
+//   [16] epi total [17] epi wait acc-full [18] epi named barriers [19] epi planes
+__device__ unsigned long long g_zm_prof[32];
+static int g_zm_prof_on = 0;
 
 struct ZmTile {
     int b, zb, nq, y0, x0, cls;
@@ -207,47 +246,58 @@ __device__ __forceinline__ int zm_unit_chunks(int c, int nch1, int nch, int gmax
     return g;
 }
 
+#define ZM_T0() (prof ? clock64() : 0ll)
+#define ZM_ACC(var, t0) do { if (prof) var += clock64() - (t0); } while (0)
+
 template <int MODE, int CT>
 __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmParams p)
 {
+    const bool prof = p.profile && blockIdx.x == 0 && blockIdx.y == 0;
     using T = ZmCfg<MODE, CT>;
     constexpr int NC = T::NC, RA = T::RA, MT = T::MT, NACC = T::NACC, EX = T::EX;
-    constexpr int MAXST = 12;
+    constexpr int MAXUB = 8;
     constexpr int NPY = (MODE == ZM_S2) ? 2 : 1, NPX = NPY;
     constexpr int TEAM_WARPS = 4 * MT, NTEAMS = ZM_EPI_WARPS / TEAM_WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long s_full[MAXST], s_empty[MAXST], s_accfull[8], s_accempty[8], s_wbar;
+    __shared__ __align__(8) unsigned long long s_full[MAXUB], s_empty[MAXUB], s_accfull[8], s_accempty[8], s_wbar;
     __shared__ uint32_t s_tmem;
+    __shared__ __align__(16) float s_sc[CT], s_bi[CT];   // epilogue: y = acc * s_sc + s_bi (operand un-scaling and BN folded)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nb = blockIdx.y;
     const int nch = (p.Cin1 + p.Cin2) >> 3, nch1 = p.Cin1 >> 3;
-    const int NST = p.nstages;
+    const int NUB = p.nstages;   // unit buffers in the ring (the pipeline hands over whole units: 1 wait + 1 commit per unit)
     const int wblocks = T::NPXL * nch * 9;
     unsigned char *sW = smem_raw;
     unsigned char *sA = sW + (size_t)wblocks * T::WBLOCK_BYTES;
-    float4 *sXall = reinterpret_cast<float4 *>(sA + (size_t)NST * T::STAGE_BYTES);
+    float4 *sXall = reinterpret_cast<float4 *>(sA + (size_t)NUB * T::UNIT_BYTES);
 
     if (tid == 0) {
-        for (int i = 0; i < NST; i++) { mbar_init(smem_u32(&s_full[i]), ZM_PROD_GROUP / 32); mbar_init(smem_u32(&s_empty[i]), 1); }
+        for (int i = 0; i < NUB; i++) { mbar_init(smem_u32(&s_full[i]), ZM_PROD_GROUP / 32); mbar_init(smem_u32(&s_empty[i]), 1); }
         for (int i = 0; i < NACC; i++) { mbar_init(smem_u32(&s_accfull[i]), 1); mbar_init(smem_u32(&s_accempty[i]), TEAM_WARPS); }
         mbar_init(smem_u32(&s_wbar), ZM_PROD_WARPS);
         fence_mbar_init();
     }
     if (warp == ZM_EPI_WARPS + ZM_PROD_WARPS) tmem_alloc(smem_u32(&s_tmem), 512);
-    // staged rows beyond the plane tile are only ever read by discarded GEMM rows; give them a defined value once
-    for (int i = tid; i < NST * T::STAGE_BYTES / 16; i += ZM_THREADS) reinterpret_cast<uint4 *>(sA)[i] = make_uint4(0, 0, 0, 0);
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem = s_tmem;
-
     // operand scales
     float amax = __ldg(p.x_amax);
     if (p.x2) amax = fmaxf(amax, __ldg(p.x2_amax));
     float inv_sx;
     const float sx = pow2_scale(amax, &inv_sx);
+    if (tid < CT) {
+        const int co = nb * CT + tid;
+        const float unscale = inv_sx * __ldg(reinterpret_cast<const float *>(p.wp) + 1);   // header: {w_scale, w_inv_scale, -, -}
+        s_sc[tid] = unscale * ((p.scale && co < p.Cout) ? __ldg(p.scale + co) : 1.f);
+        s_bi[tid] = (p.bias && co < p.Cout) ? __ldg(p.bias + co) : 0.f;
+    }
+
+    // staged rows beyond the plane tile are only ever read by discarded GEMM rows; give them a defined value once
+    for (int i = tid; i < NUB * T::UNIT_BYTES / 16; i += ZM_THREADS) reinterpret_cast<uint4 *>(sA)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = s_tmem;
 
     if (warp < ZM_EPI_WARPS) {
         // =================================== epilogue warps ===================================
@@ -255,14 +305,13 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
         // MT == 1: two teams of 4 warps taking alternate planes.  A warp reads the TMEM lanes of quadrant warp % 4.
         const int quad = warp & 3, team = (MT == 2) ? 0 : (warp >> 2), mt = (MT == 2) ? (warp >> 2) : 0;
         float4 *sX = sXall + (size_t)team * (T::X_BYTES / 16);
-        const float w_inv = __ldg(reinterpret_cast<const float *>(p.wp) + 1);   // header: {w_scale, w_inv_scale, -, -}
-        const float unscale = inv_sx * w_inv;
         constexpr int C4 = CT / 4;
         const int ncol = min(CT, p.Cout - nb * CT), co0 = nb * CT;
         const int pr = mt * 128 + quad * 32 + lane;           // GEMM row of this thread within the plane tile
         const int oy_l = pr / EX, ox_l = pr % EX;
         float vmax = 0.f;
         int qg = 0;
+        long long pe_tot = ZM_T0(), pe_wait = 0, pe_bar = 0, pe_n = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             const ZmTile t = zm_decode<MODE, CT>(p, tile);
             const int ry = (t.cls >> 1) & 1, rx = t.cls & 1;
@@ -286,13 +335,16 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                     sk[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (ok && p.skip_mode != MVSB200_SKIP_NONE && c4 * 4 < ncol) sk[c4] = ldg4(p.skip + o + c4 * 4);
                 }
+                long long tq = ZM_T0();
                 mbar_wait_relaxed(smem_u32(&s_accfull[slot]), (uint32_t)(qg / NACC) & 1u);
+                ZM_ACC(pe_wait, tq);
+                pe_n++;
                 tc_fence_after_sync();
                 float r0[CT];
 #pragma unroll
                 for (int xs = 0; xs < T::NXS; xs++) {
                     float v[2 * CT];
-                    const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + slot * T::ACC_COLS + mt * NC + xs * 2 * CT;
+                    const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + mt * T::MT_COLS + slot * NC + xs * 2 * CT;
 #pragma unroll
                     for (int j = 0; j < 2 * CT; j += 16) tmem_ld16(taddr + j, v + j);
                     tmem_ld_wait();
@@ -311,7 +363,9 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&s_accempty[slot]));
+                tq = ZM_T0();
                 if (team == 0) named_bar_sync(1, TEAM_WARPS * 32); else named_bar_sync(2, TEAM_WARPS * 32);
+                ZM_ACC(pe_bar, tq);
                 if (ok) {
 #pragma unroll
                     for (int c4 = 0; c4 < C4; c4++) {
@@ -322,10 +376,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                             const float4 nbv = sX[((xs - 1) * C4 + c4) * T::XROWS + pr + xs];
                             r[0] += nbv.x; r[1] += nbv.y; r[2] += nbv.z; r[3] += nbv.w;
                         }
-                        // BN scale / bias: 16-byte loads that stay in L1 (keeping them in registers spills at CT = 16)
-                        float4 sc = make_float4(unscale, unscale, unscale, unscale), bi = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.scale) { const float4 s4 = ldg4(p.scale + co0 + c4 * 4); sc.x *= s4.x; sc.y *= s4.y; sc.z *= s4.z; sc.w *= s4.w; }
-                        if (p.bias) bi = ldg4(p.bias + co0 + c4 * 4);
+                        const float4 sc = *reinterpret_cast<const float4 *>(&s_sc[c4 * 4]), bi = *reinterpret_cast<const float4 *>(&s_bi[c4 * 4]);
                         r[0] = fmaf(r[0], sc.x, bi.x); r[1] = fmaf(r[1], sc.y, bi.y);
                         r[2] = fmaf(r[2], sc.z, bi.z); r[3] = fmaf(r[3], sc.w, bi.w);
                         if (p.skip_mode == MVSB200_SKIP_BEFORE_RELU) { r[0] += sk[c4].x; r[1] += sk[c4].y; r[2] += sk[c4].z; r[3] += sk[c4].w; }
@@ -336,13 +387,18 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                     }
                 }
                 // sX is rewritten by the team's next plane
+                tq = ZM_T0();
                 if (team == 0) named_bar_sync(1, TEAM_WARPS * 32); else named_bar_sync(2, TEAM_WARPS * 32);
+                ZM_ACC(pe_bar, tq);
             }
         }
         if (p.y_amax) {
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, m));
             if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned int *>(p.y_amax), __float_as_uint(vmax));
+        }
+        if (prof && tid == 0) {
+            g_zm_prof[16] += clock64() - pe_tot; g_zm_prof[17] += pe_wait; g_zm_prof[18] += pe_bar; g_zm_prof[19] += pe_n;
         }
     } else if (warp < ZM_EPI_WARPS + ZM_PROD_WARPS) {
         // =================================== producer warps ===================================
@@ -365,7 +421,10 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
         }
         constexpr int XV = EX * NPX;          // voxels of one staged row run (contiguous in x)
         constexpr int BATCH = 5;              // 16-byte loads in flight per thread
-        int it = 0, un = 0;
+        int un = 0;               // units so far (all groups count all units)
+        int ub = 0;               // ring position of the current unit's buffer
+        uint32_t uphase = 1;      // parity to wait for on its empty barrier (first pass: free)
+        long long pp_tot = ZM_T0(), pp_wait = 0, pp_n = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             const ZmTile t = zm_decode<MODE, CT>(p, tile);
             const int np = zm_nplanes<MODE>(t.nq);
@@ -375,76 +434,91 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                 for (int py = 0; py < NPY; py++) {
                     for (int c0 = 0; c0 < nch;) {
                         const int G = zm_unit_chunks(c0, nch1, nch, 4 / NPX);
-                        const int nst_unit = G * NPX;
-                        if ((un++ % ZM_NGROUPS) != group) { c0 += G; it += nst_unit; continue; }
+                        const int my_ub = ub;
+                        const uint32_t my_phase = uphase;
+                        if (++ub == NUB) { ub = 0; uphase ^= 1u; }
+                        c0 += G;
+                        if ((un++ % ZM_NGROUPS) != group) continue;
                         const float *src;
                         int cs, cstride;
-                        if (c0 < nch1) { src = p.x; cs = c0 * 8; cstride = p.Cin1; }
-                        else { src = p.x2; cs = (c0 - nch1) * 8; cstride = p.Cin2; }
-                        const float *plane = src + ((long long)t.b * p.D + gz) * p.H * p.W * cstride + cs;
+                        const int cb = c0 - G;   // first chunk of this unit
+                        if (cb < nch1) { src = p.x; cs = cb * 8; cstride = p.Cin1; }
+                        else { src = p.x2; cs = (cb - nch1) * 8; cstride = p.Cin2; }
                         const int lgp = (G == 4) ? 3 : (G == 2 ? 2 : 1);     // log2(16-byte pieces per voxel)
-                        const int npieces = (T::EY * XV) << lgp;
+                        const int nvox = T::EY * XV;
+                        // A thread's pieces are idx = gt + k * ZM_PROD_GROUP; the group size is a multiple of the pieces
+                        // per voxel, so the piece within the voxel -- and with it the chunk, the 8-byte half and (S1,
+                        // DECONV) the stage buffer -- is the same for every k: everything but the voxel is hoisted.
+                        const int piece = gt & ((1 << lgp) - 1);
+                        const int vstep = ZM_PROD_GROUP >> lgp;
+                        const float *plane = src + ((long long)t.b * p.D + gz) * p.H * p.W * cstride + cs + piece * 4;
+                        uint32_t dst_px[NPX];                                  // shared address of row 0 in the stage(s) of this piece
+#pragma unroll
+                        for (int px = 0; px < NPX; px++)
+                            dst_px[px] = smem_u32(sA) + my_ub * T::UNIT_BYTES + ((piece >> 1) * NPX + px) * T::STAGE_BYTES + (piece & 1) * 8;
+                        const int ybase = (MODE == ZM_S1) ? t.y0 - 1 : (MODE == ZM_S2 ? 2 * t.y0 - 1 + py : t.y0);
+                        const int xbase = (MODE == ZM_S1) ? t.x0 - 1 : (MODE == ZM_S2 ? 2 * t.x0 - 1 : t.x0);
+                        const unsigned rowpitch = (unsigned)p.W * cstride;
                         // batch of BATCH 16-byte pieces per thread: global -> registers
-                        auto load_batch = [&](int k0, float4 (&v)[BATCH]) {
+                        auto load_batch = [&](int v0, float4 (&v)[BATCH]) {
 #pragma unroll
                             for (int k = 0; k < BATCH; k++) {
-                                const int idx = k0 + k * ZM_PROD_GROUP;
-                                const int piece = idx & ((1 << lgp) - 1), vx = idx >> lgp;
+                                const int vx = v0 + k * vstep;
                                 const int lxv = vx % XV, ly = vx / XV;
-                                int gy, gx;
-                                if (MODE == ZM_S1) { gy = t.y0 - 1 + ly; gx = t.x0 - 1 + lxv; }
-                                else if (MODE == ZM_S2) { gy = 2 * (t.y0 + ly) - 1 + py; gx = 2 * t.x0 - 1 + lxv; }
-                                else { gy = t.y0 + ly; gx = t.x0 + lxv; }
+                                const int gy = ybase + ((MODE == ZM_S2) ? 2 * ly : ly), gx = xbase + lxv;
                                 v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (idx < npieces && (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W)
-                                    v[k] = ldg4(plane + ((long long)gy * p.W + gx) * cstride + piece * 4);
+                                if (vx < nvox && (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W)
+                                    v[k] = ldg4(plane + ((unsigned)gy * rowpitch + (unsigned)gx * cstride));
                             }
                         };
                         // registers -> scaled fp16 h / l pieces -> the stage buffers of the unit
-                        auto store_batch = [&](int k0, const float4 (&v)[BATCH]) {
+                        auto store_batch = [&](int v0, const float4 (&v)[BATCH]) {
 #pragma unroll
                             for (int k = 0; k < BATCH; k++) {
-                                const int idx = k0 + k * ZM_PROD_GROUP;
-                                if (idx >= npieces) break;
-                                const int piece = idx & ((1 << lgp) - 1), vx = idx >> lgp;
+                                const int vx = v0 + k * vstep;
+                                if (vx >= nvox) break;
                                 const int lxv = vx % XV, ly = vx / XV;
                                 const int px = (NPX == 2) ? (lxv & 1) : 0, lx = (NPX == 2) ? (lxv >> 1) : lxv;
-                                const int j = (piece >> 1) * NPX + px;          // stage of the unit this piece belongs to
                                 const float f0 = v[k].x * sx, f1 = v[k].y * sx, f2 = v[k].z * sx, f3 = v[k].w * sx;
                                 const __half2 h01 = __floats2half2_rn(f0, f1), h23 = __floats2half2_rn(f2, f3);
                                 const float2 g01 = __half22float2(h01), g23 = __half22float2(h23);
                                 const __half2 l01 = __floats2half2_rn(f0 - g01.x, f1 - g01.y), l23 = __floats2half2_rn(f2 - g23.x, f3 - g23.y);
-                                unsigned char *dst = sA + (size_t)((it + j) % NST) * T::STAGE_BYTES + (size_t)(ly * EX + lx) * 16 + (piece & 1) * 8;
-                                *reinterpret_cast<uint2 *>(dst) = make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
-                                *reinterpret_cast<uint2 *>(dst + RA * 16) = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+                                const uint32_t dst = ((NPX == 2 && px) ? dst_px[NPX - 1] : dst_px[0]) + (ly * EX + lx) * 16;
+                                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(*reinterpret_cast<const uint32_t *>(&h01)),
+                                             "r"(*reinterpret_cast<const uint32_t *>(&h23)) : "memory");
+                                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + RA * 16), "r"(*reinterpret_cast<const uint32_t *>(&l01)),
+                                             "r"(*reinterpret_cast<const uint32_t *>(&l23)) : "memory");
                             }
                         };
                         // two register batches in flight: the loads of batch b+1 are issued before batch b is converted
-                        constexpr int STEP = BATCH * ZM_PROD_GROUP;
+                        const int STEP = BATCH * vstep;
+                        const int v00 = gt >> lgp;
                         float4 va[BATCH], vb[BATCH];
-                        load_batch(gt, va);
-                        if (gt + STEP < npieces) load_batch(gt + STEP, vb);
-                        // the unit's stage buffers must have been released by the MMAs that read them
-                        for (int j = 0; j < nst_unit; j++)
-                            mbar_wait_relaxed(smem_u32(&s_empty[(it + j) % NST]), ((uint32_t)((it + j) / NST) & 1u) ^ 1u);
-                        for (int k0 = gt; k0 < npieces; k0 += 2 * STEP) {
-                            store_batch(k0, va);
-                            if (k0 + 2 * STEP < npieces) load_batch(k0 + 2 * STEP, va);
-                            if (k0 + STEP < npieces) {
-                                store_batch(k0 + STEP, vb);
-                                if (k0 + 3 * STEP < npieces) load_batch(k0 + 3 * STEP, vb);
+                        load_batch(v00, va);
+                        if (v00 + STEP < nvox) load_batch(v00 + STEP, vb);
+                        // the unit's buffer must have been released by the MMAs that read it
+                        {
+                            const long long tq = ZM_T0();
+                            mbar_wait_relaxed(smem_u32(&s_empty[my_ub]), my_phase);
+                            ZM_ACC(pp_wait, tq);
+                            pp_n++;
+                        }
+                        for (int v0 = v00; v0 < nvox; v0 += 2 * STEP) {
+                            store_batch(v0, va);
+                            if (v0 + 2 * STEP < nvox) load_batch(v0 + 2 * STEP, va);
+                            if (v0 + STEP < nvox) {
+                                store_batch(v0 + STEP, vb);
+                                if (v0 + 3 * STEP < nvox) load_batch(v0 + 3 * STEP, vb);
                             }
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0)
-                            for (int j = 0; j < nst_unit; j++) mbar_arrive(smem_u32(&s_full[(it + j) % NST]));
-                        c0 += G;
-                        it += nst_unit;
+                        if (lane == 0) mbar_arrive(smem_u32(&s_full[my_ub]));
                     }
                 }
             }
         }
+        if (prof && ptid == 0) { g_zm_prof[8] += clock64() - pp_tot; g_zm_prof[9] += pp_wait; g_zm_prof[10] += pp_n; }
     } else {
         // =================================== MMA issuer ===================================
         // ONE thread issues every MMA of the CTA, so its instruction stream is the pacing item of the whole pipeline:
@@ -453,17 +527,17 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
         // (warp-uniform) control flow and waits; only the tcgen05 instructions are predicated on the elected lane, which
         // keeps descriptors in uniform registers instead of a per-instruction leader-election loop.
         {
-            constexpr uint32_t idesc = idesc_f16(128, NC);
             mbar_wait(smem_u32(&s_wbar), 0);
             tc_fence_after_sync();
             const uint32_t a_hi = (uint32_t)(smem_desc(0, RA * 16, 128) >> 32), b_hi = (uint32_t)(smem_desc(0, NC * 16, 128) >> 32);
-            const uint32_t a_lo0 = (uint32_t)smem_desc(smem_u32(sA), RA * 16, 128), b_lo0 = (uint32_t)smem_desc(smem_u32(sW), NC * 16, 128);
+            const uint32_t a_lo0 = (uint32_t)smem_desc(smem_u32(sA), RA * 16, 128), b_lo0 = (uint32_t)smem_desc(smem_u32(sW), 0, 128);
             const uint32_t full0 = smem_u32(&s_full[0]), empty0 = smem_u32(&s_empty[0]);
             const uint32_t accfull0 = smem_u32(&s_accfull[0]), accempty0 = smem_u32(&s_accempty[0]);
-            int slot = 0;            // stage ring position
-            uint32_t sphase = 0;     // parity of the current pass over the stage ring
+            int ub = 0;              // unit-buffer ring position
+            uint32_t uphase = 0;     // parity of the current pass over the ring
             int qbase = 0;           // output planes of the tiles already issued (accumulator ring position = qbase + q)
             uint32_t started = 0;    // bit per accumulator slot: the plane in it has received its first MMA
+            long long pm_tot = ZM_T0(), pm_full = 0, pm_acc = 0, pm_issue = 0, pm_n = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 const ZmTile t = zm_decode<MODE, CT>(p, tile);
                 const int np = zm_nplanes<MODE>(t.nq);
@@ -471,71 +545,119 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                 for (int pl = 0; pl < np; pl++) {
                     const int gz = zm_zin<MODE>(t.zb, pl);
                     if ((unsigned)gz < (unsigned)p.D) {
-                        // accumulator slots of the (up to 3) output planes this input plane contributes to
-                        int cq[3], ckz[3];
-                        uint32_t cd[3];
-                        int ncn = 0;
+                        // Output planes fed by this input plane: q = qf + i for i in [i0, i1).  Their accumulator slots
+                        // are consecutive ring positions; cut the range into runs of adjacent TMEM columns.
+                        //   runs "F": first window of the plane -- also cut between planes that accumulate and planes
+                        //             that start (their first MMA overwrites);   runs "R": every other window.
+                        const int ztype = zm_ztype<MODE>(pl), nblk = zm_type_nblk(MODE, ztype);
+                        const int qf = zm_qfirst<MODE>(pl);
+                        const int i0 = max(0, -qf), i1 = min(nblk, t.nq - qf);
+                        // (scalars, not arrays: the issue loop below must not touch local memory)
+                        uint32_t fd0 = 0, fb0 = 0, fn0 = 0, fa0 = 0, fd1 = 0, fb1 = 0, fn1 = 0, fa1 = 0, fd2 = 0, fb2 = 0, fn2 = 0, fa2 = 0;
+                        uint32_t rd0 = 0, rb0 = 0, rn0 = 0, rd1 = 0, rb1 = 0, rn1 = 0;
+                        int nf = 0, nr = 0;
+                        uint32_t fcur_n = 0, fcur_a = 0, rcur_n = 0;
 #pragma unroll
-                        for (int j = 0; j < 3; j++) {
-                            if (j >= zm_ncontrib<MODE>(pl)) continue;
-                            int q, kz;
-                            zm_contrib<MODE>(pl, j, q, kz);
-                            if (q < 0 || q >= t.nq) continue;
-                            const int qg = qbase + q, aslot = qg & (NACC - 1);
-                            if (!(started >> aslot & 1u)) {   // first touch: the epilogue must have drained the slot
+                        for (int i = 0; i < 3; i++) {
+                            if (i < i0 || i >= i1) continue;
+                            const int qg = qbase + qf + i, aslot = qg % NACC;
+                            const uint32_t st = (started >> aslot) & 1u;
+                            if (!st) {   // drained by the epilogue?
+                                const long long tq = ZM_T0();
                                 mbar_wait(accempty0 + aslot * 8, ((uint32_t)(qg / NACC) & 1u) ^ 1u);
+                                ZM_ACC(pm_acc, tq);
                             }
-                            cq[ncn] = aslot; ckz[ncn] = kz; cd[ncn] = tmem + aslot * T::ACC_COLS;
-                            ncn++;
+                            // (an MMA is at most 256 columns wide)
+                            if (nr == 0 || aslot == 0 || rcur_n + NC > 256) {
+                                if (nr == 0) { rd0 = aslot * NC; rb0 = i * NC; } else { rd1 = aslot * NC; rb1 = i * NC; }
+                                nr++;
+                                rcur_n = 0;
+                            }
+                            rcur_n += NC;
+                            if (nr == 1) rn0 = rcur_n; else rn1 = rcur_n;
+                            if (nf == 0 || aslot == 0 || st != fcur_a || fcur_n + NC > 256) {
+                                if (nf == 0) { fd0 = aslot * NC; fb0 = i * NC; fa0 = st; }
+                                else if (nf == 1) { fd1 = aslot * NC; fb1 = i * NC; fa1 = st; }
+                                else { fd2 = aslot * NC; fb2 = i * NC; fa2 = st; }
+                                nf++;
+                                fcur_n = 0;
+                                fcur_a = st;
+                            }
+                            fcur_n += NC;
+                            if (nf == 1) fn0 = fcur_n; else if (nf == 2) fn1 = fcur_n; else fn2 = fcur_n;
+                            started |= 1u << aslot;
                         }
                         tc_fence_after_sync();
+                        const uint32_t b_lbo = (uint32_t)(nblk * NC) << 16;   // LBO field: k-plane stride of the folded B matrix
+                        const uint32_t id0 = idesc_f16(128, rn0), id1 = idesc_f16(128, rn1);
+                        bool first = true;
                         for (int py = 0; py < NPY; py++) {
                             const int vy = (MODE == ZM_S2) ? py : vy_cls;
-                            for (int c = 0; c < nch; c++) {
+                            for (int c0 = 0; c0 < nch;) {
+                                const int G = zm_unit_chunks(c0, nch1, nch, 4 / NPX);
+                                long long tq = ZM_T0();
+                                mbar_wait(full0 + ub * 8, uphase);
+                                ZM_ACC(pm_full, tq);
+                                pm_n++;
+                                tc_fence_after_sync();
+                                tq = ZM_T0();
+                                if (elect_one_sync()) {
+                                    uint32_t a_lo = a_lo0 + ub * (T::UNIT_BYTES / 16);
+                                    for (int cc = 0; cc < G; cc++) {
 #pragma unroll
-                                for (int px = 0; px < NPX; px++) {
-                                    mbar_wait(full0 + slot * 8, sphase);
-                                    tc_fence_after_sync();
-                                    const uint32_t a_lo = a_lo0 + slot * (T::STAGE_BYTES / 16);
-                                    const uint32_t b_c = b_lo0 + ((px * nch + c) * 9) * (T::WBLOCK_BYTES / 16);
-                                    if (elect_one_sync()) {
-#pragma unroll
-                                        for (int j = 0; j < 3; j++) {
-                                            if (j >= ncn) continue;
-                                            const uint32_t b_z = b_c + ckz[j] * 3 * (T::WBLOCK_BYTES / 16);
-                                            uint32_t acc = (started >> cq[j]) & 1u;
+                                        for (int px = 0; px < NPX; px++, a_lo += T::STAGE_BYTES / 16) {
+                                            const uint32_t b_c = b_lo0 + b_lbo + (px * nch + c0 + cc) * T::WREGION16;
 #pragma unroll
                                             for (int jy = 0; jy < 3; jy++) {
                                                 if (jy >= zm_dim_opts(MODE, vy)) continue;
-                                                const int ky = zm_dim_k(MODE, vy, jy);
-                                                const uint32_t shift = zm_dim_shift(MODE, vy, jy) * EX;
-                                                const uint64_t bdesc = ((uint64_t)b_hi << 32) | (b_z + ky * (T::WBLOCK_BYTES / 16));
-#pragma unroll
-                                                for (int m = 0; m < MT; m++)
-                                                    mma_f16(cd[j] + m * NC, ((uint64_t)a_hi << 32) | (a_lo + m * 128 + shift), bdesc, idesc, acc);
-                                                acc = 1u;
+                                                const uint32_t b_y = b_c + zm_wmat_off16(MODE, ztype, zm_dim_k(MODE, vy, jy), NC);
+                                                const uint32_t a_y = a_lo + zm_dim_shift(MODE, vy, jy) * EX;
+                                                const uint64_t ad0 = ((uint64_t)a_hi << 32) | a_y, ad1 = ((uint64_t)a_hi << 32) | (a_y + 128);
+                                                if (first) {
+                                                    first = false;
+                                                    mma_f16(tmem + fd0, ad0, ((uint64_t)b_hi << 32) | (b_y + fb0), idesc_f16(128, fn0), fa0);
+                                                    if (MT == 2) mma_f16(tmem + T::MT_COLS + fd0, ad1, ((uint64_t)b_hi << 32) | (b_y + fb0), idesc_f16(128, fn0), fa0);
+                                                    if (nf > 1) {
+                                                        mma_f16(tmem + fd1, ad0, ((uint64_t)b_hi << 32) | (b_y + fb1), idesc_f16(128, fn1), fa1);
+                                                        if (MT == 2) mma_f16(tmem + T::MT_COLS + fd1, ad1, ((uint64_t)b_hi << 32) | (b_y + fb1), idesc_f16(128, fn1), fa1);
+                                                    }
+                                                    if (nf > 2) {
+                                                        mma_f16(tmem + fd2, ad0, ((uint64_t)b_hi << 32) | (b_y + fb2), idesc_f16(128, fn2), fa2);
+                                                        if (MT == 2) mma_f16(tmem + T::MT_COLS + fd2, ad1, ((uint64_t)b_hi << 32) | (b_y + fb2), idesc_f16(128, fn2), fa2);
+                                                    }
+                                                } else {
+                                                    mma_f16(tmem + rd0, ad0, ((uint64_t)b_hi << 32) | (b_y + rb0), id0, 1u);
+                                                    if (MT == 2) mma_f16(tmem + T::MT_COLS + rd0, ad1, ((uint64_t)b_hi << 32) | (b_y + rb0), id0, 1u);
+                                                    if (nr > 1) {
+                                                        mma_f16(tmem + rd1, ad0, ((uint64_t)b_hi << 32) | (b_y + rb1), id1, 1u);
+                                                        if (MT == 2) mma_f16(tmem + T::MT_COLS + rd1, ad1, ((uint64_t)b_hi << 32) | (b_y + rb1), id1, 1u);
+                                                    }
+                                                }
                                             }
                                         }
-                                        mma_commit(empty0 + slot * 8);
                                     }
-#pragma unroll
-                                    for (int j = 0; j < 3; j++)
-                                        if (j < ncn) started |= 1u << cq[j];
-                                    __syncwarp();
-                                    if (++slot == NST) { slot = 0; sphase ^= 1u; }
+                                    mma_commit(empty0 + ub * 8);
                                 }
+                                first = false;
+                                __syncwarp();
+                                ZM_ACC(pm_issue, tq);
+                                if (++ub == NUB) { ub = 0; uphase ^= 1u; }
+                                c0 += G;
                             }
                         }
                     }
                     int qlo, qhi;
                     zm_complete<MODE>(pl, t.nq, qlo, qhi);
                     for (int q = qlo; q < qhi; q++) {
-                        const int aslot = (qbase + q) & (NACC - 1);
+                        const int aslot = (qbase + q) % NACC;
                         if (elect_one_sync()) mma_commit(accfull0 + aslot * 8);
                         started &= ~(1u << aslot);
                     }
                 }
                 qbase += t.nq;
+            }
+            if (prof && lane == 0) {
+                g_zm_prof[0] += clock64() - pm_tot; g_zm_prof[1] += pm_full; g_zm_prof[2] += pm_acc; g_zm_prof[3] += pm_issue; g_zm_prof[4] += pm_n;
             }
         }
         __syncwarp();
@@ -547,7 +669,8 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
 
 // ---- weight packing ----------------------------------------------------------------------------------------------
 // layout: header {w_scale, w_inv_scale, 0, 0} (fp32, 16 bytes) then
-//   [N block][x-parity variant (S2: px, DECONV: rx; S1: single)][chunk][kz][ky][k-plane 2][NC][8 halves]
+//   [N block][x-parity variant (S2: px, DECONV: rx; S1: single)][chunk] regions of 9 * 2 * NC * 16 bytes, each holding
+//   per (plane type, ky) one matrix [k-plane 2][z blocks * NC][8 halves] at zm_wmat_off16 (z fold, see the top)
 struct ZmPackParams {
     const float *w;
     __half *wp;
@@ -588,20 +711,26 @@ __host__ __device__ constexpr int zm_kx_of(int mode, int var, int xs)
 
 __global__ void k2_zm_pack_kernel(const ZmPackParams p)
 {
-    // one block per (nb, var, c, kz, ky); threads over (k-plane, column, element)
+    // one block per (nb, var, c, plane type, ky); threads over (k-plane, z block, column, element)
     int id = blockIdx.x;
+    const int ntype = (p.mode == ZM_S2) ? 2 : 1;
     const int ky = id % 3; id /= 3;
-    const int kz = id % 3; id /= 3;
+    const int type = id % ntype; id /= ntype;
     const int c = id % p.nch; id /= p.nch;
     const int var = id % p.nvar;
     const int nb = id / p.nvar;
+    const int nblk = zm_type_nblk(p.mode, type);
     const float s = reinterpret_cast<const float *>(p.wp)[0];
-    __half *dst = p.wp + ZM_HEADER_HALVES + (size_t)blockIdx.x * (2 * p.NC * 8);
-    for (int i = threadIdx.x; i < 2 * p.NC * 8; i += blockDim.x) {
+    const size_t region = (size_t)((nb * p.nvar + var) * p.nch + c) * (9 * 2 * p.NC * 8);   // halves
+    __half *dst = p.wp + ZM_HEADER_HALVES + region + (size_t)zm_wmat_off16(p.mode, type, ky, p.NC) * 8;
+    const int rows = nblk * p.NC;
+    for (int i = threadIdx.x; i < 2 * rows * 8; i += blockDim.x) {
         const int e = i & 7;
         int r = i >> 3;
-        const int col = r % p.NC;
-        const int kp = r / p.NC;
+        const int row = r % rows;
+        const int kp = r / rows;
+        const int col = row % p.NC, blk = row / p.NC;
+        const int kz = zm_zblock_kz(p.mode, type, blk);
         const int co_l = col % p.CT, g = col / p.CT;
         const int hl = g & 1, xs = g >> 1;
         const int kx = zm_kx_of(p.mode, var, xs);
@@ -621,13 +750,13 @@ static int zm_nvar(int mode) { return mode == ZM_S1 ? 1 : 2; }
 template <int MODE, int CT> static size_t zm_smem_bytes(int nch, int nst)
 {
     using T = ZmCfg<MODE, CT>;
-    return (size_t)T::NPXL * nch * 9 * T::WBLOCK_BYTES + (size_t)nst * T::STAGE_BYTES + (size_t)T::NTEAMS * T::X_BYTES;
+    return (size_t)T::NPXL * nch * 9 * T::WBLOCK_BYTES + (size_t)nst * T::UNIT_BYTES + (size_t)T::NTEAMS * T::X_BYTES;
 }
 
-// number of pipeline stages that fit next to the resident weights (0: the layer does not fit this engine)
+// number of unit buffers that fit next to the resident weights (0: the layer does not fit this engine)
 template <int MODE, int CT> static int zm_stages(int nch)
 {
-    for (int nst = 12; nst >= 4; nst--)
+    for (int nst = 6; nst >= 2; nst--)
         if (zm_smem_bytes<MODE, CT>(nch, nst) + 2048 <= 227 * 1024) return nst;
     return 0;
 }
@@ -723,6 +852,25 @@ extern "C" int mvsb200_absmax(const float *x, long long n, float *amax, mvsb200_
     return check_launch("k2_zm_absmax_kernel");
 }
 
+// Debug aid (not part of the drop-in surface): enable != 0 switches the in-kernel cycle accounting on and zeroes the
+// counters; with `out` non-null the 32 counters are copied to host memory (synchronises the device).
+extern "C" MVSB200_API int mvsb200_debug_zm_profile(int enable, unsigned long long *out)
+{
+    if (out && cudaMemcpyFromSymbol(out, g_zm_prof, sizeof(unsigned long long) * 32) != cudaSuccess) {
+        set_error("debug_zm_profile: cudaMemcpyFromSymbol failed");
+        return MVSB200_E_CUDA;
+    }
+    g_zm_prof_on = enable;
+    if (enable) {
+        static const unsigned long long zeros[32] = {0};
+        if (cudaMemcpyToSymbol(g_zm_prof, zeros, sizeof(zeros)) != cudaSuccess) {
+            set_error("debug_zm_profile: cudaMemcpyToSymbol failed");
+            return MVSB200_E_CUDA;
+        }
+    }
+    return MVSB200_OK;
+}
+
 extern "C" int mvsb200_conv3d_zm_supported(const mvsb200_conv3d_desc *d)
 {
     return d && zm_shape_ok(d) ? 1 : 0;
@@ -751,7 +899,7 @@ extern "C" int mvsb200_conv3d_zm_pack(const mvsb200_conv3d_desc *d, const float 
     int rc = mvsb200_absmax(w, 27ll * p.Cin * p.Cout, reinterpret_cast<float *>(packed), stream);
     if (rc) return rc;
     k2_zm_header_kernel<<<1, 1, 0, st>>>(reinterpret_cast<float *>(packed));
-    k2_zm_pack_kernel<<<nblocks * p.nvar * p.nch * 9, 256, 0, st>>>(p);
+    k2_zm_pack_kernel<<<nblocks * p.nvar * p.nch * (p.mode == ZM_S2 ? 2 : 1) * 3, 256, 0, st>>>(p);
     return check_launch("k2_zm_pack_kernel");
 }
 
@@ -776,6 +924,7 @@ extern "C" int mvsb200_conv3d_zm(const mvsb200_conv3d_desc *d, const float *x, c
     p.Cin1 = d->Cin; p.Cin2 = d->Cin2; p.Cout = d->Cout;
     p.relu = d->relu; p.skip_mode = d->skip_mode;
     p.tiles_x = p.tiles_y = p.nseg = p.zseg = p.ntiles = p.nstages = 0;
+    p.profile = g_zm_prof_on;
     static int sm_count = 0;
     if (!sm_count) {
         int dev = 0;
