@@ -171,6 +171,15 @@ MVSB200_API int mvsb200_conv3d_zm(const mvsb200_conv3d_desc *desc, const float *
                                   const float *scale, const float *bias, const float *skip, float *y,
                                   const float *x_amax, const float *x2_amax, float *y_amax, mvsb200_stream_t stream);
 
+/* K2 single-output-channel head (3x3x3, stride 1, Cout == 1, Cin in {8,16,24,32}; MVSNet `prob`, Vis-MVSNet
+ * `final_conv`, CVP `prob0`: models/MVSNet/model.py:72, VisMVSNet/model_cas.py:44,61, CVP_MVSNet/models/net.py:67) on the
+ * CUDA cores in fp32: y = act(conv * scale + bias).  The weights are passed on the HOST (w_host: 27*Cin floats,
+ * tap-major [27][Cin]) because they are handed to the kernel as launch parameters (constant bank); scale / bias are host
+ * scalars.  x [B,D,H,W,Cin] device, y [B,D,H,W] device. */
+MVSB200_API int mvsb200_conv3d_c1_supported(const mvsb200_conv3d_desc *desc);
+MVSB200_API int mvsb200_conv3d_c1(const mvsb200_conv3d_desc *desc, const float *x, const float *w_host, float scale, float bias,
+                                  float *y, mvsb200_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * K3: softmax over D + depth regression + confidence (+ entropy, + probability volume).
  * Replaces F.softmax + depth_regression (+ photometric confidence): models/MVSNet/model.py:207-215,

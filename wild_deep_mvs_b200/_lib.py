@@ -61,6 +61,8 @@ SIGNATURES = {
     "mvsb200_conv3d_zm_packed_bytes": (ctypes.c_longlong, [ctypes.POINTER(Conv3dDesc)]),
     "mvsb200_conv3d_zm_pack": (_i, [ctypes.POINTER(Conv3dDesc), _vp, _vp, _vp]),
     "mvsb200_conv3d_zm": (_i, [ctypes.POINTER(Conv3dDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvsb200_conv3d_c1_supported": (_i, [ctypes.POINTER(Conv3dDesc)]),
+    "mvsb200_conv3d_c1": (_i, [ctypes.POINTER(Conv3dDesc), _vp, ctypes.POINTER(ctypes.c_float), ctypes.c_float, ctypes.c_float, _vp, _vp]),
     "mvsb200_depth_regress": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "mvsb200_vis_fuse": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }

@@ -201,6 +201,17 @@ class PackedConv:
             self.bias = conv_bias.detach().float().contiguous() if conv_bias is not None else None
         self._tc_packed = None
         self._zm_packed = None
+        self._c1_host = None
+
+    def c1_host(self):
+        """Host copies for the single-output-channel head kernel: (ctypes float array [27*Cin], scale, bias)."""
+        if self._c1_host is None:
+            w = self.w.reshape(-1).cpu()
+            arr = (ctypes.c_float * w.numel())(*w.tolist())
+            scale = float(self.scale.cpu()[0]) if self.scale is not None else 1.0
+            bias = float(self.bias.cpu()[0]) if self.bias is not None else 0.0
+            self._c1_host = (arr, scale, bias)
+        return self._c1_host
 
     def zm_packed(self, desc):
         """Weights scaled by a power of two, split into two fp16 pieces and laid out as kind::f16 B operands for the
@@ -261,6 +272,12 @@ def conv3d(x, layer, x2=None, skip=None, engine=None, out=None, amax=None):
     if skip is not None:
         _dev_f32(skip, "skip")
         assert skip.shape == y.shape, (skip.shape, y.shape)
+    if engine in ("zm", "tc") and x2 is None and skip is None and lib.mvsb200_conv3d_c1_supported(ctypes.byref(desc)):
+        # Cout == 1 heads: CUDA cores, fp32, weights as launch parameters
+        w_host, scale, bias = layer.c1_host()
+        L.check(lib.mvsb200_conv3d_c1(ctypes.byref(desc), _ptr(x), w_host, ctypes.c_float(scale), ctypes.c_float(bias), _ptr(y),
+                                      _stream()), "mvsb200_conv3d_c1")
+        return y
     if engine == "zm" and x.device == layer.w.device and lib.mvsb200_conv3d_zm_supported(ctypes.byref(desc)):
         if amax is None:
             amax = torch.zeros(1, device=x.device, dtype=torch.float32)
