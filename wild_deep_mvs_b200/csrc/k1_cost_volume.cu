@@ -1,8 +1,9 @@
 // K1: fused homography warp + cross-view aggregation (variance / softmin / group correlation).
 //
 // Layout: features NHWC so that each bilinear tap is one contiguous C*4-byte vector; a group of
-// LPV = C/4 lanes owns one reference pixel, each lane one float4 of channels.  A warp therefore covers
-// 32/LPV adjacent pixels and every tap is a 16-byte load per lane, fully coalesced per pixel.
+// LPV = C/8 lanes owns one reference pixel, each lane 8 channels (two float4).  A warp therefore covers
+// 32/LPV adjacent pixels and every tap is two 16-byte loads per lane, fully coalesced per pixel.  All per-channel
+// arithmetic runs as packed fp32 pairs (FFMA2), and 8 channels per lane halve the shuffles per channel.
 // The depth axis is walked in chunks of DCH hypotheses whose running aggregates stay in registers while
 // the source views are visited one after the other (view-outer, depth-inner), so nothing C-wide except
 // the final cost volume is ever written.  The projection / tap geometry of a (pixel, hypothesis, view) does not
@@ -17,7 +18,7 @@
 
 namespace mvsb200 {
 
-constexpr int K1_DCH = 8;       // hypotheses per thread
+constexpr int K1_DCH = 4;       // hypotheses per thread (x 8 channels x {M1, M2} = 64 accumulator registers)
 constexpr int K1_THREADS = 256;
 
 struct K1Params {
@@ -92,10 +93,24 @@ __device__ __forceinline__ PackedTaps pack_taps(const Taps &t)
     return q;
 }
 
-template <int C, int GEOM, int AGG>
-__global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Params p)
+// Packed fp32 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per instruction, same rounding
+// as the scalar forms) over the channel pairs a lane owns.
+struct F8 {   // 8 channels of one lane
+    float2 v[4];
+};
+__device__ __forceinline__ F8 ld8(const float *p)
 {
-    constexpr int LPV = C / 4;              // lanes per voxel
+    const float4 a = ldg4(p), b = ldg4(p + 4);
+    F8 r;
+    r.v[0] = make_float2(a.x, a.y); r.v[1] = make_float2(a.z, a.w);
+    r.v[2] = make_float2(b.x, b.y); r.v[3] = make_float2(b.z, b.w);
+    return r;
+}
+
+template <int C, int GEOM, int AGG>
+__global__ void __launch_bounds__(K1_THREADS, 2) k1_cost_volume_kernel(const K1Params p)
+{
+    constexpr int LPV = C / 8;              // lanes per voxel, each owning 8 channels (two 16-byte vectors per tap)
     constexpr int VPB = K1_THREADS / LPV;   // pixels per block
     constexpr int KPL = K1_DCH / LPV;       // hypotheses whose geometry each lane of a pixel group computes
     static_assert(K1_DCH % LPV == 0, "depth chunk must split evenly over the lanes of a pixel group");
@@ -113,7 +128,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
     const long long pix = active ? pix_raw : HW - 1;  // so every shuffle below runs with the full warp
     const int y = (int)(pix / p.W), x = (int)(pix % p.W);
 
-    const float4 r = ldg4(p.ref + ((long long)b * HW + pix) * C + sub * 4);
+    const F8 r = ld8(p.ref + ((long long)b * HW + pix) * C + sub * 8);
     const float interval = (p.depth_mode >= MVSB200_DEPTH_START) ? __ldg(p.interval + b) : 0.f;
 
     // The projection of a (pixel, hypothesis, view) is the same for every channel: lane `sub` of the pixel group
@@ -125,16 +140,19 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
         dv[j] = hypothesis(p.depth_mode, p.depth, interval, b, d, p.D, HW, pix);
     }
 
-    float4 acc1[K1_DCH], acc2[K1_DCH];
+    float2 acc1[K1_DCH][4], acc2[K1_DCH][4];
     float sum_exp[K1_DCH];
 #pragma unroll
     for (int k = 0; k < K1_DCH; k++) {
-        if (AGG == MVSB200_AGG_VARIANCE || AGG == MVSB200_AGG_VARIANCE_MEAN) {
-            acc1[k] = r;
-            acc2[k] = make_float4(r.x * r.x, r.y * r.y, r.z * r.z, r.w * r.w);
-        } else {
-            acc1[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            acc2[k] = acc1[k];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (AGG == MVSB200_AGG_VARIANCE || AGG == MVSB200_AGG_VARIANCE_MEAN) {
+                acc1[k][q] = r.v[q];
+                acc2[k][q] = __fmul2_rn(r.v[q], r.v[q]);
+            } else {
+                acc1[k][q] = make_float2(0.f, 0.f);
+                acc2[k][q] = acc1[k][q];
+            }
         }
         sum_exp[k] = 0.f;
     }
@@ -184,9 +202,11 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
         }
 
         // Consecutive hypotheses of a pixel move along the epipolar line by a fraction of a pixel, so they mostly
-        // fall into the same 2x2 tap cell: the four 16-byte taps stay in registers until the cell changes.
+        // fall into the same 2x2 tap cell: the four 32-byte taps stay in registers until the cell changes.
         int cur_cell = -1;
-        float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta, tc = ta, td = ta;
+        F8 ta, tb, tc, td;
+#pragma unroll
+        for (int q = 0; q < 4; q++) ta.v[q] = tb.v[q] = tc.v[q] = td.v[q] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < K1_DCH; k++) {
             const int owner = k % LPV, j = k / LPV;
@@ -197,39 +217,58 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
             const float w11 = __shfl_sync(0xffffffffu, own[j].w11, owner, LPV);
             if (cell != cur_cell) {
                 cur_cell = cell;
-                const unsigned o00 = (unsigned)(cell & 0x1fffffff) * C + sub * 4;
+                const unsigned o00 = (unsigned)(cell & 0x1fffffff) * C + sub * 8;
                 const unsigned ox = ((cell >> 29) & 1) * C, oy = ((cell >> 30) & 1) * (unsigned)(Ws * C);
-                ta = ldg4(map + o00);
-                tb = ldg4(map + (o00 + ox));
-                tc = ldg4(map + (o00 + oy));
-                td = ldg4(map + (o00 + oy + ox));
+                ta = ld8(map + o00);
+                tb = ld8(map + (o00 + ox));
+                tc = ld8(map + (o00 + oy));
+                td = ld8(map + (o00 + oy + ox));
             }
-            float4 w;
+            const float2 p00 = make_float2(w00, w00), p01 = make_float2(w01, w01), p10 = make_float2(w10, w10), p11 = make_float2(w11, w11);
+            float2 w[4];
             // accumulation order nw, ne, sw, se (ATen grid_sampler_2d)
-            w.x = ta.x * w00; w.y = ta.y * w00; w.z = ta.z * w00; w.w = ta.w * w00;
-            w.x += tb.x * w01; w.y += tb.y * w01; w.z += tb.z * w01; w.w += tb.w * w01;
-            w.x += tc.x * w10; w.y += tc.y * w10; w.z += tc.z * w10; w.w += tc.w * w10;
-            w.x += td.x * w11; w.y += td.y * w11; w.z += td.z * w11; w.w += td.w * w11;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                w[q] = __fmul2_rn(ta.v[q], p00);
+                w[q] = __ffma2_rn(tb.v[q], p01, w[q]);
+                w[q] = __ffma2_rn(tc.v[q], p10, w[q]);
+                w[q] = __ffma2_rn(td.v[q], p11, w[q]);
+            }
             if (AGG == MVSB200_AGG_VARIANCE || AGG == MVSB200_AGG_VARIANCE_MEAN) {
-                acc1[k].x += w.x; acc1[k].y += w.y; acc1[k].z += w.z; acc1[k].w += w.w;
-                acc2[k].x += w.x * w.x; acc2[k].y += w.y * w.y; acc2[k].z += w.z * w.z; acc2[k].w += w.w * w.w;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    acc1[k][q] = __fadd2_rn(acc1[k][q], w[q]);
+                    acc2[k][q] = __ffma2_rn(w[q], w[q], acc2[k][q]);
+                }
             } else if (AGG == MVSB200_AGG_SOFTMIN) {
-                float4 df = make_float4(w.x - r.x, w.y - r.y, w.z - r.z, w.w - r.w);
-                df.x *= df.x; df.y *= df.y; df.z *= df.z; df.w *= df.w;
-                float ssd = (df.x + df.y) + (df.z + df.w);
+                float2 df[4];
+                const float2 m1 = make_float2(-1.f, -1.f);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    df[q] = __ffma2_rn(r.v[q], m1, w[q]);   // w - r (the product is exact)
+                    df[q] = __fmul2_rn(df[q], df[q]);
+                }
+                float ssd = ((df[0].x + df[0].y) + (df[1].x + df[1].y)) + ((df[2].x + df[2].y) + (df[3].x + df[3].y));
 #pragma unroll
                 for (int m = LPV / 2; m >= 1; m >>= 1) ssd += __shfl_xor_sync(0xffffffffu, ssd, m);
-                float e = expf(-temp * ssd);
+                const float e = expf(-temp * ssd);
                 sum_exp[k] += e;
-                acc1[k].x += df.x * e; acc1[k].y += df.y * e; acc1[k].z += df.z * e; acc1[k].w += df.w * e;
-            } else {  // GROUPCORR: one lane == one group of 4 channels; one output volume per source view
-                float g = r.x * w.x;
-                g += r.y * w.y;
-                g += r.z * w.z;
-                g += r.w * w.w;
+                const float2 ee = make_float2(e, e);
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc1[k][q] = __ffma2_rn(df[q], ee, acc1[k][q]);
+            } else {  // GROUPCORR: groups of 4 channels, two per lane; one output volume per source view
+                float g0 = r.v[0].x * w[0].x;
+                g0 += r.v[0].y * w[0].y;
+                g0 += r.v[1].x * w[1].x;
+                g0 += r.v[1].y * w[1].y;
+                float g1 = r.v[2].x * w[2].x;
+                g1 += r.v[2].y * w[2].y;
+                g1 += r.v[3].x * w[3].x;
+                g1 += r.v[3].y * w[3].y;
                 if (active && d0 + k < p.D) {
-                    vmax = fmaxf(vmax, fabsf(g));
-                    __stcs(p.out + s * p.out_view_stride + (((long long)b * p.D + d0 + k) * HW + pix) * LPV + sub, g);
+                    vmax = fmaxf(vmax, fmaxf(fabsf(g0), fabsf(g1)));
+                    __stcs(reinterpret_cast<float2 *>(p.out + s * p.out_view_stride + (((long long)b * p.D + d0 + k) * HW + pix) * (2 * LPV) + sub * 2),
+                           make_float2(g0, g1));
                 }
             }
         }
@@ -237,29 +276,33 @@ __global__ void __launch_bounds__(K1_THREADS) k1_cost_volume_kernel(const K1Para
 
     const float V = (float)(p.S + 1), V2 = V * V;
     const float rV = 1.f / V, rV2 = 1.f / V2;
+    // x / d for a divisor whose correctly rounded reciprocal r is known (see div_by), on channel pairs
+    auto div2 = [](float2 xx, float d, float rr) {
+        const float2 q = __fmul2_rn(xx, make_float2(rr, rr));
+        const float2 t = __ffma2_rn(q, make_float2(-d, -d), xx);
+        return __ffma2_rn(t, make_float2(rr, rr), q);
+    };
 #pragma unroll
     for (int k = 0; k < K1_DCH; k++) {
         if (AGG == MVSB200_AGG_GROUPCORR || !active || d0 + k >= p.D) break;
-        float4 o;
-        if (AGG == MVSB200_AGG_VARIANCE) {
-            o.x = div_by(acc2[k].x, V, rV) - div_by(acc1[k].x * acc1[k].x, V2, rV2);
-            o.y = div_by(acc2[k].y, V, rV) - div_by(acc1[k].y * acc1[k].y, V2, rV2);
-            o.z = div_by(acc2[k].z, V, rV) - div_by(acc1[k].z * acc1[k].z, V2, rV2);
-            o.w = div_by(acc2[k].w, V, rV) - div_by(acc1[k].w * acc1[k].w, V2, rV2);
-        } else if (AGG == MVSB200_AGG_VARIANCE_MEAN) {
-            const float mx = div_by(acc1[k].x, V, rV), my = div_by(acc1[k].y, V, rV), mz = div_by(acc1[k].z, V, rV),
-                        mw = div_by(acc1[k].w, V, rV);
-            o.x = div_by(acc2[k].x, V, rV) - mx * mx;
-            o.y = div_by(acc2[k].y, V, rV) - my * my;
-            o.z = div_by(acc2[k].z, V, rV) - mz * mz;
-            o.w = div_by(acc2[k].w, V, rV) - mw * mw;
-        } else {
-            const float den = sum_exp[k] + 1e-6f, rden = 1.f / den;
-            o.x = div_by(acc1[k].x, den, rden); o.y = div_by(acc1[k].y, den, rden);
-            o.z = div_by(acc1[k].z, den, rden); o.w = div_by(acc1[k].w, den, rden);
+        float2 o[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (AGG == MVSB200_AGG_VARIANCE) {
+                const float2 m2 = div2(acc2[k][q], V, rV), m11 = div2(__fmul2_rn(acc1[k][q], acc1[k][q]), V2, rV2);
+                o[q] = __ffma2_rn(m11, make_float2(-1.f, -1.f), m2);
+            } else if (AGG == MVSB200_AGG_VARIANCE_MEAN) {
+                const float2 m = div2(acc1[k][q], V, rV), m2 = div2(acc2[k][q], V, rV);
+                o[q] = __ffma2_rn(__fmul2_rn(m, m), make_float2(-1.f, -1.f), m2);
+            } else {
+                const float den = sum_exp[k] + 1e-6f, rden = 1.f / den;
+                o[q] = div2(acc1[k][q], den, rden);
+            }
+            vmax = fmaxf(vmax, fmaxf(fabsf(o[q].x), fabsf(o[q].y)));
         }
-        vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
-        st4_stream(p.out + (((long long)b * p.D + d0 + k) * HW + pix) * C + sub * 4, o);
+        float *dst = p.out + (((long long)b * p.D + d0 + k) * HW + pix) * C + sub * 8;
+        st4_stream(dst, make_float4(o[0].x, o[0].y, o[1].x, o[1].y));
+        st4_stream(dst + 4, make_float4(o[2].x, o[2].y, o[3].x, o[3].y));
     }
     if (p.out_amax) {
 #pragma unroll
@@ -324,7 +367,7 @@ extern "C" int mvsb200_build_cost_volume(const mvsb200_cost_volume_desc *d, cons
     p.out_view_stride = d->out_view_stride;
     p.B = d->B; p.S = d->S; p.D = d->D; p.H = d->H; p.W = d->W; p.depth_mode = d->depth_mode;
     const long long HW = (long long)d->H * d->W;
-    const int vpb = K1_THREADS / (d->C / 4);
+    const int vpb = K1_THREADS / (d->C / 8);
     dim3 grid((unsigned)((HW + vpb - 1) / vpb), (unsigned)((d->D + K1_DCH - 1) / K1_DCH), (unsigned)d->B);
     MVSB200_REQUIRE(grid.y <= 65535, "build_cost_volume: D too large");
     cudaStream_t st = (cudaStream_t)stream;
