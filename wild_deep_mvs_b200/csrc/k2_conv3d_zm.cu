@@ -38,8 +38,9 @@ namespace mvsb200 {
 using namespace umma;
 
 constexpr int ZM_S1 = 0, ZM_S2 = 1, ZM_DECONV = 2;
-constexpr int ZM_EPI_WARPS = 8, ZM_PROD_WARPS = 9;   // 18 warps with the MMA warp: at most 5 per scheduler, 96 registers each
-constexpr int ZM_THREADS = (ZM_EPI_WARPS + ZM_PROD_WARPS + 1) * 32;   // 576
+constexpr int ZM_EPI_WARPS = 8, ZM_PROD_WARPS = 9;   // 19 warps with the MMA and planner warps: at most 5 per scheduler, 96 registers each
+constexpr int ZM_THREADS = (ZM_EPI_WARPS + ZM_PROD_WARPS + 2) * 32;   // 608: + MMA issuer warp + planner warp
+constexpr int ZM_NPLAN = 4;                                            // plans the planner may run ahead of the issuer
 constexpr int ZM_PROD_GROUP = 96;                                      // producer threads working on one unit
 constexpr int ZM_NGROUPS = ZM_PROD_WARPS * 32 / ZM_PROD_GROUP;         // units being filled concurrently
 constexpr int ZM_HEADER_HALVES = 8;                                    // 16-byte header in front of the packed weights
@@ -97,9 +98,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 // from the MMA-issuing thread (bounded like umma::mbar_wait: a pipeline bug must trap, not hang the GPU).
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
 {
+    if (mbar_try_wait(bar, parity)) return;
+#pragma unroll 1
     for (uint32_t i = 0; i < (1u << 24); i++) {
-        if (mbar_try_wait(bar, parity)) return;
         __nanosleep(64);
+        if (mbar_try_wait(bar, parity)) return;
     }
     __trap();
 }
@@ -261,6 +264,8 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_full[MAXUB], s_empty[MAXUB], s_accfull[8], s_accempty[8], s_wbar;
     __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) unsigned long long s_planfull[ZM_NPLAN], s_planempty[ZM_NPLAN];
+    __shared__ __align__(16) uint32_t s_plan[ZM_NPLAN][8];   // planner -> MMA issuer, see the planner warp
     __shared__ __align__(16) float s_sc[CT], s_bi[CT];   // epilogue: y = acc * s_sc + s_bi (operand un-scaling and BN folded)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -276,6 +281,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
         for (int i = 0; i < NUB; i++) { mbar_init(smem_u32(&s_full[i]), ZM_PROD_GROUP / 32); mbar_init(smem_u32(&s_empty[i]), 1); }
         for (int i = 0; i < NACC; i++) { mbar_init(smem_u32(&s_accfull[i]), 1); mbar_init(smem_u32(&s_accempty[i]), TEAM_WARPS); }
         mbar_init(smem_u32(&s_wbar), ZM_PROD_WARPS);
+        for (int i = 0; i < ZM_NPLAN; i++) { mbar_init(smem_u32(&s_planfull[i]), 1); mbar_init(smem_u32(&s_planempty[i]), 1); }
         fence_mbar_init();
     }
     if (warp == ZM_EPI_WARPS + ZM_PROD_WARPS) tmem_alloc(smem_u32(&s_tmem), 512);
@@ -519,83 +525,61 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
             }
         }
         if (prof && ptid == 0) { g_zm_prof[8] += clock64() - pp_tot; g_zm_prof[9] += pp_wait; g_zm_prof[10] += pp_n; }
-    } else {
+    } else if (warp == ZM_EPI_WARPS + ZM_PROD_WARPS) {
         // =================================== MMA issuer ===================================
-        // ONE thread issues every MMA of the CTA, so its instruction stream is the pacing item of the whole pipeline:
-        // ring positions and phases are carried incrementally (no division), the tap loops are fully unrolled and a
-        // descriptor is the 32-bit low word (start address | LBO) plus a constant high word.  The whole warp runs the
-        // (warp-uniform) control flow and waits; only the tcgen05 instructions are predicated on the elected lane, which
-        // keeps descriptors in uniform registers instead of a per-instruction leader-election loop.
+        // ONE thread issues every MMA of the CTA and the queue between it and the tensor core is shallow, so whatever
+        // this warp does besides issuing idles the tensor core.  It therefore does nothing else: which accumulator slots
+        // an input plane feeds, how they are cut into runs of adjacent TMEM columns, the waits for drained slots and
+        // the list of output planes to hand to the epilogue come ready-made from the planner warp (s_plan); ring
+        // positions and phases are carried incrementally, the tap loops are fully unrolled, a descriptor is a 32-bit
+        // low word (start address | LBO) plus a constant high word.  The whole warp runs the (warp-uniform) control
+        // flow; only the tcgen05 instructions are predicated on the elected lane, which keeps descriptors in uniform
+        // registers instead of a per-instruction leader-election loop.
         {
             mbar_wait(smem_u32(&s_wbar), 0);
             tc_fence_after_sync();
             const uint32_t a_hi = (uint32_t)(smem_desc(0, RA * 16, 128) >> 32), b_hi = (uint32_t)(smem_desc(0, NC * 16, 128) >> 32);
             const uint32_t a_lo0 = (uint32_t)smem_desc(smem_u32(sA), RA * 16, 128), b_lo0 = (uint32_t)smem_desc(smem_u32(sW), 0, 128);
             const uint32_t full0 = smem_u32(&s_full[0]), empty0 = smem_u32(&s_empty[0]);
-            const uint32_t accfull0 = smem_u32(&s_accfull[0]), accempty0 = smem_u32(&s_accempty[0]);
+            const uint32_t accfull0 = smem_u32(&s_accfull[0]);
+            const uint32_t planfull0 = smem_u32(&s_planfull[0]), planempty0 = smem_u32(&s_planempty[0]);
             int ub = 0;              // unit-buffer ring position
             uint32_t uphase = 0;     // parity of the current pass over the ring
-            int qbase = 0;           // output planes of the tiles already issued (accumulator ring position = qbase + q)
-            uint32_t started = 0;    // bit per accumulator slot: the plane in it has received its first MMA
+            int pi = 0;              // plan ring position
+            uint32_t pphase = 0;
             long long pm_tot = ZM_T0(), pm_full = 0, pm_acc = 0, pm_issue = 0, pm_n = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 const ZmTile t = zm_decode<MODE, CT>(p, tile);
                 const int np = zm_nplanes<MODE>(t.nq);
                 const int vy_cls = (t.cls >> 1) & 1;
                 for (int pl = 0; pl < np; pl++) {
-                    const int gz = zm_zin<MODE>(t.zb, pl);
-                    if ((unsigned)gz < (unsigned)p.D) {
-                        // Output planes fed by this input plane: q = qf + i for i in [i0, i1).  Their accumulator slots
-                        // are consecutive ring positions; cut the range into runs of adjacent TMEM columns.
-                        //   runs "F": first window of the plane -- also cut between planes that accumulate and planes
-                        //             that start (their first MMA overwrites);   runs "R": every other window.
+                    // ---- the plan of this input plane ----
+                    long long tq = ZM_T0();
+                    mbar_wait(planfull0 + pi * 8, pphase);
+                    ZM_ACC(pm_acc, tq);
+                    const uint4 pa = *reinterpret_cast<const uint4 *>(&s_plan[pi][0]);
+                    const uint4 pb = *reinterpret_cast<const uint4 *>(&s_plan[pi][4]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(planempty0 + pi * 8);
+                    if (++pi == ZM_NPLAN) { pi = 0; pphase ^= 1u; }
+                    const uint32_t flags = pa.x;
+                    if (flags & 1u) {   // the plane lies inside the volume: its units are in the pipeline
+                        const int nf = (flags >> 8) & 0xf, nr = (flags >> 12) & 0xf;
                         const int ztype = zm_ztype<MODE>(pl), nblk = zm_type_nblk(MODE, ztype);
-                        const int qf = zm_qfirst<MODE>(pl);
-                        const int i0 = max(0, -qf), i1 = min(nblk, t.nq - qf);
-                        // (scalars, not arrays: the issue loop below must not touch local memory)
-                        uint32_t fd0 = 0, fb0 = 0, fn0 = 0, fa0 = 0, fd1 = 0, fb1 = 0, fn1 = 0, fa1 = 0, fd2 = 0, fb2 = 0, fn2 = 0, fa2 = 0;
-                        uint32_t rd0 = 0, rb0 = 0, rn0 = 0, rd1 = 0, rb1 = 0, rn1 = 0;
-                        int nf = 0, nr = 0;
-                        uint32_t fcur_n = 0, fcur_a = 0, rcur_n = 0;
-#pragma unroll
-                        for (int i = 0; i < 3; i++) {
-                            if (i < i0 || i >= i1) continue;
-                            const int qg = qbase + qf + i, aslot = qg % NACC;
-                            const uint32_t st = (started >> aslot) & 1u;
-                            if (!st) {   // drained by the epilogue?
-                                const long long tq = ZM_T0();
-                                mbar_wait(accempty0 + aslot * 8, ((uint32_t)(qg / NACC) & 1u) ^ 1u);
-                                ZM_ACC(pm_acc, tq);
-                            }
-                            // (an MMA is at most 256 columns wide)
-                            if (nr == 0 || aslot == 0 || rcur_n + NC > 256) {
-                                if (nr == 0) { rd0 = aslot * NC; rb0 = i * NC; } else { rd1 = aslot * NC; rb1 = i * NC; }
-                                nr++;
-                                rcur_n = 0;
-                            }
-                            rcur_n += NC;
-                            if (nr == 1) rn0 = rcur_n; else rn1 = rcur_n;
-                            if (nf == 0 || aslot == 0 || st != fcur_a || fcur_n + NC > 256) {
-                                if (nf == 0) { fd0 = aslot * NC; fb0 = i * NC; fa0 = st; }
-                                else if (nf == 1) { fd1 = aslot * NC; fb1 = i * NC; fa1 = st; }
-                                else { fd2 = aslot * NC; fb2 = i * NC; fa2 = st; }
-                                nf++;
-                                fcur_n = 0;
-                                fcur_a = st;
-                            }
-                            fcur_n += NC;
-                            if (nf == 1) fn0 = fcur_n; else if (nf == 2) fn1 = fcur_n; else fn2 = fcur_n;
-                            started |= 1u << aslot;
-                        }
-                        tc_fence_after_sync();
                         const uint32_t b_lbo = (uint32_t)(nblk * NC) << 16;   // LBO field: k-plane stride of the folded B matrix
-                        const uint32_t id0 = idesc_f16(128, rn0), id1 = idesc_f16(128, rn1);
+                        // run word: TMEM column | B row offset << 10 | N << 20 | accumulate << 31
+#define ZM_RUN(w, d, bo, id) const uint32_t d = (w) & 0x3ffu, bo = ((w) >> 10) & 0x3ffu, id = idesc_f16(128, ((w) >> 20) & 0x1ffu)
+                        ZM_RUN(pa.y, fd0, fb0, fi0); ZM_RUN(pa.z, fd1, fb1, fi1); ZM_RUN(pa.w, fd2, fb2, fi2);
+                        ZM_RUN(pb.x, rd0, rb0, id0); ZM_RUN(pb.y, rd1, rb1, id1);
+#undef ZM_RUN
+                        const uint32_t fa0 = pa.y >> 31, fa1 = pa.z >> 31, fa2 = pa.w >> 31;
+                        tc_fence_after_sync();
                         bool first = true;
                         for (int py = 0; py < NPY; py++) {
                             const int vy = (MODE == ZM_S2) ? py : vy_cls;
                             for (int c0 = 0; c0 < nch;) {
                                 const int G = zm_unit_chunks(c0, nch1, nch, 4 / NPX);
-                                long long tq = ZM_T0();
+                                tq = ZM_T0();
                                 mbar_wait(full0 + ub * 8, uphase);
                                 ZM_ACC(pm_full, tq);
                                 pm_n++;
@@ -615,15 +599,15 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                                                 const uint64_t ad0 = ((uint64_t)a_hi << 32) | a_y, ad1 = ((uint64_t)a_hi << 32) | (a_y + 128);
                                                 if (first) {
                                                     first = false;
-                                                    mma_f16(tmem + fd0, ad0, ((uint64_t)b_hi << 32) | (b_y + fb0), idesc_f16(128, fn0), fa0);
-                                                    if (MT == 2) mma_f16(tmem + T::MT_COLS + fd0, ad1, ((uint64_t)b_hi << 32) | (b_y + fb0), idesc_f16(128, fn0), fa0);
+                                                    mma_f16(tmem + fd0, ad0, ((uint64_t)b_hi << 32) | (b_y + fb0), fi0, fa0);
+                                                    if (MT == 2) mma_f16(tmem + T::MT_COLS + fd0, ad1, ((uint64_t)b_hi << 32) | (b_y + fb0), fi0, fa0);
                                                     if (nf > 1) {
-                                                        mma_f16(tmem + fd1, ad0, ((uint64_t)b_hi << 32) | (b_y + fb1), idesc_f16(128, fn1), fa1);
-                                                        if (MT == 2) mma_f16(tmem + T::MT_COLS + fd1, ad1, ((uint64_t)b_hi << 32) | (b_y + fb1), idesc_f16(128, fn1), fa1);
+                                                        mma_f16(tmem + fd1, ad0, ((uint64_t)b_hi << 32) | (b_y + fb1), fi1, fa1);
+                                                        if (MT == 2) mma_f16(tmem + T::MT_COLS + fd1, ad1, ((uint64_t)b_hi << 32) | (b_y + fb1), fi1, fa1);
                                                     }
                                                     if (nf > 2) {
-                                                        mma_f16(tmem + fd2, ad0, ((uint64_t)b_hi << 32) | (b_y + fb2), idesc_f16(128, fn2), fa2);
-                                                        if (MT == 2) mma_f16(tmem + T::MT_COLS + fd2, ad1, ((uint64_t)b_hi << 32) | (b_y + fb2), idesc_f16(128, fn2), fa2);
+                                                        mma_f16(tmem + fd2, ad0, ((uint64_t)b_hi << 32) | (b_y + fb2), fi2, fa2);
+                                                        if (MT == 2) mma_f16(tmem + T::MT_COLS + fd2, ad1, ((uint64_t)b_hi << 32) | (b_y + fb2), fi2, fa2);
                                                     }
                                                 } else {
                                                     mma_f16(tmem + rd0, ad0, ((uint64_t)b_hi << 32) | (b_y + rb0), id0, 1u);
@@ -646,21 +630,82 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                             }
                         }
                     }
-                    int qlo, qhi;
-                    zm_complete<MODE>(pl, t.nq, qlo, qhi);
-                    for (int q = qlo; q < qhi; q++) {
-                        const int aslot = (qbase + q) % NACC;
-                        if (elect_one_sync()) mma_commit(accfull0 + aslot * 8);
-                        started &= ~(1u << aslot);
+                    // output planes that are complete now: hand them to the epilogue
+                    const int ncommit = (flags >> 16) & 0xf;
+                    if (ncommit > 0 && elect_one_sync()) {
+                        mma_commit(accfull0 + (pb.z & 0xffu) * 8);
+                        if (ncommit > 1) mma_commit(accfull0 + ((pb.z >> 8) & 0xffu) * 8);
                     }
+                    __syncwarp();
                 }
-                qbase += t.nq;
             }
             if (prof && lane == 0) {
                 g_zm_prof[0] += clock64() - pm_tot; g_zm_prof[1] += pm_full; g_zm_prof[2] += pm_acc; g_zm_prof[3] += pm_issue; g_zm_prof[4] += pm_n;
             }
         }
         __syncwarp();
+    } else {
+        // =================================== planner warp ===================================
+        // Runs ahead of the MMA issuer (ring of ZM_NPLAN plans).  Per input plane: the output planes q = qf + i,
+        // i in [i0, i1), it feeds sit in consecutive accumulator ring positions; cut them into runs of adjacent TMEM
+        // columns -- runs "F" for the first window of the plane (also cut between planes that accumulate and planes
+        // that start: their first MMA overwrites), runs "R" for every other window -- wait until the epilogue has
+        // drained the slots that start, and list the output planes that are complete after this plane.
+        const uint32_t accempty0 = smem_u32(&s_accempty[0]);
+        int qbase = 0;           // output planes of the tiles already planned (accumulator ring position = qbase + q)
+        uint32_t started = 0;    // bit per accumulator slot: the plane in it has received its first MMA
+        int pi = 0;
+        uint32_t pphase = 1;     // first pass over the plan ring: free
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            const ZmTile t = zm_decode<MODE, CT>(p, tile);
+            const int np = zm_nplanes<MODE>(t.nq);
+            for (int pl = 0; pl < np; pl++) {
+                const int gz = zm_zin<MODE>(t.zb, pl);
+                uint32_t flags = 0, fw[3] = {0, 0, 0}, rw[2] = {0, 0}, commits = 0;
+                if ((unsigned)gz < (unsigned)p.D) {
+                    const int nblk = zm_type_nblk(MODE, zm_ztype<MODE>(pl));
+                    const int qf = zm_qfirst<MODE>(pl);
+                    const int i0 = max(0, -qf), i1 = min(nblk, t.nq - qf);
+                    int nf = 0, nr = 0;
+                    uint32_t fcur_n = 0, fcur_a = 0, rcur_n = 0;
+                    for (int i = i0; i < i1; i++) {
+                        const int qg = qbase + qf + i, aslot = qg % NACC;
+                        const uint32_t st = (started >> aslot) & 1u;
+                        if (!st) mbar_wait_relaxed(accempty0 + aslot * 8, ((uint32_t)(qg / NACC) & 1u) ^ 1u);   // drained by the epilogue?
+                        // (an MMA is at most 256 columns wide)
+                        if (nr == 0 || aslot == 0 || rcur_n + NC > 256) { rw[nr] = (uint32_t)(aslot * NC) | ((uint32_t)(i * NC) << 10); nr++; rcur_n = 0; }
+                        rcur_n += NC;
+                        rw[nr - 1] = (rw[nr - 1] & 0x000fffffu) | (rcur_n << 20);
+                        if (nf == 0 || aslot == 0 || st != fcur_a || fcur_n + NC > 256) {
+                            fw[nf] = (uint32_t)(aslot * NC) | ((uint32_t)(i * NC) << 10) | (st << 31);
+                            nf++; fcur_n = 0; fcur_a = st;
+                        }
+                        fcur_n += NC;
+                        fw[nf - 1] = (fw[nf - 1] & 0x800fffffu) | (fcur_n << 20);
+                        started |= 1u << aslot;
+                    }
+                    flags = 1u | ((uint32_t)nf << 8) | ((uint32_t)nr << 12);
+                }
+                int qlo, qhi;
+                zm_complete<MODE>(pl, t.nq, qlo, qhi);
+                int nc = 0;
+                for (int q = qlo; q < qhi; q++, nc++) {
+                    const int aslot = (qbase + q) % NACC;
+                    commits |= (uint32_t)aslot << (8 * nc);
+                    started &= ~(1u << aslot);
+                }
+                flags |= (uint32_t)nc << 16;
+                mbar_wait_relaxed(smem_u32(&s_planempty[pi]), pphase);
+                if (lane == 0) {
+                    *reinterpret_cast<uint4 *>(&s_plan[pi][0]) = make_uint4(flags, fw[0], fw[1], fw[2]);
+                    *reinterpret_cast<uint4 *>(&s_plan[pi][4]) = make_uint4(rw[0], rw[1], commits, 0u);
+                    mbar_arrive(smem_u32(&s_planfull[pi]));
+                }
+                __syncwarp();
+                if (++pi == ZM_NPLAN) { pi = 0; pphase ^= 1u; }
+            }
+            qbase += t.nq;
+        }
     }
     tc_fence_before_sync();
     __syncthreads();

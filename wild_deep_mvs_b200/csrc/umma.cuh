@@ -38,6 +38,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 // Bounded spin: a descriptor bug must trap, not hang the GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
+    if (mbar_try_wait(bar, parity)) return;
+#pragma unroll 1   // keep the spin loop small: an unrolled copy per call site evicts the issue loop from the instruction cache
     for (uint32_t i = 0; i < (1u << 26); i++)
         if (mbar_try_wait(bar, parity)) return;
     __trap();
