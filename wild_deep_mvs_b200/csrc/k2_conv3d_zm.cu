@@ -71,6 +71,7 @@ template <int MODE, int CT> struct ZmCfg {
     static constexpr int WREGION16 = 9 * WBLOCK_BYTES / 16;   // 16-byte units of one (variant, chunk) weight region
     static constexpr int X_BYTES = (NXS - 1) * (CT / 4) * XROWS * 16;   // x-shift exchange buffer of one epilogue team
     static constexpr int NTEAMS = (MT == 2) ? 1 : 2;
+    static constexpr int XBUF = (NTEAMS == 1) ? 2 : 1;       // exchange buffers per team (one team: alternate per plane)
     static_assert(TY * EX <= MT * 128, "plane tile does not fit the MMA row tiles");
     static_assert(MT * MT_COLS <= 512, "accumulators exceed TMEM");
     static_assert(NC % 16 == 0 && NC <= 256, "invalid MMA N");
@@ -310,7 +311,8 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
         // MT == 2: one team of 8 warps, warps 0-3 take row tile 0 and warps 4-7 row tile 1 of every plane;
         // MT == 1: two teams of 4 warps taking alternate planes.  A warp reads the TMEM lanes of quadrant warp % 4.
         const int quad = warp & 3, team = (MT == 2) ? 0 : (warp >> 2), mt = (MT == 2) ? (warp >> 2) : 0;
-        float4 *sX = sXall + (size_t)team * (T::X_BYTES / 16);
+        float4 *sX0 = sXall + (size_t)team * (T::XBUF * T::X_BYTES / 16);   // XBUF exchange buffers per team, alternating per plane
+        int xpar = 0;
         constexpr int C4 = CT / 4;
         const int ncol = min(CT, p.Cout - nb * CT), co0 = nb * CT;
         const int pr = mt * 128 + quad * 32 + lane;           // GEMM row of this thread within the plane tile
@@ -328,41 +330,82 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                 oy = 2 * oy + ry; ox = 2 * ox + rx;
             }
             ok_yx = ok_yx && oy < p.Ho && ox < p.Wo;
-            for (int q = 0; q < t.nq; q++, qg++) {
-                if (NTEAMS == 2 && (qg & 1) != team) continue;
-                const int slot = qg % NACC;
-                const int oz = (MODE == ZM_DECONV ? 2 * t.zb : t.zb) + q;
-                const bool ok = ok_yx && oz < p.Do;
-                const long long o = ((((long long)t.b * p.Do + oz) * p.Ho + oy) * p.Wo + ox) * p.Cout + co0;
-                // the skip operand does not depend on the accumulator: fetch it while the MMAs are still running
-                float4 sk[C4];
+            // The skip operand does not depend on the accumulator: it is fetched one of this team's planes AHEAD, so its
+            // (HBM) latency overlaps the previous plane's epilogue instead of sitting between "accumulator ready" and
+            // "store" (which is what bounded the up-sampling layers: the epilogue was 80 % busy, mostly in this wait).
+            const long long plane_stride = (long long)p.Ho * p.Wo * p.Cout;
+            const long long o_yx = (((long long)t.b * p.Do * p.Ho + oy) * p.Wo + ox) * p.Cout + co0;
+            const int oz0 = (MODE == ZM_DECONV) ? 2 * t.zb : t.zb;
+            auto load_skip = [&](int q, float4 (&sk)[C4]) {
 #pragma unroll
                 for (int c4 = 0; c4 < C4; c4++) {
                     sk[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok && p.skip_mode != MVSB200_SKIP_NONE && c4 * 4 < ncol) sk[c4] = ldg4(p.skip + o + c4 * 4);
+                    if (q < t.nq && ok_yx && oz0 + q < p.Do && p.skip_mode != MVSB200_SKIP_NONE && c4 * 4 < ncol)
+                        sk[c4] = ldg4(p.skip + o_yx + (oz0 + q) * plane_stride + c4 * 4);
+                }
+            };
+            constexpr bool AHEAD = (CT == 8);   // CT = 16: a second skip buffer would spill; its two teams overlap instead
+            float4 sk[C4], sk_next[AHEAD ? C4 : 1];
+            if (AHEAD) load_skip((NTEAMS == 2 && (qg & 1) != team) ? 1 : 0, reinterpret_cast<float4 (&)[C4]>(sk_next));   // first plane of this team in the tile
+            for (int q = 0; q < t.nq; q++, qg++) {
+                if (NTEAMS == 2 && (qg & 1) != team) continue;
+                const int slot = qg % NACC;
+                const int oz = oz0 + q;
+                const bool ok = ok_yx && oz < p.Do;
+                const long long o = o_yx + oz * plane_stride;
+                if (AHEAD) {
+#pragma unroll
+                    for (int c4 = 0; c4 < C4; c4++) sk[c4] = sk_next[c4 < (AHEAD ? C4 : 1) ? c4 : 0];
+                    load_skip(q + NTEAMS, reinterpret_cast<float4 (&)[C4]>(sk_next));
+                } else {
+                    load_skip(q, sk);
                 }
                 long long tq = ZM_T0();
                 mbar_wait_relaxed(smem_u32(&s_accfull[slot]), (uint32_t)(qg / NACC) & 1u);
                 ZM_ACC(pe_wait, tq);
                 pe_n++;
                 tc_fence_after_sync();
+                float4 *sX = sX0 + xpar * (T::X_BYTES / 16);
+                if (T::XBUF == 2) xpar ^= 1;
                 float r0[CT];
+                const uint32_t taddr0 = tmem + ((uint32_t)(quad * 32) << 16) + mt * T::MT_COLS + slot * NC;
+                if (CT == 8) {
+                    // all TMEM loads of the row in flight at once, one wait
+                    float v[T::NXS][16];
 #pragma unroll
-                for (int xs = 0; xs < T::NXS; xs++) {
-                    float v[2 * CT];
-                    const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + mt * T::MT_COLS + slot * NC + xs * 2 * CT;
-#pragma unroll
-                    for (int j = 0; j < 2 * CT; j += 16) tmem_ld16(taddr + j, v + j);
+                    for (int xs = 0; xs < T::NXS; xs++) tmem_ld16(taddr0 + xs * 16, v[xs]);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int k = 0; k < CT; k++) v[k] += v[CT + k];
-                    if (xs == 0) {
+                    for (int xs = 0; xs < T::NXS; xs++) {
 #pragma unroll
-                        for (int k = 0; k < CT; k++) r0[k] = v[k];
-                    } else {
+                        for (int k = 0; k < 8; k++) v[xs][k] += v[xs][8 + k];
+                        if (xs == 0) {
 #pragma unroll
-                        for (int c4 = 0; c4 < C4; c4++)
-                            sX[((xs - 1) * C4 + c4) * T::XROWS + pr] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+                            for (int k = 0; k < 8; k++) r0[k] = v[0][k];
+                        } else {
+#pragma unroll
+                            for (int c4 = 0; c4 < 2; c4++)
+                                sX[((xs - 1) * C4 + c4) * T::XROWS + pr] = make_float4(v[xs][c4 * 4], v[xs][c4 * 4 + 1], v[xs][c4 * 4 + 2], v[xs][c4 * 4 + 3]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int xs = 0; xs < T::NXS; xs++) {
+                        float v[2 * CT];
+                        const uint32_t taddr = taddr0 + xs * 2 * CT;
+#pragma unroll
+                        for (int j = 0; j < 2 * CT; j += 16) tmem_ld16(taddr + j, v + j);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < CT; k++) v[k] += v[CT + k];
+                        if (xs == 0) {
+#pragma unroll
+                            for (int k = 0; k < CT; k++) r0[k] = v[k];
+                        } else {
+#pragma unroll
+                            for (int c4 = 0; c4 < C4; c4++)
+                                sX[((xs - 1) * C4 + c4) * T::XROWS + pr] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+                        }
                     }
                 }
                 // the accumulator plane is in registers / shared memory: hand the TMEM slot back to the MMA thread
@@ -392,10 +435,9 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                         st4(p.y + o + c4 * 4, make_float4(r[0], r[1], r[2], r[3]));
                     }
                 }
-                // sX is rewritten by the team's next plane
-                tq = ZM_T0();
-                if (team == 0) named_bar_sync(1, TEAM_WARPS * 32); else named_bar_sync(2, TEAM_WARPS * 32);
-                ZM_ACC(pe_bar, tq);
+                // One team: no second barrier -- the next plane writes the OTHER exchange buffer, and the barrier of that
+                // plane orders this plane's reads before the writes of the plane after it.  Two teams: single buffer.
+                if (T::XBUF == 1) { if (team == 0) named_bar_sync(1, TEAM_WARPS * 32); else named_bar_sync(2, TEAM_WARPS * 32); }
             }
         }
         if (p.y_amax) {
@@ -795,13 +837,15 @@ static int zm_nvar(int mode) { return mode == ZM_S1 ? 1 : 2; }
 template <int MODE, int CT> static size_t zm_smem_bytes(int nch, int nst)
 {
     using T = ZmCfg<MODE, CT>;
-    return (size_t)T::NPXL * nch * 9 * T::WBLOCK_BYTES + (size_t)nst * T::UNIT_BYTES + (size_t)T::NTEAMS * T::X_BYTES;
+    return (size_t)T::NPXL * nch * 9 * T::WBLOCK_BYTES + (size_t)nst * T::UNIT_BYTES + (size_t)T::NTEAMS * T::XBUF * T::X_BYTES;
 }
 
 // number of unit buffers that fit next to the resident weights (0: the layer does not fit this engine)
 template <int MODE, int CT> static int zm_stages(int nch)
 {
-    for (int nst = 6; nst >= 2; nst--)
+    // At least as many buffers as producer groups: a group waits on the "empty" barrier of a buffer by phase parity,
+    // which is only unambiguous if it can never be two completions behind (true for nst >= ZM_NGROUPS).
+    for (int nst = 6; nst >= ZM_NGROUPS; nst--)
         if (zm_smem_bytes<MODE, CT>(nch, nst) + 2048 <= 227 * 1024) return nst;
     return 0;
 }
