@@ -155,3 +155,29 @@ def test_cuda_graph_replay_equals_eager_launches(golden):
     d2_eager, _ = net.depth_from_features(feats2, projs, dv)
     d2_graph, _ = graphed(feats2, projs, dv)
     assert torch.equal(d2_graph, d2_eager) and not torch.equal(d2_graph, d_eager)
+
+
+def test_streamed_pinned_host_samples_equal_eager(golden):
+    """StreamedHotPath: pinned host inputs, H2D on a copy stream overlapping the previous sample's kernels, two graph
+    slots round-robin, results copied back to pinned host buffers -- every sample must equal the eager device path."""
+    g = golden("mvsnet_variance")
+    net = _load(g, "variance")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    feats = [ops.to_nhwc(t(g["feat%d" % i])) for i in range(3)]
+    projs = [t(g["proj"][:, i]) for i in range(3)]
+    dv = t(g["depth_values"])
+    streamed = net.streamed(feats, projs, dv)
+    samples = [feats, [f.flip(1).contiguous() for f in feats], [f.flip(2).contiguous() for f in feats],
+               [(f * 0.5).contiguous() for f in feats], feats]
+    hp = [p.cpu().pin_memory() for p in projs]
+    hd = dv.cpu().pin_memory()
+    want = [net.depth_from_features(s, projs, dv) for s in samples]
+    got = []
+    for s in samples:   # submitted back to back: slot reuse after two submissions
+        hs = [f.cpu().pin_memory() for f in s]
+        d, c, ev = streamed.submit(hs, hp, hd)
+        ev.synchronize()
+        got.append((d.clone(), c.clone()))
+    for (d, c), (wd, wc) in zip(got, want):
+        assert torch.equal(d, wd.cpu()) and torch.equal(c, wc.cpu())
+    assert not torch.equal(got[0][0], got[1][0])

@@ -158,6 +158,46 @@ class GraphedHotPath:
         return self.depth, self.conf
 
 
+class StreamedHotPath:
+    """A stream of samples whose inputs sit in PINNED HOST memory (the reconstruction pipeline's loop over the reference
+    views of a scene, evaluation/run_depthmaps.py:53-68): `slots` graph instances are used round-robin, the H2D copies of
+    sample i+1 run on a copy stream while sample i's graph runs, and depth + confidence of every sample are copied back
+    to pinned host buffers.  submit() returns (host_depth, host_conf, event); the buffers are valid once the event has
+    completed and until the slot is reused (`slots` submissions later)."""
+
+    def __init__(self, net, feats_nhwc, proj_matrices, depth_values, reference_frame=0, slots=2):
+        self.slots = [GraphedHotPath(net, feats_nhwc, proj_matrices, depth_values, reference_frame) for _ in range(slots)]
+        self.copy_stream = torch.cuda.Stream()
+        self.ready = [torch.cuda.Event() for _ in range(slots)]
+        self.done = [torch.cuda.Event() for _ in range(slots)]
+        for e in self.done:
+            e.record()
+        g = self.slots[0]
+        self.out_depth = [torch.empty(g.depth.shape, dtype=g.depth.dtype).pin_memory() for _ in range(slots)]
+        self.out_conf = [torch.empty(g.conf.shape, dtype=g.conf.dtype).pin_memory() for _ in range(slots)]
+        self.count = 0
+
+    def submit(self, host_feats_nhwc, host_projs, host_depth_values):
+        k = self.count % len(self.slots)
+        self.count += 1
+        g = self.slots[k]
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.done[k])   # the slot's previous sample has been computed and read back
+            for dst, src in zip(g.feats, host_feats_nhwc):
+                dst.copy_(src, non_blocking=True)
+            for dst, src in zip(g.projs, host_projs):
+                dst.copy_(src, non_blocking=True)
+            g.depth_values.copy_(host_depth_values, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        main.wait_event(self.ready[k])
+        g.graph.replay()
+        self.out_depth[k].copy_(g.depth, non_blocking=True)
+        self.out_conf[k].copy_(g.conf, non_blocking=True)
+        self.done[k].record(main)
+        return self.out_depth[k], self.out_conf[k], self.done[k]
+
+
 class MVSNet(nn.Module):
     def __init__(self, aggregation="variance"):
         super().__init__()
@@ -206,6 +246,10 @@ class MVSNet(nn.Module):
     def graphed(self, feats_nhwc, proj_matrices, depth_values, reference_frame=0):
         """CUDA-graph version of depth_from_features for inputs of these shapes (see GraphedHotPath)."""
         return GraphedHotPath(self, feats_nhwc, proj_matrices, depth_values, reference_frame)
+
+    def streamed(self, feats_nhwc, proj_matrices, depth_values, reference_frame=0, slots=2):
+        """Double-buffered, copy-overlapped version for a stream of pinned-host samples (see StreamedHotPath)."""
+        return StreamedHotPath(self, feats_nhwc, proj_matrices, depth_values, reference_frame, slots)
 
     def forward(self, imgs, K, R, t, depth_min, depth_max, reference_frame=0, **kwargs):
         if self.training:
