@@ -1,0 +1,91 @@
+"""All BASELINE.json configs on one B200 (bench.py itself measures configs[1] only, as its contract says): full
+`forward` of the three drop-in model families at the BASELINE sizes, timed with CUDA events, split into the 2-D feature
+extractors (PyTorch / cuDNN, "next" row f1) and the hot path (features -> depth: K1-K4), which is what Mvox/s counts.
+
+    python profiles/bench_configs.py [out.json]
+
+Random-init weights with randomised BN statistics (no checkpoints offline), synthetic DTU-like cameras (synth.py).
+"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from wild_deep_mvs_b200 import ops, synth  # noqa: E402
+from wild_deep_mvs_b200.cvpmvsnet import Frontend as CVP  # noqa: E402
+from wild_deep_mvs_b200.mvsnet import MVSNet  # noqa: E402
+from wild_deep_mvs_b200.vismvsnet import Frontend as Vis  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def timed(fn, reps=5, warmup=2):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    return sorted(ts)[len(ts) // 2]
+
+
+def sample(views, h, w):
+    return {k: v.to(DEV) for k, v in synth.make_sample(1, views, h, w, seed=0).items()}
+
+
+def run(name, net, s, vox, feat_fn, **kw):
+    net = net.to(DEV).eval()
+    call = lambda: net(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"], **kw)
+    out = call()
+    assert torch.isfinite(out["depth"]).all(), name
+    ms_fwd = timed(call)
+    with torch.no_grad():
+        ms_feat = timed(lambda: feat_fn(net, s))
+    ms_hot = ms_fwd - ms_feat
+    r = {"config": name, "voxels": vox, "forward_ms": round(ms_fwd, 3), "features_ms": round(ms_feat, 3),
+         "hot_path_ms": round(ms_hot, 3), "hot_path_Mvox_per_s": round(vox / ms_hot / 1e3, 1),
+         "depth_maps_per_s": round(1e3 / ms_fwd, 1), "depth_shape": list(out["depth"].shape)}
+    print(json.dumps(r), flush=True)
+    return r
+
+
+def main():
+    torch.manual_seed(0)
+    res = []
+    # cfg1 / cfg2: MVSNet-s (softmin, D=48, 1+2 views) and MVSNet (variance, D=192, 1+4 views), 640x512
+    feat_mvs = lambda net, s: net.extract_features(list(torch.unbind(s["imgs"], 1)))
+    for name, agg, views, D in (("cfg1 MVSNet-s 1+2 views 640x512 D=48", "softmin", 3, 48),
+                                ("cfg2 MVSNet 1+4 views 640x512 D=192", "variance", 5, 192)):
+        net = MVSNet(agg)
+        synth.randomize_norm_stats(net, seed=1)
+        net.num_depth = D
+        res.append(run(name, net, sample(views, 512, 640), D * 128 * 160, feat_mvs))
+    # cfg3: Vis-MVSNet, 1+4 views, 640x512, default [32,16,8] and eval [64,32,16] hypotheses per stage
+    feat_vis = lambda net, s: ops.map_views(net.model.feat_ext, torch.unbind(s["imgs"], 1))
+    for name, nums, scales in (("cfg3 Vis-MVSNet 1+4 views 640x512 depth_nums [32,16,8]", [32, 16, 8], [4, 2, 1]),
+                               ("cfg3' Vis-MVSNet eval setting depth_nums [64,32,16]", [64, 32, 16], [2, 1, 0.5])):
+        net = Vis()
+        synth.randomize_norm_stats(net, seed=2)
+        net.depth_nums, net.interval_scales = nums, scales
+        vox = nums[0] * 64 * 80 + nums[1] * 128 * 160 + nums[2] * 256 * 320
+        res.append(run(name, net, sample(5, 512, 640), vox, feat_vis, depth_nums=nums, interval_scales=scales))
+    # cfg4: CVP-MVSNet, 1+4 views, 1600x1184, 5 pyramid levels (eval: 96 coarse hypotheses, 8 per refinement level)
+    feat_cvp = lambda net, s: ops.map_views(lambda im: net.model.featurePyramid(im, 5), torch.unbind(s["imgs"], 1))
+    net = CVP()
+    synth.randomize_norm_stats(net, seed=3)
+    vox = 96 * 74 * 100 + 8 * (148 * 200 + 296 * 400 + 592 * 800 + 1184 * 1600)
+    res.append(run("cfg4 CVP-MVSNet 1+4 views 1600x1184 nscale=5", net, sample(5, 1184, 1600), vox, feat_cvp, nscale=5))
+    out = sys.argv[1] if len(sys.argv) > 1 else None
+    if out:
+        json.dump({"engine": ops.DEFAULT_ENGINE, "gpu": torch.cuda.get_device_name(0), "results": res}, open(out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

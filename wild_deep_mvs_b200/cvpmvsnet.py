@@ -236,8 +236,8 @@ class network(nn.Module):
             raise NotImplementedError("libmvsb200 implements inference only; call .eval() (SURVEY.md 8-f2)")
         nscale = kwargs["nscale"] if "nscale" in kwargs else self.nscale
         with torch.no_grad():
-            ref_pyr = self.featurePyramid(ref_img, nscale)
-            src_pyrs = [self.featurePyramid(im, nscale) for im in src_imgs]
+            pyrs = ops.map_views(lambda im: self.featurePyramid(im, nscale), [ref_img] + list(src_imgs))
+            ref_pyr, src_pyrs = pyrs[0], pyrs[1:]
             ref_in_ms = condition_intrinsics(ref_in, ref_img.shape, [f.shape for f in ref_pyr])
             src_in_ms = torch.stack([condition_intrinsics(src_in[:, i], ref_img.shape, [f.shape for f in src_pyrs[i]])
                                      for i in range(len(src_imgs))]).permute(1, 0, 2, 3, 4)

@@ -210,8 +210,8 @@ class MVSNet(nn.Module):
 
     def extract_features(self, imgs):
         if self.aggregation.startswith("norm"):
-            return [F.normalize(self.feature(img), dim=1) for img in imgs]
-        return [self.feature(img) for img in imgs]
+            return [F.normalize(f, dim=1) for f in ops.map_views(self.feature, imgs)]
+        return ops.map_views(self.feature, imgs)
 
     # ---- channels-last engine entry (what forward uses) ------------------------------------------
     def cost_volume_cl(self, ref_nhwc, srcs_nhwc, ref_proj, src_projs, depth_values):

@@ -65,6 +65,24 @@ def absmax(t):
     return a
 
 
+def map_views(extract, imgs):
+    """Run a 2-D feature extractor over the views of a sample.  The reference calls it once per view
+    (models/MVSNet/model.py:195, VisMVSNet/frontend.py:59-62, CVP_MVSNet/models/net.py:110-114); when the views have the
+    same size they go through as ONE batch (same weights, per-sample arithmetic unchanged), which cuts the launch count
+    of these small CNNs by the number of views.  `extract` returns a tensor or a list/tuple of tensors; the result is a
+    list with one such item per view."""
+    imgs = list(imgs)
+    if len(imgs) > 1 and all(im.shape == imgs[0].shape for im in imgs[1:]):
+        b = imgs[0].shape[0]
+        out = extract(torch.cat(imgs, 0))
+        if isinstance(out, torch.Tensor):
+            return list(torch.split(out, b, 0))
+        per_level = [torch.split(o, b, 0) for o in out]
+        return [type(out)(lvl[v] for lvl in per_level) if isinstance(out, tuple) else [lvl[v] for lvl in per_level]
+                for v in range(len(imgs))]
+    return [extract(im) for im in imgs]
+
+
 def to_nhwc(x):
     """[B,C,H,W] (any strides) -> contiguous [B,H,W,C]."""
     return x.permute(0, 2, 3, 1).contiguous()

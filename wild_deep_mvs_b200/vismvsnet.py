@@ -287,7 +287,8 @@ class Frontend(nn.Module):
                                           depth_min[:, reference_frame], depth_interval[:, reference_frame])
             src_cams = torch.stack([self.fill_cam_array(K[:, i], R[:, i], t[:, i], depth_min[:, i], depth_interval[:, i])
                                     for i in src_idx], 1)
-            feats = [[ops.to_nhwc(f) for f in self.model.feat_ext(imgs[i])] for i in [reference_frame] + src_idx]
+            feats = [[ops.to_nhwc(f) for f in fv]
+                     for fv in ops.map_views(self.model.feat_ext, [imgs[i] for i in [reference_frame] + src_idx])]
             ests, probs, pairs = self.depth_from_features(feats, ref_cam, src_cams, depth_min[:, reference_frame],
                                                           depth_interval[:, reference_frame].contiguous(), depth_nums,
                                                           interval_scales)
