@@ -56,6 +56,25 @@ def run(name, net, s, vox, feat_fn, **kw):
     return r
 
 
+def vis_graphed(name, net, s, vox, nums, scales):
+    """Hot path of Vis-MVSNet replayed as one CUDA graph (features resident): what the launch-bound eager number hides."""
+    net = net.to(DEV).eval()
+    with torch.no_grad():
+        interval = ((s["depth_max"] - s["depth_min"]) / 128)
+        ref_cam = net.fill_cam_array(s["K"][:, 0], s["R"][:, 0], s["t"][:, 0], s["depth_min"][:, 0], interval[:, 0])
+        src_cams = torch.stack([net.fill_cam_array(s["K"][:, i], s["R"][:, i], s["t"][:, i], s["depth_min"][:, i], interval[:, i])
+                                for i in range(1, s["K"].shape[1])], 1)
+        feats = [[ops.to_nhwc(f) for f in fv] for fv in ops.map_views(net.model.feat_ext, torch.unbind(s["imgs"], 1))]
+        g = net.graphed(feats, ref_cam, src_cams, s["depth_min"][:, 0].contiguous(), interval[:, 0].contiguous(), nums, scales)
+        eager = net.depth_from_features(feats, ref_cam, src_cams, s["depth_min"][:, 0].contiguous(), interval[:, 0].contiguous(), nums, scales)
+        assert torch.equal(g()[0][2], eager[0][2])
+        ms = timed(lambda: g(), reps=20, warmup=3)
+    r = {"config": name + " -- hot path as one CUDA graph", "voxels": vox, "hot_path_ms": round(ms, 3),
+         "hot_path_Mvox_per_s": round(vox / ms / 1e3, 1)}
+    print(json.dumps(r), flush=True)
+    return r
+
+
 def main():
     torch.manual_seed(0)
     res = []
@@ -76,6 +95,7 @@ def main():
         net.depth_nums, net.interval_scales = nums, scales
         vox = nums[0] * 64 * 80 + nums[1] * 128 * 160 + nums[2] * 256 * 320
         res.append(run(name, net, sample(5, 512, 640), vox, feat_vis, depth_nums=nums, interval_scales=scales))
+        res.append(vis_graphed(name, net, sample(5, 512, 640), vox, nums, scales))
     # cfg4: CVP-MVSNet, 1+4 views, 1600x1184, 5 pyramid levels (eval: 96 coarse hypotheses, 8 per refinement level)
     feat_cvp = lambda net, s: ops.map_views(lambda im: net.model.featurePyramid(im, 5), torch.unbind(s["imgs"], 1))
     net = CVP()

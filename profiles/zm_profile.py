@@ -16,11 +16,16 @@ lib.mvsb200_debug_zm_profile.restype = ctypes.c_int
 lib.mvsb200_debug_zm_profile.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]
 dev = "cuda:0"
 torch.manual_seed(0)
-LAYERS = [("conv0", 32, 8, 1, False, (192, 128, 160)), ("conv1", 8, 16, 2, False, (192, 128, 160)),
-          ("conv2", 16, 16, 1, False, (96, 64, 80)), ("conv9", 32, 16, 2, True, (48, 32, 40)),
-          ("conv11", 16, 8, 2, True, (96, 64, 80))]
+LAYERS = [("conv0", 32, 8, 1, False, (1, 192, 128, 160)), ("conv1", 8, 16, 2, False, (1, 192, 128, 160)),
+          ("conv2", 16, 16, 1, False, (1, 96, 64, 80)), ("conv9", 32, 16, 2, True, (1, 48, 32, 40)),
+          ("conv11", 16, 8, 2, True, (1, 96, 64, 80)),
+          # Vis-MVSNet Reg blocks: 4 source views on the batch axis, stage 3 / stage 1 volumes
+          ("vis8x8s3", 8, 8, 1, False, (4, 8, 256, 320)), ("vis8x8s1", 8, 8, 1, False, (4, 32, 64, 80)),
+          ("vis8x16s3", 8, 16, 2, False, (4, 8, 256, 320)), ("visup-s3", 16, 8, 2, True, (4, 4, 128, 160))]
+if len(sys.argv) > 1:
+    LAYERS = [l for l in LAYERS if any(a in l[0] for a in sys.argv[1:])]
 for name, cin, cout, stride, tr, dims in LAYERS:
-    x = torch.randn(1, *dims, cin, device=dev)
+    x = torch.randn(*dims, cin, device=dev)
     w = torch.randn((cin, cout, 3, 3, 3) if tr else (cout, cin, 3, 3, 3), device=dev) / (cin * 27) ** 0.5
     layer = ops.PackedConv(w, None, stride=stride, transposed=tr, relu=True)
     y = ops.conv3d(x, layer, engine="zm")

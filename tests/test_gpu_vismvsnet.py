@@ -94,3 +94,19 @@ def test_forward_api(golden):
     est, heads = out["depth_pair_list"][0][0]
     assert est.shape == (2, 1, 32, 40) and heads[0].shape == (2, 1, 32, 40)
     assert all(torch.isfinite(d).all() for d in out["depth_est_list"])
+
+
+def test_graphed_cascade_equals_eager(golden):
+    """Frontend.graphed: the three stages replayed as one CUDA graph give exactly the eager result, also on new inputs."""
+    g = golden("vis")
+    net = _load(g)
+    feats, ref_cam, src_cams, dmin, interval = _inputs(g)
+    args = (net.depth_nums, net.interval_scales)
+    graphed = net.graphed(feats, ref_cam, src_cams, dmin, interval, *args)
+    want, _, _ = net.depth_from_features(feats, ref_cam, src_cams, dmin, interval, *args)
+    got, probs, pairs = graphed()
+    assert all(torch.equal(a, b) for a, b in zip(got, want))
+    feats2 = [[f.flip(2).contiguous() for f in fv] for fv in feats]
+    want2, _, _ = net.depth_from_features(feats2, ref_cam, src_cams, dmin, interval, *args)
+    got2, _, _ = graphed(feats2)
+    assert all(torch.equal(a, b) for a, b in zip(got2, want2)) and not torch.equal(got2[2], want[2])

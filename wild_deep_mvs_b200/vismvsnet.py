@@ -206,8 +206,10 @@ class SingleStage(nn.Module):
         warp = ops.vis_homography_params(ref_cam, src_cams, 1.0 / s_scale)
         cost = ops.build_cost_volume(ref, srcs, warp, depth_start, D, L.GEOM_VIS, L.AGG_GROUPCORR,
                                      interval=depth_interval, groups=8)            # [S,B,D,H,W,8]
-        interm = _RegUNet.run(pk["reg"], cost.view(S * B, D, H, W, 8))              # pairs stacked on the batch axis
-        del cost
+        cost_sb = cost.view(S * B, D, H, W, 8)                                      # pairs stacked on the batch axis
+        cost_sb._mvs_amax = cost._mvs_amax                                          # abs-max tracked by K1 (views drop attributes)
+        interm = _RegUNet.run(pk["reg"], cost_sb)
+        del cost, cost_sb
         score = ops.conv3d(interm, pk["pair_head"]).squeeze(-1)                     # [S*B,D,H,W]
         start_sb = depth_start.repeat(S, *([1] * (depth_start.dim() - 1)))
         pair = ops.depth_regress(score, start_sb, interval=depth_interval.reshape(-1).repeat(S), want_entropy=True)
@@ -215,8 +217,10 @@ class SingleStage(nn.Module):
         u = ops.conv3d(ent, pk["u1"])
         u = ops.conv3d(u, pk["u2"], skip=ent.expand(-1, -1, -1, -1, 8).contiguous())  # out += x (broadcast), model_cas.py:95
         u = ops.conv3d(u, pk["uh"]).view(S, B, H, W)
+        interm_amax = interm._mvs_amax
         interm = interm.view(S, B, D, H, W, 8)
         fused = ops.vis_fuse([interm[s] for s in range(S)], [u[s] for s in range(S)])
+        fused._mvs_amax = interm_amax   # a convex combination of the per-pair volumes: their abs-max bounds it
         pair_depth = pair["depth"].view(S, B, H, W)
         pairs = [[pair_depth[s].unsqueeze(1), [u[s].unsqueeze(1)]] for s in range(S)]
         del interm
@@ -232,6 +236,35 @@ class Model(nn.Module):
         self.stage1 = SingleStage()
         self.stage2 = SingleStage()
         self.stage3 = SingleStage()
+
+
+class _GraphedCascade:
+    def __init__(self, net, feats, ref_cam, src_cams, depth_min, depth_interval, depth_nums, interval_scales, warmup=2):
+        self.feats = [[f.clone() for f in fv] for fv in feats]
+        self.ref_cam, self.src_cams = ref_cam.clone(), src_cams.clone()
+        self.depth_min, self.depth_interval = depth_min.clone(), depth_interval.clone()
+        args = (self.feats, self.ref_cam, self.src_cams, self.depth_min, self.depth_interval, depth_nums, interval_scales)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):   # first calls pack weights and set kernel attributes: keep them out of the capture
+            for _ in range(warmup):
+                net.depth_from_features(*args)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = net.depth_from_features(*args)
+
+    def __call__(self, feats=None, ref_cam=None, src_cams=None, depth_min=None, depth_interval=None):
+        if feats is not None:
+            for dv, sv in zip(self.feats, feats):
+                for d, s in zip(dv, sv):
+                    d.copy_(s, non_blocking=True)
+        for dst, src in ((self.ref_cam, ref_cam), (self.src_cams, src_cams), (self.depth_min, depth_min),
+                         (self.depth_interval, depth_interval)):
+            if src is not None:
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.out
 
 
 class Frontend(nn.Module):
@@ -271,6 +304,13 @@ class Frontend(nn.Module):
             probs.append(p)
             pairs.append(pr)
         return ests, probs, pairs
+
+    def graphed(self, feats, ref_cam, src_cams, depth_min, depth_interval, depth_nums, interval_scales):
+        """CUDA-graph version of depth_from_features for inputs of these shapes: the ~90 launches of the three stages
+        (and the PyTorch glue between them) replay as one graph.  Returns a callable taking the same tensors (copied
+        into the captured buffers) and returning (ests, probs, pairs) -- the captured outputs, overwritten by the next
+        replay."""
+        return _GraphedCascade(self, feats, ref_cam, src_cams, depth_min, depth_interval, depth_nums, interval_scales)
 
     def forward(self, imgs, K, R, t, depth_min, depth_max, reference_frame=0, **kwargs):
         if self.training:
