@@ -197,6 +197,16 @@ MVSB200_API int mvsb200_depth_regress(const float *score, int B, int D, int H, i
                           float *entropy_out, float *prob_out, mvsb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K5: the per-pixel part of CVP-MVSNet's calDepthHypo (models/CVP_MVSNet/models/modules.py:131-226), fp64 inside:
+ * abs_delta[b][y*W+x] = |depth change that moves the projection of pixel (x,y) at depth ref_depth[b][y][x] into the
+ * first source view by one pixel along the epipolar line|, +inf where the reference's validity test fails
+ * (modules.py:206-209).  The level's hypothesis interval is the (lower) median of the finite entries.
+ * ref_depth [B,H,W] fp32; ref_in, src_in [B,3,3] (level-conditioned intrinsics, first source view); ref_ex, src_ex
+ * [B,4,4]; abs_delta [B,H*W] fp64. */
+MVSB200_API int mvsb200_cvp_depth_delta(const float *ref_depth, const float *ref_in, const float *src_in, const float *ref_ex,
+                                        const float *src_ex, int B, int H, int W, double *abs_delta, mvsb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * K4: visibility-weighted fusion of per-pair volumes (models/VisMVSNet/model_cas.py:354-357,385-386):
  *   fused = sum_s exp(-uncert_s) * interm_s / sum_s exp(-uncert_s)
  * interm, uncert: HOST arrays of S device pointers; interm[s] [B,D,H,W,G], uncert[s] [B,H,W]. */

@@ -118,3 +118,36 @@ def test_full_size_properties():
     assert torch.equal(out["depth"], out_b["depth"])
     coarse_up = torch.nn.functional.interpolate(out["depth_est_list"][1][None], scale_factor=2, mode="bilinear")[0]
     assert (out["depth"] - coarse_up).abs().mean() < 0.05 * (hi - lo)
+
+
+def test_k5_depth_hypotheses_against_oracle():
+    """K5 (calDepthHypo): per-pixel fp64 solve + device median vs the numpy restatement of modules.py:131-226, incl. a
+    batch of two different cameras, invalid pixels (depth behind the source camera) and the degenerate fallback."""
+    from wild_deep_mvs_b200.cvpmvsnet import cal_depth_hypo
+    rng = np.random.default_rng(4)
+    B, H, W = 2, 37, 53
+    K, R, tt, dmin, dmax = synth.make_cameras(B, 3, 4 * H, 4 * W)
+    K = K.clone()
+    K[:, :, :2] /= 4
+    R[1, 1] = R[0, 2]                     # second sample: a different relative pose
+    tt[1, 1] = tt[0, 2] * 1.5
+    last = torch.tensor([0., 0., 0., 1.])
+    E = torch.cat((torch.cat((R, tt), dim=3), last.view(1, 1, 1, 4).expand(B, 3, 1, 4)), dim=2)
+    depth = (425 + 480 * rng.random((B, H, W))).astype(np.float32)
+    depth[0, :3] = -50.0                  # behind the cameras: fails the z > 1e-8 test, excluded from the median
+    d = torch.from_numpy(depth).to(DEV)
+    got = cal_depth_hypo(d, K[:, 0].to(DEV), K[:, 1:].to(DEV), E[:, 0].to(DEV), E[:, 1:].to(DEV), dmin[:, 0].to(DEV), dmax[:, 0].to(DEV))
+    assert got.dtype == torch.float32 and got.shape == (B, 8, H, W)
+    for b in range(B):
+        want = nets.cvp_depth_hypos(depth[b], K[b, 0].numpy(), K[b, 1].numpy(), E[b, 0].numpy(), E[b, 1].numpy(),
+                                    float(dmin[b, 0]), float(dmax[b, 0]))
+        assert rel_linf(got[b].cpu().numpy(), want) < 1e-6
+        step = float(got[b, 5, 10, 10] - got[b, 4, 10, 10])
+        assert 0.05 < step < 500.0        # a plausible interval: about one pixel of parallax on a 53-pixel-wide map
+    # the raw per-pixel values: +inf exactly where the reference's validity test fails
+    delta = ops.cvp_depth_delta(d, K[:, 0].to(DEV), K[:, 1].to(DEV), E[:, 0].to(DEV), E[:, 1].to(DEV)).view(B, H, W)
+    assert torch.isinf(delta[0, :3]).all() and torch.isfinite(delta[0, 3:]).all() and torch.isfinite(delta[1]).all()
+    # identical cameras: no parallax, every pixel invalid -> the (max - min) / 128 fallback (modules.py:211-213)
+    got = cal_depth_hypo(d[:1], K[:1, 0].to(DEV), K[:1, :1].to(DEV), E[:1, 0].to(DEV), E[:1, :1].to(DEV), dmin[:1, 0].to(DEV), dmax[:1, 0].to(DEV))
+    step = (got[0, 5] - got[0, 4])[5:].cpu().numpy()
+    assert np.allclose(step, (905.0 - 425.0) / 128, rtol=1e-4)

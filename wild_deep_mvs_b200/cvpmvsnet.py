@@ -136,47 +136,20 @@ def sweeping_depth_hypos(depth_min, depth_max, n):
 def cal_depth_hypo(ref_depths, ref_in, src_in, ref_ex, src_ex, depth_min, depth_max, d=4):
     """Per-level hypotheses depth_up + k * interval, k in [-d, d), with the interval = median over pixels of the depth
     change that moves the projection into the FIRST source view by one pixel along the epipolar line (fp64).
-    Restates calDepthHypo, models/CVP_MVSNet/models/modules.py:131-226.  ref_depths [B,H,W]; ref_in [B,3,3];
-    src_in [B,S,3,3]; ref_ex [B,4,4]; src_ex [B,S,4,4] -> [B,2d,H,W] fp32."""
+    calDepthHypo, models/CVP_MVSNet/models/modules.py:131-226: the per-pixel solve is K5 (mvsb200_cvp_depth_delta), the
+    median a device sort -- no host synchronisation.  ref_depths [B,H,W]; ref_in [B,3,3]; src_in [B,S,3,3];
+    ref_ex [B,4,4]; src_ex [B,S,4,4] -> [B,2d,H,W] fp32."""
     B, H, W = ref_depths.shape
-    dev = ref_depths.device
+    delta = ops.cvp_depth_delta(ref_depths, ref_in, src_in[:, 0], ref_ex, src_ex[:, 0])          # [B,HW] fp64, +inf = invalid
+    nvalid = torch.isfinite(delta).sum(1)
+    srt = torch.sort(delta, dim=1).values
+    med = srt.gather(1, ((nvalid - 1).clamp(min=0) // 2).unsqueeze(1)).squeeze(1)                 # torch.median: the lower middle value
+    fallback = ((depth_max - depth_min) / 128).double()                                           # degenerate geometry (modules.py:211-213)
+    interval = torch.where(nvalid > 0, med, fallback)
+    steps = torch.arange(-d, d, device=ref_depths.device, dtype=torch.float64).view(1, -1, 1, 1)
     hyp = ref_depths.unsqueeze(1).repeat(1, 2 * d, 1, 1)
-    steps = torch.arange(-d, d, device=dev, dtype=torch.float64).view(-1, 1, 1)
-    xx, yy = torch.meshgrid(torch.arange(W, device=dev), torch.arange(H, device=dev), indexing="ij")  # x-major (:151)
-    X = torch.stack([xx.reshape(-1), yy.reshape(-1), torch.ones(H * W, device=dev, dtype=torch.long)], 0).double()
-    ones = torch.ones(1, H * W, device=dev, dtype=torch.float64)
-    for b in range(B):
-        Kr, Ks = ref_in[b].double(), src_in[b, 0].double()
-        Er, Es = ref_ex[b].double(), src_ex[b, 0].double()
-        D1 = ref_depths[b].t().reshape(-1)  # fp32 until it meets the fp64 grid (:161-165)
-        D2 = D1 + 1
-        Kr_inv, Er_inv = torch.inverse(Kr), torch.inverse(Er)
-
-        def to_src(Dv):
-            ray = Kr_inv @ (X * Dv)
-            P = Er_inv @ torch.cat([ray, ones], 0)
-            P = Ks @ (Es @ P)[:3]
-            z = P[2].clone()
-            return P / z, z
-
-        X1, X1d = to_src(D1)
-        X2, X2d = to_src(D2)
-        dirv = X2 - X1
-        nrm = torch.norm(dirv, dim=0)
-        X3 = X1 + dirv / torch.clamp(nrm, min=1e-8)
-        A = (Kr @ Er[:3, :3]) @ torch.inverse(Ks @ Es[:3, :3])
-        tmp1 = X1d * (A @ X1)
-        tmp2 = A @ X3
-        M1 = torch.cat([X.t().unsqueeze(2), tmp2.t().unsqueeze(2)], 2)[:, 1:, :]
-        M2 = tmp1.t()[:, 1:]
-        valid = (nrm > 1e-8) & (X1d > 1e-8) & (X2d > 1e-8) & (torch.abs(torch.det(M1)) > 1e-8)
-        if valid.sum() > 0:
-            delta = torch.matmul(torch.inverse(M1[valid]), M2.unsqueeze(2)[valid])[:, 0, 0]
-        else:  # degenerate geometry (modules.py:211-213)
-            delta = ((depth_max[b] - depth_min[b]) / 128).double() * torch.ones_like(X1d)
-        interval = torch.abs(delta).median()
-        hyp[b] += (steps * interval).expand(2 * d, H, W)   # in-place add of fp64 into the fp32 map (:219)
-    return hyp.float()
+    hyp += steps * interval.view(B, 1, 1, 1)   # in-place add of fp64 into the fp32 map (:219)
+    return hyp
 
 
 class network(nn.Module):

@@ -349,3 +349,18 @@ def vis_fuse(interms, uncerts):
     out = torch.empty_like(interms[0])
     L.check(lib.mvsb200_vis_fuse(ip, up, S, B, D, H, W, G, _ptr(out), _stream()), "mvsb200_vis_fuse")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K5
+# ------------------------------------------------------------------------------------------------
+def cvp_depth_delta(ref_depth, ref_in, src_in, ref_ex, src_ex):
+    """ref_depth [B,H,W]; ref_in, src_in [B,3,3]; ref_ex, src_ex [B,4,4] -> |delta| [B,H*W] fp64, +inf where invalid
+    (the per-pixel solve of calDepthHypo, CVP_MVSNet/models/modules.py:131-214)."""
+    ref_depth = _dev_f32(ref_depth.contiguous(), "ref_depth")
+    B, H, W = ref_depth.shape
+    mats = [_dev_f32(m.contiguous(), n) for m, n in ((ref_in, "ref_in"), (src_in, "src_in"), (ref_ex, "ref_ex"), (src_ex, "src_ex"))]
+    out = torch.empty(B, H * W, device=ref_depth.device, dtype=torch.float64)
+    L.check(L.load().mvsb200_cvp_depth_delta(_ptr(ref_depth), *[_ptr(m) for m in mats], B, H, W, _ptr(out), _stream()),
+            "mvsb200_cvp_depth_delta")
+    return out
