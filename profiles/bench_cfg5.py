@@ -1,0 +1,90 @@
+"""BASELINE cfg5: Vis-MVSNet over a batch of 64 reference views (each 1+4 views, 640x512, 128-interval range, eval
+setting depth_nums [64,32,16]) sharded over the GPUs of one box -- contiguous blocks of reference views per rank, no
+data-path collective, ONE NCCL all-gather of the depth maps at the end (models/trainer.py:101,246-247).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P profiles/bench_cfg5.py [out.json]
+
+Features are resident in HBM (the hot path: features -> depth; the 2-D extractor is row f1); every rank replays the
+three-stage cascade as one CUDA graph per reference view; timed on the device, max over ranks.
+"""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from wild_deep_mvs_b200 import ops, shard, synth  # noqa: E402
+from wild_deep_mvs_b200.vismvsnet import Frontend as Vis  # noqa: E402
+
+N_VIEWS, NUMS, SCALES = 64, [64, 32, 16], [2, 1, 0.5]
+
+
+def main():
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    net = Vis()
+    synth.randomize_norm_stats(net, seed=2)
+    net.depth_nums, net.interval_scales = NUMS, SCALES
+    net = net.to(dev).eval()
+    a, b = shard.block_partition(N_VIEWS, world, rank)
+    with torch.no_grad():
+        s = {k: v.to(dev) for k, v in synth.make_sample(1, 5, 512, 640, seed=rank).items()}
+        interval = (s["depth_max"] - s["depth_min"]) / 128
+        ref_cam = net.fill_cam_array(s["K"][:, 0], s["R"][:, 0], s["t"][:, 0], s["depth_min"][:, 0], interval[:, 0])
+        src_cams = torch.stack([net.fill_cam_array(s["K"][:, i], s["R"][:, i], s["t"][:, i], s["depth_min"][:, i], interval[:, i])
+                                for i in range(1, 5)], 1)
+        feats = [[ops.to_nhwc(f) for f in fv] for fv in ops.map_views(net.model.feat_ext, torch.unbind(s["imgs"], 1))]
+        g = net.graphed(feats, ref_cam, src_cams, s["depth_min"][:, 0].contiguous(), interval[:, 0].contiguous(), NUMS, SCALES)
+        # every reference view of the block: its own features (here: the sample's maps scaled per view, so that the
+        # gathered result can be checked), copied into the graph's buffers, one replay, depth map kept
+        maps = torch.empty(b - a, 256, 320, device=dev)
+
+        def block():
+            for i in range(a, b):
+                gain = 1.0 + 0.01 * i
+                ests, _, _ = g([[f * gain for f in fv] for fv in feats])
+                maps[i - a].copy_(ests[2][0])
+            return shard.gather_depth_maps(maps, N_VIEWS)
+
+        for _ in range(2):
+            out = block()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        ea.record()
+        for _ in range(reps):
+            out = block()
+        eb.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ea.elapsed_time(eb) / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # every rank holds all 64 maps, ordered by global view index; view i of any rank equals a single-GPU run of view i
+        assert out.shape == (N_VIEWS, 256, 320) and torch.isfinite(out).all()
+        chk = g([[f * (1.0 + 0.01 * 5) for f in fv] for fv in feats])[0][2][0]
+        same_inputs = world == 1 or rank == 0   # ranks use different samples (seed = rank): only rank 0 owns view 5's inputs
+        if same_inputs:
+            assert torch.equal(out[5], chk)
+    vox = NUMS[0] * 64 * 80 + NUMS[1] * 128 * 160 + NUMS[2] * 256 * 320
+    if rank == 0:
+        ms = t.item()
+        r = {"config": "cfg5 Vis-MVSNet, 64 reference views (1+4 views, 640x512, depth_nums [64,32,16]), view-sharded + 1 all-gather",
+             "n_gpus": world, "ms_per_batch_of_64": round(ms, 2), "depth_maps_per_s": round(N_VIEWS / ms * 1e3, 1),
+             "hot_path_Mvox_per_s": round(N_VIEWS * vox / ms / 1e3, 1), "gathered_bytes": N_VIEWS * 256 * 320 * 4}
+        print(json.dumps(r))
+        if len(sys.argv) > 1:
+            json.dump(r, open(sys.argv[1], "w"), indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
