@@ -213,6 +213,16 @@ MVSB200_API int mvsb200_cvp_depth_delta(const float *ref_depth, const float *ref
 MVSB200_API int mvsb200_vis_fuse(const float *const *interm, const float *const *uncert, int S, int B, int D, int H, int W,
                      int G, float *fused, mvsb200_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * K6: UncertNet of Vis-MVSNet (models/VisMVSNet/model_cas.py:77-98) fused into one kernel:
+ *   u = head( relu(bn2(conv2( relu(bn1(conv1(e))) ))) + e ),   e = per-pair entropy map, all convs 3x3, pad 1.
+ * entropy, out: [N,H,W] device (N = pairs x batch).  params_host: HOST array of 752 floats
+ *   w1[9][8] (tap-major, tap = ky*3+kx), scale1[8], bias1[8], w2[9][8 in][8 out], scale2[8], bias2[8], w_head[9][8]
+ * (eval-mode BatchNorm folded into scale/bias); they become launch parameters. */
+#define MVSB200_UNCERT_PARAMS 752
+MVSB200_API int mvsb200_vis_uncert_net(const float *entropy, int N, int H, int W, const float *params_host, float *out,
+                                       mvsb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

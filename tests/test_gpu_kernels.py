@@ -341,3 +341,31 @@ def test_errors_are_loud():
                               torch.zeros(1, 1, 16, device=DEV), torch.ones(1, 2, device=DEV), 2, L.GEOM_MVS, L.AGG_VARIANCE)
     with pytest.raises(L.Mvsb200Error):
         ops.conv3d(torch.zeros(1, 4, 4, 4, 16), layer)  # CPU tensor
+
+
+def test_k6_uncert_net_against_oracle():
+    """Fused UncertNet (conv 1->8 + BN + ReLU, conv 8->8 + BN + ReLU + input, 8->1 head) vs the composed oracle convs,
+    on maps whose sizes are not multiples of the 16 x 16 tile."""
+    from oracle import nets
+    rng = np.random.default_rng(21)
+    N, H, W = 3, 37, 53
+    ent = rng.random((N, H, W)).astype(np.float32) * 3
+    sd = {"u.conv1.0.weight": (rng.standard_normal((8, 1, 3, 3)) / 3).astype(np.float32),
+          "u.conv2.0.weight": (rng.standard_normal((8, 8, 3, 3)) / 8).astype(np.float32),
+          "u.head_convs.0.weight": (rng.standard_normal((1, 8, 3, 3)) / 8).astype(np.float32)}
+    bns = []
+    for name in ("u.conv1.1", "u.conv2.1"):
+        bn = torch.nn.BatchNorm2d(8).to(DEV).eval()
+        with torch.no_grad():
+            bn.weight.copy_(cu(rng.random(8) + 0.5)); bn.bias.copy_(cu(rng.standard_normal(8) * 0.1))
+            bn.running_mean.copy_(cu(rng.standard_normal(8) * 0.1)); bn.running_var.copy_(cu(rng.random(8) + 0.5))
+        for k in ("weight", "bias", "running_mean", "running_var"):
+            sd[name + "." + k] = getattr(bn, k).detach().cpu().numpy()
+        bns.append(bn)
+    params = ops.uncert_net_params(ops.PackedConv(cu(sd["u.conv1.0.weight"]), bns[0], relu=True),
+                                   ops.PackedConv(cu(sd["u.conv2.0.weight"]), bns[1], relu=True),
+                                   ops.PackedConv(cu(sd["u.head_convs.0.weight"])))
+    got = ops.vis_uncert_net(cu(ent), params).cpu().numpy()
+    for n in range(N):
+        want = nets.vis_uncert_net(sd, "u.", ent[n][None])
+        assert rel_linf(got[n], want[0]) < 1e-5

@@ -351,6 +351,24 @@ def vis_fuse(interms, uncerts):
     return out
 
 
+def uncert_net_params(conv1, conv2, head):
+    """Host parameter block of mvsb200_vis_uncert_net from three PackedConv (2-D, BN folded): a ctypes float array."""
+    parts = [conv1.w.reshape(-1), conv1.scale, conv1.bias, conv2.w.reshape(-1), conv2.scale, conv2.bias, head.w.reshape(-1)]
+    flat = torch.cat([t.detach().float().reshape(-1).cpu() for t in parts])
+    if flat.numel() != 752:
+        raise L.Mvsb200Error("uncert_net_params: expected 752 parameters, got %d" % flat.numel())
+    return (ctypes.c_float * 752)(*flat.tolist())
+
+
+def vis_uncert_net(entropy, params):
+    """entropy [N,H,W] -> log-uncertainty [N,H,W] (UncertNet, VisMVSNet/model_cas.py:77-98, one fused kernel)."""
+    entropy = _dev_f32(entropy.contiguous(), "entropy")
+    N, H, W = entropy.shape
+    out = torch.empty_like(entropy)
+    L.check(L.load().mvsb200_vis_uncert_net(_ptr(entropy), N, H, W, params, _ptr(out), _stream()), "mvsb200_vis_uncert_net")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # K5
 # ------------------------------------------------------------------------------------------------

@@ -189,6 +189,8 @@ class SingleStage(nn.Module):
                 "u2": ops.PackedConv(u.conv2[0].weight, u.conv2[1], relu=True, skip_mode=L.SKIP_AFTER_RELU),
                 "uh": ops.PackedConv(u.head_convs[0].weight),
             }
+            pk = self._packed
+            pk["uncert"] = ops.uncert_net_params(pk["u1"], pk["u2"], pk["uh"])
             self._key = key
         return self._packed
 
@@ -213,10 +215,7 @@ class SingleStage(nn.Module):
         score = ops.conv3d(interm, pk["pair_head"]).squeeze(-1)                     # [S*B,D,H,W]
         start_sb = depth_start.repeat(S, *([1] * (depth_start.dim() - 1)))
         pair = ops.depth_regress(score, start_sb, interval=depth_interval.reshape(-1).repeat(S), want_entropy=True)
-        ent = pair["entropy"].view(S * B, 1, H, W, 1)
-        u = ops.conv3d(ent, pk["u1"])
-        u = ops.conv3d(u, pk["u2"], skip=ent.expand(-1, -1, -1, -1, 8).contiguous())  # out += x (broadcast), model_cas.py:95
-        u = ops.conv3d(u, pk["uh"]).view(S, B, H, W)
+        u = ops.vis_uncert_net(pair["entropy"].view(S * B, H, W), pk["uncert"]).view(S, B, H, W)   # K6, model_cas.py:77-98
         interm_amax = interm._mvs_amax
         interm = interm.view(S, B, D, H, W, 8)
         fused = ops.vis_fuse([interm[s] for s in range(S)], [u[s] for s in range(S)])
