@@ -266,6 +266,47 @@ __global__ void k2_conv3d_naive_kernel(const K2Params p, int stride, int transpo
     p.y[i] = v;
 }
 
+// 1x1x1 convolution (the stride-2 projection shortcut of Vis-MVSNet's BasicBlock, nn_utils.py:150-158): a per-voxel
+// Cin x Cout matrix product.  One thread per (output voxel, 4 output channels); the weights sit in shared memory,
+// the input voxel is a handful of 16-byte loads that the threads of a voxel share through L1.
+__global__ void __launch_bounds__(256) k2_pointwise_kernel(const K2Params p, int stride)
+{
+    extern __shared__ float s_wpt[];   // [Cin][Cout]
+    for (int i = threadIdx.x; i < p.Cin1 * p.Cout; i += blockDim.x) s_wpt[i] = __ldg(p.w + i);
+    __syncthreads();
+    const int q4 = p.Cout >> 2;
+    const long long n = (long long)p.B * p.Do * p.Ho * p.Wo * q4;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c4 = (int)(i % q4);
+    long long r = i / q4;
+    const int ox = (int)(r % p.Wo); r /= p.Wo;
+    const int oy = (int)(r % p.Ho); r /= p.Ho;
+    const int oz = (int)(r % p.Do);
+    const int b = (int)(r / p.Do);
+    const float *xin = p.x + ((((long long)b * p.D + (long long)oz * stride) * p.H + (long long)oy * stride) * p.W + (long long)ox * stride) * p.Cin1;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < p.Cin1; c += 4) {
+        const float4 v = ldg4(xin + c);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float4 w = *reinterpret_cast<const float4 *>(&s_wpt[(c + k) * p.Cout + c4 * 4]);
+            acc.x = fmaf(vv[k], w.x, acc.x); acc.y = fmaf(vv[k], w.y, acc.y); acc.z = fmaf(vv[k], w.z, acc.z); acc.w = fmaf(vv[k], w.w, acc.w);
+        }
+    }
+    const long long o = (i / q4) * p.Cout + c4 * 4;
+    float y[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (p.scale) { const float4 s4 = ldg4(p.scale + c4 * 4); y[0] *= s4.x; y[1] *= s4.y; y[2] *= s4.z; y[3] *= s4.w; }
+    if (p.bias) { const float4 b4 = ldg4(p.bias + c4 * 4); y[0] += b4.x; y[1] += b4.y; y[2] += b4.z; y[3] += b4.w; }
+    float4 sk = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.skip_mode != MVSB200_SKIP_NONE) sk = ldg4(p.skip + o);
+    if (p.skip_mode == MVSB200_SKIP_BEFORE_RELU) { y[0] += sk.x; y[1] += sk.y; y[2] += sk.z; y[3] += sk.w; }
+    if (p.relu) { y[0] = fmaxf(y[0], 0.f); y[1] = fmaxf(y[1], 0.f); y[2] = fmaxf(y[2], 0.f); y[3] = fmaxf(y[3], 0.f); }
+    if (p.skip_mode == MVSB200_SKIP_AFTER_RELU) { y[0] += sk.x; y[1] += sk.y; y[2] += sk.z; y[3] += sk.w; }
+    st4(p.y + o, make_float4(y[0], y[1], y[2], y[3]));
+}
+
 template <int MODE, int COUT_T>
 static int launch_tiled(K2Params p, cudaStream_t st)
 {
@@ -349,6 +390,13 @@ extern "C" int mvsb200_conv3d(const mvsb200_conv3d_desc *d, const float *x, cons
     p.tiles_x = p.tiles_y = p.tiles_z = 0;
     cudaStream_t st = (cudaStream_t)stream;
 
+    if (d->kd == 1 && d->kh == 1 && d->kw == 1 && !d->transposed && d->Cin2 == 0 && d->Cin % 4 == 0 && d->Cout % 4 == 0 &&
+        (size_t)d->Cin * d->Cout * sizeof(float) <= 48 * 1024) {
+        const long long n = (long long)p.B * p.Do * p.Ho * p.Wo * (p.Cout / 4);
+        MVSB200_REQUIRE(n < (1ll << 31) * 256, "conv3d: volume too large");
+        k2_pointwise_kernel<<<(unsigned)((n + 255) / 256), 256, (size_t)d->Cin * d->Cout * sizeof(float), st>>>(p, d->stride);
+        return check_launch("k2_pointwise_kernel");
+    }
     const bool tiled_ok = (d->Cin % 8 == 0) && (d->Cin2 % 8 == 0) && (d->Cout == 1 || d->Cout % 8 == 0);
     if (!tiled_ok) {
         const long long n = (long long)p.B * p.Do * p.Ho * p.Wo * p.Cout;

@@ -132,12 +132,14 @@ class _RegUNet(nn.Module):
         }
 
     @staticmethod
-    def run(pk, x):
-        e0 = ops.conv3d(ops.conv3d(x, pk["b0c1"]), pk["b0c2"], skip=x)
-        r = ops.conv3d(e0, pk["b1ds"])
-        e1 = ops.conv3d(ops.conv3d(e0, pk["b1c1"]), pk["b1c2"], skip=r)
-        up = ops.conv3d(e1, pk["up"])
-        return ops.conv3d(up, pk["post"], x2=e0)  # conv(cat([up, e0], 1)), nn_utils.py:268-269
+    def run(pk, x, am):
+        """am: ops.AmaxPool -- abs-max scalars of the layer outputs (one fill for the whole stage)."""
+        conv = lambda t, name, **kw: ops.conv3d(t, pk[name], amax=am.take(), **kw)
+        e0 = conv(conv(x, "b0c1"), "b0c2", skip=x)
+        r = conv(e0, "b1ds")
+        e1 = conv(conv(e0, "b1c1"), "b1c2", skip=r)
+        up = conv(e1, "up")
+        return conv(up, "post", x2=e0)  # conv(cat([up, e0], 1)), nn_utils.py:268-269
 
 
 class Reg(nn.Module):
@@ -205,12 +207,13 @@ class SingleStage(nn.Module):
         D = depth_num
         if D % 2 or H % 2 or W % 2:
             raise L.Mvsb200Error("Vis-MVSNet regulariser needs even D,H,W (got %d,%d,%d)" % (D, H, W))
+        am = ops.AmaxPool(ref.device, 24)
         warp = ops.vis_homography_params(ref_cam, src_cams, 1.0 / s_scale)
         cost = ops.build_cost_volume(ref, srcs, warp, depth_start, D, L.GEOM_VIS, L.AGG_GROUPCORR,
-                                     interval=depth_interval, groups=8)            # [S,B,D,H,W,8]
+                                     interval=depth_interval, groups=8, amax=am.take())   # [S,B,D,H,W,8]
         cost_sb = cost.view(S * B, D, H, W, 8)                                      # pairs stacked on the batch axis
         cost_sb._mvs_amax = cost._mvs_amax                                          # abs-max tracked by K1 (views drop attributes)
-        interm = _RegUNet.run(pk["reg"], cost_sb)
+        interm = _RegUNet.run(pk["reg"], cost_sb, am)
         del cost, cost_sb
         score = ops.conv3d(interm, pk["pair_head"]).squeeze(-1)                     # [S*B,D,H,W]
         start_sb = depth_start.repeat(S, *([1] * (depth_start.dim() - 1)))
@@ -223,7 +226,7 @@ class SingleStage(nn.Module):
         pair_depth = pair["depth"].view(S, B, H, W)
         pairs = [[pair_depth[s].unsqueeze(1), [u[s].unsqueeze(1)]] for s in range(S)]
         del interm
-        fscore = ops.conv3d(_RegUNet.run(pk["fuse"], fused), pk["fuse_head"]).squeeze(-1)
+        fscore = ops.conv3d(_RegUNet.run(pk["fuse"], fused, am), pk["fuse_head"]).squeeze(-1)
         out = ops.depth_regress(fscore, depth_start, interval=depth_interval, conf_mode=L.CONF_WINDOW)
         return out["depth"], out["conf"], pairs
 
