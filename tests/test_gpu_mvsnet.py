@@ -181,3 +181,19 @@ def test_streamed_pinned_host_samples_equal_eager(golden):
     for (d, c), (wd, wc) in zip(got, want):
         assert torch.equal(d, wd.cpu()) and torch.equal(c, wc.cpu())
     assert not torch.equal(got[0][0], got[1][0])
+
+
+def test_feature_net_fused_inference_path_equals_module_path():
+    """FeatureNet under no_grad runs conv + folded BN + ReLU as one cuDNN call per layer; it must agree with the plain
+    conv -> BatchNorm -> ReLU modules (taken when grad mode is on)."""
+    torch.manual_seed(0)
+    net = MVSNet("variance").feature
+    synth.randomize_norm_stats(net, seed=5)
+    net = net.to(DEV).eval()
+    x = torch.rand(3, 3, 96, 128, device=DEV)
+    with torch.no_grad():
+        fused = net(x)
+    with torch.enable_grad():
+        plain = net(x).detach()
+    assert fused.shape == plain.shape == (3, 32, 24, 32)
+    assert rel_linf(fused.cpu().numpy(), plain.cpu().numpy()) < 1e-3   # cuDNN may pick TF32 algorithms for either path

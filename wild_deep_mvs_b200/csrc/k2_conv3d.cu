@@ -327,15 +327,7 @@ static int launch_tiled(K2Params p, cudaStream_t st)
         set_error("conv3d: volume too large");
         return MVSB200_E_INVALID;
     }
-    static bool attr_set = false;  // per template instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k2_conv3d_kernel<MODE, COUT_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        if (e != cudaSuccess) {
-            set_error("conv3d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return MVSB200_E_CUDA;
-        }
-        attr_set = true;
-    }
+    if (int rc = ensure_dynamic_smem(k2_conv3d_kernel<MODE, COUT_T>, 100 * 1024, "conv3d")) return rc;
     dim3 grid((unsigned)tiles, (unsigned)(p.Cout / COUT_T), (MODE == MODE_DECONV) ? 8 : 1);
     k2_conv3d_kernel<MODE, COUT_T><<<grid, K2_THREADS, smem, st>>>(p);
     return check_launch("k2_conv3d_kernel");

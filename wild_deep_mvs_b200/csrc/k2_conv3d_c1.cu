@@ -123,15 +123,8 @@ static int launch_c1(const mvsb200_conv3d_desc *d, const float *x, const float *
         return MVSB200_E_INVALID;
     }
     const size_t smem = (size_t)2 * (CIN / 4) * C1_NPOS * sizeof(float4);
-    static bool attr_set = false;   // per template instantiation
-    if (!attr_set && smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k2_conv3d_c1_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            set_error("conv3d_c1: cudaFuncSetAttribute(%zu bytes): %s", smem, cudaGetErrorString(e));
-            return MVSB200_E_CUDA;
-        }
-        attr_set = true;
-    }
+    if (smem > 48 * 1024)
+        if (int rc = ensure_dynamic_smem(k2_conv3d_c1_kernel<CIN>, smem, "conv3d_c1")) return rc;
     k2_conv3d_c1_kernel<CIN><<<(unsigned)blocks, C1_THREADS, smem, st>>>(p);
     return check_launch("k2_conv3d_c1_kernel");
 }

@@ -406,15 +406,7 @@ static int launch_tc(TcParams p, cudaStream_t st)
         set_error("conv3d_tc: volume too large");
         return MVSB200_E_INVALID;
     }
-    static bool attr_set = false;  // per template instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k2_conv3d_tc_kernel<MODE, CT, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            set_error("conv3d_tc: cudaFuncSetAttribute(%zu bytes): %s", smem, cudaGetErrorString(e));
-            return MVSB200_E_CUDA;
-        }
-        attr_set = true;
-    }
+    if (int rc = ensure_dynamic_smem(k2_conv3d_tc_kernel<MODE, CT, NPROD>, smem, "conv3d_tc")) return rc;
     dim3 grid((unsigned)tiles, (unsigned)((p.Cout + CT - 1) / CT), (MODE == TC_DECONV) ? 8 : 1);
     k2_conv3d_tc_kernel<MODE, CT, NPROD><<<grid, TC_THREADS, smem, st>>>(p);
     return check_launch("k2_conv3d_tc_kernel");

@@ -904,15 +904,7 @@ static int launch_zm(ZmParams p, int sm_count, cudaStream_t st)
         return MVSB200_E_INVALID;
     }
     p.ntiles = (int)tiles;
-    static size_t attr_smem = 0;  // per template instantiation
-    if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(k2_conv3d_zm_kernel<MODE, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            set_error("conv3d_zm: cudaFuncSetAttribute(%zu bytes): %s", smem, cudaGetErrorString(e));
-            return MVSB200_E_CUDA;
-        }
-        attr_smem = smem;
-    }
+    if (int rc = ensure_dynamic_smem(k2_conv3d_zm_kernel<MODE, CT>, smem, "conv3d_zm")) return rc;
     dim3 grid((unsigned)(tiles < ctas ? tiles : ctas), (unsigned)nblocks, 1);
     if (MODE == ZM_DECONV && grid.x % 4) grid.x = (grid.x + 3) / 4 * 4;   // ntiles is a multiple of 4
     k2_conv3d_zm_kernel<MODE, CT><<<grid, ZM_THREADS, smem, st>>>(p);
@@ -1014,12 +1006,9 @@ extern "C" int mvsb200_conv3d_zm(const mvsb200_conv3d_desc *d, const float *x, c
     p.relu = d->relu; p.skip_mode = d->skip_mode;
     p.tiles_x = p.tiles_y = p.nseg = p.zseg = p.ntiles = p.nstages = 0;
     p.profile = g_zm_prof_on;
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
-    }
+    int sm_count = 0, dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
     cudaStream_t st = (cudaStream_t)stream;
     const int mode = zm_mode(d), ct = zm_ct(d);
     if (mode == ZM_S1) return ct == 8 ? launch_zm<ZM_S1, 8>(p, sm_count, st) : launch_zm<ZM_S1, 16>(p, sm_count, st);

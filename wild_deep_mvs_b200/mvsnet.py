@@ -38,8 +38,31 @@ class FeatureNet(nn.Module):
             setattr(self, "conv%d" % i, _cbr2d(*s))
         self.feature = nn.Conv2d(32, 32, 3, 1, 1)
 
+    def _folded(self):
+        """Eval-mode BatchNorm folded into the conv weights / bias (cached until a parameter or buffer changes)."""
+        key = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        if getattr(self, "_fold_key", None) != key:
+            fold = []
+            for i in range(7):
+                m = getattr(self, "conv%d" % i)
+                scale = m.bn.weight / torch.sqrt(m.bn.running_var + m.bn.eps)
+                w = (m.conv.weight * scale.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
+                fold.append((w, (m.bn.bias - m.bn.running_mean * scale).contiguous(), m.conv.stride, m.conv.padding))
+            self._fold, self._fold_key = fold, key
+        return self._fold
+
     def forward(self, x):
         x = x.contiguous(memory_format=torch.channels_last)
+        if not self.training and x.is_cuda and not torch.is_grad_enabled():
+            # inference: conv + folded BN + ReLU as ONE cuDNN call per layer instead of three kernels (row f1 of
+            # SURVEY.md 8-f stays library code; this only removes two passes over every activation)
+            x_in = x
+            try:
+                for w, b, stride, pad in self._folded():
+                    x = torch.cudnn_convolution_relu(x, w, b, stride, pad, (1, 1), 1)
+                return self.feature(x)
+            except RuntimeError:
+                x = x_in   # no fused cuDNN kernel for this shape: the plain path below
         for i in range(7):
             m = getattr(self, "conv%d" % i)
             x = F.relu(m.bn(m.conv(x)), inplace=True)
