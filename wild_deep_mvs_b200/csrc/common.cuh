@@ -21,22 +21,13 @@ inline int check_launch(const char *what)
     return MVSB200_OK;
 }
 
-// Opt a kernel into `bytes` of dynamic shared memory.  The attribute is per device: remembered per (kernel, device) so
-// that a process driving several GPUs (nn.DataParallel worker threads) configures each of them.
+// Opt a kernel into `bytes` of dynamic shared memory.  The attribute is per (kernel, device): remembered in a small
+// table so that a process driving several GPUs (nn.DataParallel worker threads) configures each of them.
+// (Keyed by the kernel's ADDRESS: all instantiations of a kernel template share one function-pointer type.)
+int ensure_dynamic_smem_impl(const void *kernel, size_t bytes, const char *what);
 template <typename K> inline int ensure_dynamic_smem(K kernel, size_t bytes, const char *what)
 {
-    constexpr int MAXDEV = 64;
-    static size_t done[MAXDEV] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < MAXDEV && done[dev] >= bytes) return MVSB200_OK;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) {
-        set_error("%s: cudaFuncSetAttribute(%zu bytes): %s", what, bytes, cudaGetErrorString(e));
-        return MVSB200_E_CUDA;
-    }
-    if (dev >= 0 && dev < MAXDEV) done[dev] = bytes;
-    return MVSB200_OK;
+    return ensure_dynamic_smem_impl(reinterpret_cast<const void *>(kernel), bytes, what);
 }
 
 #define MVSB200_REQUIRE(cond, ...)          \

@@ -1,5 +1,6 @@
 // Error plumbing, device query and the two geometry prologue kernels of mvsb200.h.
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -16,6 +17,29 @@ void set_error(const char *fmt, ...)
 }
 
 void clear_error() { g_err[0] = 0; }
+
+int ensure_dynamic_smem_impl(const void *kernel, size_t bytes, const char *what)
+{
+    struct Entry { const void *kernel; int dev; size_t bytes; };
+    static Entry table[256];
+    static int n = 0;
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    Entry *e = nullptr;
+    for (int i = 0; i < n; i++)
+        if (table[i].kernel == kernel && table[i].dev == dev) e = &table[i];
+    if (e && e->bytes >= bytes) return MVSB200_OK;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (err != cudaSuccess) {
+        set_error("%s: cudaFuncSetAttribute(%zu bytes): %s", what, bytes, cudaGetErrorString(err));
+        return MVSB200_E_CUDA;
+    }
+    if (!e && n < 256) e = &table[n++];
+    if (e) { e->kernel = kernel; e->dev = dev; e->bytes = bytes; }
+    return MVSB200_OK;
+}
 
 // ---- small dense fp64 helpers (one thread does a whole camera pair) -----------------------------
 
