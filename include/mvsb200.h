@@ -223,6 +223,15 @@ MVSB200_API int mvsb200_vis_fuse(const float *const *interm, const float *const 
 MVSB200_API int mvsb200_vis_uncert_net(const float *entropy, int N, int H, int W, const float *params_host, float *out,
                                        mvsb200_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * K7: 2-D convolution + folded BatchNorm + ReLU over channels-last maps (fp32, CUDA cores): ConvBnReLU of
+ * models/MVSNet/module.py:9-17 as used by FeatureNet (models/MVSNet/model.py:21-41), row f1 of SURVEY.md 8.
+ *   y = act(conv(x, w) * scale + bias),  padding k/2;  (k, stride) in {(3,1), (5,2)};  Cin in {4,8,16,32} (a 3-channel
+ *   image is passed zero-padded to 4 channels), Cout in {8,16,32}.
+ * x [B,H,W,Cin], w [k*k][Cin][Cout] (tap-major, tap = ky*k+kx), scale/bias [Cout] or NULL, y [B,Ho,Wo,Cout]. */
+MVSB200_API int mvsb200_conv2d(int B, int H, int W, int Cin, int Cout, int k, int stride, int relu, const float *x, const float *w,
+                               const float *scale, const float *bias, float *y, mvsb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,20 @@ def mvsnet_from_features(sd, feats, rel_projs, depth_values, aggregation="varian
 # ---------------------------------------------------------------------------------------------
 # Vis-MVSNet Reg / RegFuse UNet -- models/VisMVSNet/model_cas.py:38-74, nn_utils.py:123-278
 # ---------------------------------------------------------------------------------------------
+def mvsnet_featurenet(sd, img, prefix="feature."):
+    """FeatureNet, models/MVSNet/model.py:21-41: seven ConvBnReLU (module.py:9-17; k5 s2 at layers 2 and 5) and a
+    biased 3x3 conv.  img [3,H,W] -> [32,H/4,W/4]."""
+    spec = [(3, 1), (3, 1), (5, 2), (3, 1), (3, 1), (5, 2), (3, 1)]
+    x = img
+    for i, (k, s) in enumerate(spec):
+        w = sd[prefix + "conv%d.conv.weight" % i]
+        x = orc.conv3d(x[:, None], w[:, :, None], None, s, (0, k // 2, k // 2))[:, 0]
+        # a stride also applies to the dummy depth axis: D = 1, kd = 1, pad 0 -> one output plane
+        x = _bn(sd, prefix + "conv%d.bn" % i, x, True)
+    w = sd[prefix + "feature.weight"]
+    return orc.conv3d(x[:, None], w[:, :, None], sd[prefix + "feature.bias"], 1, (0, 1, 1))[:, 0]
+
+
 def _basic_block(sd, p, x, stride):  # nn_utils.py:123-171
     y = orc.conv3d(x, sd[p + ".conv1.weight"], None, stride)
     y = _bn(sd, p + ".bn1", y, True)

@@ -38,31 +38,31 @@ class FeatureNet(nn.Module):
             setattr(self, "conv%d" % i, _cbr2d(*s))
         self.feature = nn.Conv2d(32, 32, 3, 1, 1)
 
-    def _folded(self):
-        """Eval-mode BatchNorm folded into the conv weights / bias (cached until a parameter or buffer changes)."""
+    def _pack(self):
+        """Layers packed for K7 (mvsb200_conv2d): BN folded, 3-channel image weights padded to 4 input channels."""
         key = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
-        if getattr(self, "_fold_key", None) != key:
-            fold = []
+        if getattr(self, "_pack_key", None) != key:
+            pk = []
             for i in range(7):
                 m = getattr(self, "conv%d" % i)
-                scale = m.bn.weight / torch.sqrt(m.bn.running_var + m.bn.eps)
-                w = (m.conv.weight * scale.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
-                fold.append((w, (m.bn.bias - m.bn.running_mean * scale).contiguous(), m.conv.stride, m.conv.padding))
-            self._fold, self._fold_key = fold, key
-        return self._fold
+                pk.append(ops.PackedConv2d(m.conv.weight, m.bn, stride=m.conv.stride[0], relu=True))
+            pk.append(ops.PackedConv2d(self.feature.weight, None, conv_bias=self.feature.bias))
+            self._packed, self._pack_key = pk, key
+        return self._packed
+
+    def run(self, x):
+        """x [B,3,H,W] (any memory format) -> channels-last features [B,H/4,W/4,32] through K7."""
+        B, C, H, W = x.shape
+        x4 = torch.zeros(B, H, W, 4, device=x.device, dtype=torch.float32)
+        x4[..., :C] = x.permute(0, 2, 3, 1)
+        for layer in self._pack():
+            x4 = ops.conv2d(x4, layer)
+        return x4
 
     def forward(self, x):
-        x = x.contiguous(memory_format=torch.channels_last)
         if not self.training and x.is_cuda and not torch.is_grad_enabled():
-            # inference: conv + folded BN + ReLU as ONE cuDNN call per layer instead of three kernels (row f1 of
-            # SURVEY.md 8-f stays library code; this only removes two passes over every activation)
-            x_in = x
-            try:
-                for w, b, stride, pad in self._folded():
-                    x = torch.cudnn_convolution_relu(x, w, b, stride, pad, (1, 1), 1)
-                return self.feature(x)
-            except RuntimeError:
-                x = x_in   # no fused cuDNN kernel for this shape: the plain path below
+            return self.run(x).permute(0, 3, 1, 2)   # reference layout [B,32,h,w] as a view of channels-last memory
+        x = x.contiguous(memory_format=torch.channels_last)
         for i in range(7):
             m = getattr(self, "conv%d" % i)
             x = F.relu(m.bn(m.conv(x)), inplace=True)

@@ -370,6 +370,45 @@ def vis_uncert_net(entropy, params):
 
 
 # ------------------------------------------------------------------------------------------------
+# K7
+# ------------------------------------------------------------------------------------------------
+class PackedConv2d:
+    """A 2-D conv (+ eval-mode BatchNorm) packed for mvsb200_conv2d: weights [k*k][Cin_padded][Cout], folded scale/bias."""
+
+    def __init__(self, weight, bn=None, conv_bias=None, stride=1, relu=False):
+        w = weight.detach().float()                      # [Cout,Cin,k,k]
+        self.cout, cin, self.k, _ = w.shape
+        self.cin = (cin + 3) // 4 * 4                    # a 3-channel image is consumed zero-padded to 4 channels
+        if self.cin != cin:
+            w = torch.cat([w, w.new_zeros(self.cout, self.cin - cin, self.k, self.k)], 1)
+        self.w = w.permute(2, 3, 1, 0).contiguous()
+        self.stride, self.relu = stride, int(relu)
+        if bn is not None:
+            scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+            bias = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+            if conv_bias is not None:
+                bias = bias + conv_bias.detach().float() * scale
+            self.scale, self.bias = scale.contiguous(), bias.contiguous()
+        else:
+            self.scale = None
+            self.bias = conv_bias.detach().float().contiguous() if conv_bias is not None else None
+
+
+def conv2d(x, layer):
+    """x [B,H,W,Cin] channels-last -> [B,Ho,Wo,Cout] (K7)."""
+    x = _dev_f32(x, "x")
+    B, H, W, C = x.shape
+    if C != layer.cin:
+        raise L.Mvsb200Error("conv2d: input has %d channels, layer expects %d" % (C, layer.cin))
+    pad = layer.k // 2
+    ho, wo = (H + 2 * pad - layer.k) // layer.stride + 1, (W + 2 * pad - layer.k) // layer.stride + 1
+    y = torch.empty(B, ho, wo, layer.cout, device=x.device, dtype=torch.float32)
+    L.check(L.load().mvsb200_conv2d(B, H, W, C, layer.cout, layer.k, layer.stride, layer.relu, _ptr(x), _ptr(layer.w),
+                                    _ptr(layer.scale), _ptr(layer.bias), _ptr(y), _stream()), "mvsb200_conv2d")
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
 # K5
 # ------------------------------------------------------------------------------------------------
 def cvp_depth_delta(ref_depth, ref_in, src_in, ref_ex, src_ex):
