@@ -66,6 +66,51 @@ def mvsnet_featurenet(sd, img, prefix="feature."):
     return orc.conv3d(x[:, None], w[:, :, None], sd[prefix + "feature.bias"], 1, (0, 1, 1))[:, 0]
 
 
+def _c2d(x, w, stride=1, pad=None):
+    """nn.Conv2d on [C,H,W] through the 3-D oracle conv (a one-plane volume, kd = 1)."""
+    k = w.shape[2]
+    pad = k // 2 if pad is None else pad
+    return orc.conv3d(x[:, None], w[:, :, None], None, stride, (0, pad, pad))[:, 0]
+
+
+def _basic_block2d(sd, p, x, stride):  # nn_utils.py:123-171 with dim = 2
+    y = _bn(sd, p + ".bn1", _c2d(x, sd[p + ".conv1.weight"], stride), True)
+    y = _bn(sd, p + ".bn2", _c2d(y, sd[p + ".conv2.weight"]), False)
+    if (p + ".downsample.0.weight") in sd:
+        r = _bn(sd, p + ".downsample.1", _c2d(x, sd[p + ".downsample.0.weight"], stride, 0), False)
+    else:
+        r = x
+    return np.maximum(y + r, 0.0).astype(np.float32)
+
+
+def _deconv2d(x, w):
+    """nn.ConvTranspose2d(k=3, stride=2, padding=1, output_padding=1) on [C,H,W]: the 3-D oracle deconv on a one-plane
+    volume with the 2-D kernel as the middle depth tap; output plane 0 is the 2-D result."""
+    w3 = np.zeros(w.shape[:2] + (3, 3, 3), np.float32)
+    w3[:, :, 1] = w
+    return orc.deconv3d(x[:, None], w3, None, 2, 1, 1)[:, 0]
+
+
+def vis_featext(sd, img, prefix="model.feat_ext."):
+    """FeatExt, models/VisMVSNet/model_cas.py:18-35 over UNet(16, 2, 1, 2, [], [32, 64, 128], [], '2d', 2)
+    (nn_utils.py:194-278).  img [3,H,W] -> features at 1/8, 1/4, 1/2 resolution, each [32,h,w]."""
+    x = _bn(sd, prefix + "init_conv.1", _c2d(img, sd[prefix + "init_conv.0.weight"], 2), True)
+    u = prefix + "unet."
+    enc = []
+    for name, stride in (("2d2_0", 1), ("2d4_1", 2), ("2d8_2", 2)):
+        x = _basic_block2d(sd, u + "enc_blocks.%s.0" % name, x, stride)
+        x = _basic_block2d(sd, u + "enc_blocks.%s.1" % name, x, 1)
+        enc.append(x)
+    outs = [x]
+    for i, name in enumerate(("2d16_3", "2d8_4")):
+        d = u + "dec_blocks.%s." % name
+        x = _deconv2d(x, sd[d + "0.weight"])
+        x = _c2d(np.concatenate([x, enc[-2 - i]], 0), sd[d + "1.weight"])
+        x = _basic_block2d(sd, d + "2.0", x, 1)
+        outs.append(x)
+    return [_c2d(o, sd[prefix + "final_conv_%d.weight" % (k + 1)]) for k, o in enumerate(outs)]
+
+
 def _basic_block(sd, p, x, stride):  # nn_utils.py:123-171
     y = orc.conv3d(x, sd[p + ".conv1.weight"], None, stride)
     y = _bn(sd, p + ".bn1", y, True)

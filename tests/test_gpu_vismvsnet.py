@@ -110,3 +110,29 @@ def test_graphed_cascade_equals_eager(golden):
     want2, _, _ = net.depth_from_features(feats2, ref_cam, src_cams, dmin, interval, *args)
     got2, _, _ = graphed(feats2)
     assert all(torch.equal(a, b) for a, b in zip(got2, want2)) and not torch.equal(got2[2], want[2])
+
+
+def test_featext_on_library_kernels_against_reference_golden(golden):
+    """Row f1: FeatExt.run executes the extractor on K7 (stem), the K2 engines over one-plane volumes (U-Net) and the
+    pointwise kernel (1x1 shortcuts); checked against the features the reference produced for the same image and weights
+    (tests/golden/featext.npz) and against the plain PyTorch modules at a size with several tiles.  (Opt-in in forward:
+    the cuDNN modules are still faster for these 64-128 channel 2-D layers.)"""
+    g = golden("featext")
+    net = Frontend().model.feat_ext
+    net.load_state_dict({k[len("model.feat_ext."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("model.feat_ext.")},
+                        strict=True)
+    net = net.to(DEV).eval()
+    with torch.no_grad():
+        got = [f.permute(0, 3, 1, 2) for f in net.run(torch.from_numpy(g["img"]).to(DEV))]
+    for k in range(3):
+        assert got[k].shape == g["feat_s%d" % (k + 1)].shape
+        assert rel_linf(got[k].cpu().numpy(), g["feat_s%d" % (k + 1)]) < 2e-5
+    x = torch.rand(2, 3, 136, 200, device=DEV)
+    with torch.no_grad():
+        lib = [f.permute(0, 3, 1, 2) for f in net.run(x)]
+    with torch.enable_grad():
+        torch.backends.cudnn.allow_tf32, old = False, torch.backends.cudnn.allow_tf32
+        plain = [t.detach() for t in net(x)]
+        torch.backends.cudnn.allow_tf32 = old
+    for a, b in zip(lib, plain):
+        assert a.shape == b.shape and rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 1e-4

@@ -12,6 +12,8 @@ Per stage (SingleStage.forward, models/VisMVSNet/model_cas.py:303-420, mode='sof
 FeatExt (2-D U-Net) and the bilinear up-sampling of the previous stage's depth stay in PyTorch ("next" rows).
 Inference only.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -90,6 +92,29 @@ class _FeatUNet(nn.Module):
         return outs
 
 
+def _w3d(w2d):
+    """A 3x3 2-D kernel as the middle depth tap of a 3x3x3 kernel: on a one-plane volume ([N,1,H,W,C]) the 3-D conv
+    engines (K2) then compute exactly the 2-D convolution -- the planes above and below are padding, and the z-march
+    engine does not even stage them."""
+    w3 = w2d.new_zeros(w2d.shape[0], w2d.shape[1], 3, w2d.shape[2], w2d.shape[3])
+    w3[:, :, 1] = w2d
+    return w3
+
+
+def _pack_block2d(b):
+    """BasicBlock (nn_utils.py:123-171) of the 2-D U-Net packed for K2 on one-plane volumes."""
+    pk = {"c1": ops.PackedConv(_w3d(b.conv1.weight), b.bn1, stride=b.stride, relu=True),
+          "c2": ops.PackedConv(_w3d(b.conv2.weight), b.bn2, relu=True, skip_mode=L.SKIP_BEFORE_RELU)}
+    if b.downsample is not None:
+        pk["ds"] = ops.PackedConv(b.downsample[0].weight, b.downsample[1], stride=b.stride)   # 1x1: pointwise kernel
+    return pk
+
+
+def _run_block2d(pk, x):
+    r = ops.conv3d(x, pk["ds"]) if "ds" in pk else x
+    return ops.conv3d(ops.conv3d(x, pk["c1"]), pk["c2"], skip=r)
+
+
 class FeatExt(nn.Module):
     """models/VisMVSNet/model_cas.py:18-35: 32-channel features at 1/8, 1/4, 1/2 image resolution."""
 
@@ -101,7 +126,52 @@ class FeatExt(nn.Module):
         self.final_conv_2 = nn.Conv2d(64, 32, 3, 1, 1, bias=False)
         self.final_conv_3 = nn.Conv2d(32, 32, 3, 1, 1, bias=False)
 
+    def _pack(self):
+        key = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        if getattr(self, "_pack_key", None) != key:
+            u = self.unet
+            pk = {"init": ops.PackedConv2d(self.init_conv[0].weight, self.init_conv[1], stride=2, relu=True),
+                  "enc": [[_pack_block2d(b) for b in layer] for layer in u.enc_blocks],
+                  "dec": [{"up": ops.PackedConv(_w3d(d[0].weight), None, stride=2, transposed=True),
+                           "post": ops.PackedConv(_w3d(d[1].weight), None),
+                           "blocks": [_pack_block2d(b) for b in d[2]]} for d in u.dec_blocks],
+                  "final": [ops.PackedConv(_w3d(c.weight), None) for c in (self.final_conv_1, self.final_conv_2, self.final_conv_3)]}
+            self._packed, self._pack_key = pk, key
+        return self._packed
+
+    def run(self, x):
+        """x [N,3,H,W] -> three channels-last feature maps [N,H/8,W/8,32], [N,H/4,W/4,32], [N,H/2,W/2,32], every layer on
+        the library's kernels (row f1): the 5x5 stride-2 stem on K7, the U-Net on the K2 engines over one-plane volumes,
+        the 1x1 shortcuts on the pointwise kernel."""
+        pk = self._pack()
+        N, C, H, W = x.shape
+        x4 = torch.zeros(N, H, W, 4, device=x.device, dtype=torch.float32)
+        x4[..., :C] = x.permute(0, 2, 3, 1)
+        v = ops.conv2d(x4, pk["init"]).unsqueeze(1)                      # [N,1,H/2,W/2,16]
+        enc = []
+        for layer in pk["enc"]:
+            for b in layer:
+                v = _run_block2d(b, v)
+            enc.append(v)
+        outs = [v]
+        for i, d in enumerate(pk["dec"]):
+            up = ops.conv3d(v, d["up"])                                   # the 3-D transposed conv doubles the plane count:
+            amax = getattr(up, "_mvs_amax", None)                        # (tracked by the z-march engine only)
+            up = up[:, :1].contiguous()                                   # plane 0 is the 2-D result, plane 1 has no taps
+            if amax is not None:
+                up._mvs_amax = amax
+            v = ops.conv3d(up, d["post"], x2=enc[-2 - i])                 # conv(cat([up, enc], 1))
+            for b in d["blocks"]:
+                v = _run_block2d(b, v)
+            outs.append(v)
+        return tuple(ops.conv3d(o, f).squeeze(1) for o, f in zip(outs, pk["final"]))
+
     def forward(self, x):
+        # run() is parity-tested against the reference but, at 4.8 ms for five 640x512 views, slower than the cuDNN
+        # modules below (3.0 ms): 2-D layers with 64-128 channels waste two thirds of the tile engine's taps.  It is
+        # therefore opt-in (MVSB200_VIS_FEATEXT=lib) until K7 grows a tensor-core path for wide layers.
+        if os.environ.get("MVSB200_VIS_FEATEXT") == "lib" and not self.training and x.is_cuda and not torch.is_grad_enabled():
+            return tuple(f.permute(0, 3, 1, 2) for f in self.run(x))      # reference layout as views of channels-last memory
         x = x.contiguous(memory_format=torch.channels_last)
         o1, o2, o3 = self.unet(self.init_conv(x))
         return self.final_conv_1(o1), self.final_conv_2(o2), self.final_conv_3(o3)
