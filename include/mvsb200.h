@@ -170,6 +170,14 @@ MVSB200_API int mvsb200_conv3d_zm_pack(const mvsb200_conv3d_desc *desc, const fl
 MVSB200_API int mvsb200_conv3d_zm(const mvsb200_conv3d_desc *desc, const float *x, const float *x2, const void *packed,
                                   const float *scale, const float *bias, const float *skip, float *y,
                                   const float *x_amax, const float *x2_amax, float *y_amax, mvsb200_stream_t stream);
+/* The same with x being channels [x_first_channel, x_first_channel + desc->Cin) of a tensor with x_channels channels
+ * per voxel.  A layer whose packed weights do not fit the engine's shared memory (Cin * Cout >= 64 * 64) is run as two
+ * launches over the two halves of its input channels, the second adding the first's output as its skip operand
+ * (skip may alias y: every output element is read and written by the same thread). */
+MVSB200_API int mvsb200_conv3d_zm_slice(const mvsb200_conv3d_desc *desc, const float *x, int x_channels, int x_first_channel,
+                                        const float *x2, const void *packed, const float *scale, const float *bias,
+                                        const float *skip, float *y, const float *x_amax, const float *x2_amax,
+                                        float *y_amax, mvsb200_stream_t stream);
 
 /* K2 single-output-channel head (3x3x3, stride 1, Cout == 1, Cin in {8,16,24,32}; MVSNet `prob`, Vis-MVSNet
  * `final_conv`, CVP `prob0`: models/MVSNet/model.py:72, VisMVSNet/model_cas.py:44,61, CVP_MVSNet/models/net.py:67) on the

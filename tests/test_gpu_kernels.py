@@ -369,3 +369,26 @@ def test_k6_uncert_net_against_oracle():
     for n in range(N):
         want = nets.vis_uncert_net(sd, "u.", ent[n][None])
         assert rel_linf(got[n], want[0]) < 1e-5
+
+
+def test_k2_zm_split_over_input_channels_with_fused_epilogue():
+    """A 64 -> 64 layer does not fit the z-march engine's resident-weight budget: ops.conv3d runs it as two launches over
+    the halves of the input channels, the second adding the first's output in place.  BN, ReLU and a skip connection
+    before the activation must come out exactly as for a single launch."""
+    rng = np.random.default_rng(13)
+    dims = (3, 9, 21)
+    x = rng.standard_normal((64,) + dims).astype(np.float32)
+    w = (rng.standard_normal((64, 64, 3, 3, 3)) / np.sqrt(64 * 27)).astype(np.float32)
+    skip = rng.standard_normal((64,) + dims).astype(np.float32)
+    bn = torch.nn.BatchNorm3d(64).to(DEV).eval()
+    with torch.no_grad():
+        bn.weight.copy_(cu(rng.random(64) + 0.5)); bn.bias.copy_(cu(rng.standard_normal(64)))
+        bn.running_mean.copy_(cu(rng.standard_normal(64) * 0.1)); bn.running_var.copy_(cu(rng.random(64) + 0.5))
+    npy = lambda t: t.detach().cpu().numpy()
+    y = orc.bn_relu(orc.conv3d(x, w, None, 1), npy(bn.weight), npy(bn.bias), npy(bn.running_mean), npy(bn.running_var), bn.eps, relu=False)
+    layer = ops.PackedConv(cu(w), bn, relu=True, skip_mode=L.SKIP_BEFORE_RELU)
+    got = ops.conv3d(ndhwc(x), layer, skip=ndhwc(skip), engine="zm")
+    assert rel_linf(from_ndhwc(got), np.maximum(y + skip, 0)) < 1e-5
+    assert float(got._mvs_amax) == float(got.abs().max())
+    plain = ops.PackedConv(cu(w), bn, relu=True)
+    assert rel_linf(from_ndhwc(ops.conv3d(ndhwc(x), plain, engine="zm")), np.maximum(y, 0)) < 1e-5

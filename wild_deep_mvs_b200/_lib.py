@@ -63,6 +63,7 @@ SIGNATURES = {
     "mvsb200_conv3d_zm": (_i, [ctypes.POINTER(Conv3dDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvsb200_conv3d_c1_supported": (_i, [ctypes.POINTER(Conv3dDesc)]),
     "mvsb200_conv3d_c1": (_i, [ctypes.POINTER(Conv3dDesc), _vp, ctypes.POINTER(ctypes.c_float), ctypes.c_float, ctypes.c_float, _vp, _vp]),
+    "mvsb200_conv3d_zm_slice": (_i, [ctypes.POINTER(Conv3dDesc), _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvsb200_depth_regress": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "mvsb200_cvp_depth_delta": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "mvsb200_vis_uncert_net": (_i, [_vp, _i, _i, _i, ctypes.POINTER(ctypes.c_float), _vp, _vp]),

@@ -87,6 +87,7 @@ struct ZmParams {
     int Cin1, Cin2, Cout;
     int relu, skip_mode;
     int tiles_x, tiles_y, nseg, zseg, ntiles, nstages;
+    int x_cstride, x_coff;   // x may be a channel slice of a wider tensor: voxel pitch and first channel (floats)
     int profile;
 };
 
@@ -490,7 +491,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                         const float *src;
                         int cs, cstride;
                         const int cb = c0 - G;   // first chunk of this unit
-                        if (cb < nch1) { src = p.x; cs = cb * 8; cstride = p.Cin1; }
+                        if (cb < nch1) { src = p.x; cs = cb * 8 + p.x_coff; cstride = p.x_cstride; }
                         else { src = p.x2; cs = (cb - nch1) * 8; cstride = p.Cin2; }
                         const int lgp = (G == 4) ? 3 : (G == 2 ? 2 : 1);     // log2(16-byte pieces per voxel)
                         const int nvox = T::EY * XV;
@@ -988,7 +989,17 @@ extern "C" int mvsb200_conv3d_zm(const mvsb200_conv3d_desc *d, const float *x, c
                                  const float *scale, const float *bias, const float *skip, float *y,
                                  const float *x_amax, const float *x2_amax, float *y_amax, mvsb200_stream_t stream)
 {
+    return mvsb200_conv3d_zm_slice(d, x, d ? d->Cin : 0, 0, x2, packed, scale, bias, skip, y, x_amax, x2_amax, y_amax, stream);
+}
+
+extern "C" int mvsb200_conv3d_zm_slice(const mvsb200_conv3d_desc *d, const float *x, int x_channels, int x_first_channel,
+                                       const float *x2, const void *packed, const float *scale, const float *bias,
+                                       const float *skip, float *y, const float *x_amax, const float *x2_amax, float *y_amax,
+                                       mvsb200_stream_t stream)
+{
     MVSB200_REQUIRE(d && x && packed && y && x_amax, "conv3d_zm: null pointer");
+    MVSB200_REQUIRE(x_first_channel >= 0 && x_first_channel % 4 == 0 && x_channels % 4 == 0 && x_first_channel + d->Cin <= x_channels,
+                    "conv3d_zm: channel slice [%d, %d) of %d channels", x_first_channel, x_first_channel + d->Cin, x_channels);
     MVSB200_REQUIRE(zm_shape_ok(d), "conv3d_zm: layer not supported by the z-march engine");
     MVSB200_REQUIRE(d->B > 0 && d->D > 0 && d->H > 0 && d->W > 0, "conv3d_zm: bad shape B=%d D=%d H=%d W=%d", d->B, d->D, d->H, d->W);
     MVSB200_REQUIRE(d->Cin2 == 0 || (x2 && x2_amax), "conv3d_zm: Cin2=%d but x2 / x2_amax is null", d->Cin2);
@@ -1005,6 +1016,7 @@ extern "C" int mvsb200_conv3d_zm(const mvsb200_conv3d_desc *d, const float *x, c
     p.Cin1 = d->Cin; p.Cin2 = d->Cin2; p.Cout = d->Cout;
     p.relu = d->relu; p.skip_mode = d->skip_mode;
     p.tiles_x = p.tiles_y = p.nseg = p.zseg = p.ntiles = p.nstages = 0;
+    p.x_cstride = x_channels; p.x_coff = x_first_channel;
     p.profile = g_zm_prof_on;
     int sm_count = 0, dev = 0;
     cudaGetDevice(&dev);

@@ -220,6 +220,25 @@ class PackedConv:
         self._tc_packed = None
         self._zm_packed = None
         self._c1_host = None
+        self._halves = None
+
+    def halves(self):
+        """The layer split over its input channels into two layers whose sum is this layer (z-march engine, layers whose
+        weights do not fit its shared memory): A = conv(x[:h]) * scale + bias (+ skip before the activation),
+        B = act(conv(x[h:]) * scale + A).  Only layers without a skip after the activation can be split this way."""
+        if self._halves is None:
+            h = self.cin // 2
+            a, b = object.__new__(PackedConv), object.__new__(PackedConv)
+            for part, sl in ((a, slice(0, h)), (b, slice(h, self.cin))):
+                part.w = self.w[..., sl, :].contiguous()
+                part.cin, part.cout, part.k = h, self.cout, self.k
+                part.stride, part.transposed = self.stride, self.transposed
+                part.scale = self.scale
+                part._tc_packed = part._zm_packed = part._c1_host = part._halves = None
+            a.bias, a.relu, a.skip_mode = self.bias, 0, self.skip_mode
+            b.bias, b.relu, b.skip_mode = None, self.relu, L.SKIP_BEFORE_RELU
+            self._halves = (a, b)
+        return self._halves
 
     def c1_host(self):
         """Host copies for the single-output-channel head kernel: (ctypes float array [27*Cin], scale, bias)."""
@@ -304,6 +323,24 @@ def conv3d(x, layer, x2=None, skip=None, engine=None, out=None, amax=None):
                                       _ptr(absmax(x2)) if x2 is not None else None, _ptr(amax), _stream()), "mvsb200_conv3d_zm")
         y._mvs_amax = amax
         return y
+    if (engine == "zm" and x.device == layer.w.device and x2 is None and C1 % 16 == 0 and layer.skip_mode != L.SKIP_AFTER_RELU
+            and layer.k == (3, 3, 3)):
+        # weights too large to stay resident: two launches over the halves of the input channels (see PackedConv.halves)
+        half = L.Conv3dDesc.from_buffer_copy(desc)
+        half.Cin = C1 // 2
+        if lib.mvsb200_conv3d_zm_supported(ctypes.byref(half)):
+            a, b = layer.halves()
+            if amax is None:
+                amax = torch.zeros(1, device=x.device, dtype=torch.float32)
+            xa = _ptr(absmax(x))
+            half.relu, half.skip_mode = a.relu, (a.skip_mode if skip is not None else L.SKIP_NONE)
+            L.check(lib.mvsb200_conv3d_zm_slice(ctypes.byref(half), _ptr(x), C1, 0, None, _ptr(a.zm_packed(half)), _ptr(a.scale),
+                                                _ptr(a.bias), _ptr(skip), _ptr(y), xa, None, None, _stream()), "mvsb200_conv3d_zm_slice")
+            half.relu, half.skip_mode = b.relu, L.SKIP_BEFORE_RELU
+            L.check(lib.mvsb200_conv3d_zm_slice(ctypes.byref(half), _ptr(x), C1, C1 // 2, None, _ptr(b.zm_packed(half)), _ptr(b.scale),
+                                                None, _ptr(y), _ptr(y), xa, None, _ptr(amax), _stream()), "mvsb200_conv3d_zm_slice")
+            y._mvs_amax = amax
+            return y
     if engine != "fp32" and x.device == layer.w.device and lib.mvsb200_conv3d_tc_supported(ctypes.byref(desc)):
         prec = L.PRECISION_TF32 if engine == "tc_tf32" else L.PRECISION_3XTF32
         L.check(lib.mvsb200_conv3d_tc(ctypes.byref(desc), _ptr(x), _ptr(x2), _ptr(layer.tc_packed(desc)), _ptr(layer.scale),
