@@ -31,6 +31,9 @@ K2_ENGINE_NOTE = {
     "tc_tf32": "tc_tf32 (tcgen05 kind::tf32 single pass; outside the parity bar)",
     "fp32": "fp32 (CUDA cores)",
 }
+# library kernels per step: geometry prologue, K1, conv0..conv5, conv6 (two launches: split over input channels),
+# conv7, conv9, conv11, prob (C1 head), K3
+LAUNCHES_PER_STEP = 15
 CFG = {"name": "cfg2", "views": 5, "C": 32, "h": 128, "w": 160, "D": 192}
 
 
@@ -322,7 +325,7 @@ def own_arm(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(world), "maps_per_s": world / (ms_per_step * 1e-3),
-                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": 14 * args.steps,
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP * args.steps,
                 "roofline": roof, "kernels": kernels,
                 "path_hbm": {"algorithmic_bytes_per_map": total_bytes, "achieved_GBps": total_bytes / (ms_per_step * 1e-3) / 1e9,
                              "frac_of_measured_hbm": total_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak()[0]}}
