@@ -240,6 +240,20 @@ MVSB200_API int mvsb200_vis_uncert_net(const float *entropy, int N, int H, int W
 MVSB200_API int mvsb200_conv2d(int B, int H, int W, int Cin, int Cout, int k, int stride, int relu, const float *x, const float *w,
                                const float *scale, const float *bias, float *y, mvsb200_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * K8: geometric-consistency filter of one depth map against its N source depth maps (evaluation/filtering.py:59-84
+ * with utils/utils_3D.py:64-73,98-132,162-178,243-273,296-311), row f3 of SURVEY.md 8.
+ * depth [H,W]; src_depth: HOST array of N device pointers, map i is [src_h[i], src_w[i]] (src_h, src_w: host arrays);
+ * K, R [1+N,3,3], t [1+N,3] (view 0 = the reference view, x_cam = R X + t, intrinsics already divided by the down-scale
+ * factor); thresholds as the reference's --depth_threshold / --max_reproj_error / --min_tri_angle / --num_consistent.
+ * Outputs (bytes, 0/1) [H,W]: mask_depth, mask_disp, geo_mask = at least num_consistent-1 sources agree;
+ * votes [3,H,W] (optional): the number of agreeing sources behind each mask. */
+MVSB200_API int mvsb200_geometric_filter(const float *depth, int H, int W, const float *const *src_depth, const int *src_h,
+                                         const int *src_w, int N, const float *K, const float *R, const float *t,
+                                         float depth_threshold, float max_reproj_error, float min_tri_angle, int num_consistent,
+                                         unsigned char *mask_depth, unsigned char *mask_disp, unsigned char *geo_mask,
+                                         unsigned char *votes, mvsb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,8 @@ SIGNATURES = {
     "mvsb200_cvp_depth_delta": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "mvsb200_vis_uncert_net": (_i, [_vp, _i, _i, _i, ctypes.POINTER(ctypes.c_float), _vp, _vp]),
     "mvsb200_conv2d": (_i, [_i] * 8 + [_vp] * 6),
+    "mvsb200_geometric_filter": (_i, [_vp, _i, _i, ctypes.POINTER(_vp), ctypes.POINTER(_i), ctypes.POINTER(_i), _i, _vp, _vp, _vp,
+                                      ctypes.c_float, ctypes.c_float, ctypes.c_float, _i, _vp, _vp, _vp, _vp, _vp]),
     "mvsb200_vis_fuse": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 
