@@ -24,6 +24,10 @@ NVCC_FLAGS = [
 ]
 
 
+# extra nvcc flags for experiment builds, e.g. MVSB200_NVCC_EXTRA="-DMVSB200_K1_EXPERIMENTS" (profiles/k1_variants.py)
+NVCC_FLAGS += os.environ.get("MVSB200_NVCC_EXTRA", "").split()
+
+
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 

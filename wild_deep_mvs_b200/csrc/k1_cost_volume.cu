@@ -1,9 +1,11 @@
 // K1: fused homography warp + cross-view aggregation (variance / softmin / group correlation).
 //
 // Layout: features NHWC so that each bilinear tap is one contiguous C*4-byte vector; a group of
-// LPV = C/8 lanes owns one reference pixel, each lane 8 channels (two float4).  A warp therefore covers
-// 32/LPV adjacent pixels and every tap is two 16-byte loads per lane, fully coalesced per pixel.  All per-channel
-// arithmetic runs as packed fp32 pairs (FFMA2), and 8 channels per lane halve the shuffles per channel.
+// LPV = C/8 lanes owns one reference pixel, each lane 8 contiguous channels moved by ONE 256-bit access (LDG.256 /
+// STG.256, sm_100): a tap of a C = 32 pixel is one 128-byte line read by its four lanes, so a warp-wide load touches
+// 32/LPV lines in one instruction -- the L1 data pipe (wavefronts = instructions x lines touched) is the unit this
+// kernel loads most.  A warp covers 32/LPV adjacent pixels.  All per-channel arithmetic runs as packed fp32 pairs
+// (FFMA2), and 8 channels per lane halve the shuffles per channel.
 // The depth axis is walked in chunks of DCH hypotheses whose running aggregates stay in registers while
 // the source views are visited one after the other (view-outer, depth-inner), so nothing C-wide except
 // the final cost volume is ever written.  The projection / tap geometry of a (pixel, hypothesis, view) does not
@@ -15,16 +17,25 @@
 //   VIS geometry  models/VisMVSNet/homography.py:77-121 (pixel centres +0.5, normalise by size, clamp +-1.1)
 //   grid_sample(bilinear, zeros, align_corners=True): per-tap zero padding.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace mvsb200 {
 
 constexpr int K1_DCH = 4;       // hypotheses per thread (x 8 channels x {M1, M2} = 64 accumulator registers)
 constexpr int K1_THREADS = 256;
+#ifdef MVSB200_K1_EXPERIMENTS
+#define K1_DBG(p) ((p).dbg)
+#else
+#define K1_DBG(p) 0
+#endif
 
 struct K1Params {
     const float *ref;
     const float *src[MVSB200_MAX_SRC];
     int src_h[MVSB200_MAX_SRC], src_w[MVSB200_MAX_SRC];
+    // divisor that normalises a projected coordinate and its correctly rounded reciprocal (host, IEEE):
+    // MVS (Ws-1)/2, (Hs-1)/2 (module.py:151-152); VIS Ws, Hs (homography.py:93-94)
+    float nx[MVSB200_MAX_SRC], rnx[MVSB200_MAX_SRC], ny[MVSB200_MAX_SRC], rny[MVSB200_MAX_SRC];
     const float *warp;
     const float *depth;
     const float *interval;
@@ -33,64 +44,69 @@ struct K1Params {
     float *out_amax;
     long long out_view_stride;
     int B, S, D, H, W, depth_mode;
+    int chunks;   // depth chunks (of K1_DCH hypotheses) a block walks
+#ifdef MVSB200_K1_EXPERIMENTS
+    int dbg;      // MVSB200_K1_DEBUG experiment mask (profiles/k1_variants.py); compiled out of the product
+#endif
 };
 
-struct Taps {
-    long long o00;   // element offset of the north-west tap (pixel index, not yet times C)
-    float w00, w01, w10, w11;
-    int dx, dy;      // offsets (in pixels) to the east / south taps
-};
-
-// Normalised grid coordinate -> four taps with per-tap zero padding folded into the weights.
-__device__ __forceinline__ Taps make_taps(float gx, float gy, int Hs, int Ws)
-{
-    float ix = ((gx + 1.f) / 2.f) * (float)(Ws - 1);
-    float iy = ((gy + 1.f) / 2.f) * (float)(Hs - 1);
-    float fx = floorf(ix), fy = floorf(iy);
-    int x0 = (int)fx, y0 = (int)fy;
-    float x1 = fx + 1.f, y1 = fy + 1.f;
-    Taps t;
-    t.w00 = (x1 - ix) * (y1 - iy);
-    t.w01 = (ix - fx) * (y1 - iy);
-    t.w10 = (x1 - ix) * (iy - fy);
-    t.w11 = (ix - fx) * (iy - fy);
-    bool xin0 = (x0 >= 0) & (x0 < Ws), xin1 = (x0 + 1 >= 0) & (x0 + 1 < Ws);
-    bool yin0 = (y0 >= 0) & (y0 < Hs), yin1 = (y0 + 1 >= 0) & (y0 + 1 < Hs);
-    if (!(xin0 & yin0)) t.w00 = 0.f;
-    if (!(xin1 & yin0)) t.w01 = 0.f;
-    if (!(xin0 & yin1)) t.w10 = 0.f;
-    if (!(xin1 & yin1)) t.w11 = 0.f;
-    // clamp the addresses into the map; out-of-range taps carry weight 0
-    const int xa = min(max(x0, 0), Ws - 1), xb = min(max(x0 + 1, 0), Ws - 1);
-    const int ya = min(max(y0, 0), Hs - 1), yb = min(max(y0 + 1, 0), Hs - 1);
-    t.dx = xb - xa;
-    t.dy = yb - ya;
-    t.o00 = (long long)ya * Ws + xa;
-    return t;
-}
-
-// x / d for a divisor whose correctly rounded reciprocal r is known: one residual correction of x*r gives the
-// correctly rounded quotient for normal operands (the fast path of the IEEE division sequence, without its range
-// check and slow-path call -- the epilogue divides 64 values per thread by V and V^2).
-__device__ __forceinline__ float div_by(float x, float d, float r)
-{
-    const float q = x * r;
-    return fmaf(fmaf(-q, d, x), r, q);
-}
-
-// Packed taps as they travel between lanes: cell = clamped north-west pixel index with the east/south steps in the
-// two top bits (maps are far below 2^29 pixels), plus the four zero-padding-folded weights.
+// The four taps of a sample as they travel between the lanes of a pixel group: `cell` = index of the north-west pixel
+// of the 2x2 block that is LOADED, and the weights of its four pixels.  The block is clamped into the map
+// (xa in [0, Ws-2], ya in [0, Hs-2]) so that its pixels sit at fixed offsets (+1 pixel, +1 row): where the sample's own
+// 2x2 cell straddles the border, the weights of its in-range taps move onto the loaded pixels they coincide with and
+// the out-of-range taps (zero padding) drop out.  A moved weight multiplies the same feature value and the vacated slot
+// contributes an exact 0, so the sum nw, ne, sw, se (ATen grid_sampler_2d order) is bit for bit the reference's.
 struct PackedTaps {
     int cell;
     float w00, w01, w10, w11;
 };
 
-__device__ __forceinline__ PackedTaps pack_taps(const Taps &t)
+// Normalised grid coordinate -> packed taps (grid_sample bilinear, zeros padding, align_corners=True).
+__device__ __forceinline__ PackedTaps make_taps(float gx, float gy, int Hs, int Ws)
 {
-    PackedTaps q;
-    q.cell = (int)t.o00 | (t.dx << 29) | (t.dy << 30);
-    q.w00 = t.w00; q.w01 = t.w01; q.w10 = t.w10; q.w11 = t.w11;
-    return q;
+    const float ix = ((gx + 1.f) / 2.f) * (float)(Ws - 1);
+    const float iy = ((gy + 1.f) / 2.f) * (float)(Hs - 1);
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy;
+    const float x1 = fx + 1.f, y1 = fy + 1.f;
+    float w00 = (x1 - ix) * (y1 - iy);
+    float w01 = (ix - fx) * (y1 - iy);
+    float w10 = (x1 - ix) * (iy - fy);
+    float w11 = (ix - fx) * (iy - fy);
+    const int xa = min(max(x0, 0), Ws - 2), ya = min(max(y0, 0), Hs - 2);
+    const int sx = x0 - xa, sy = y0 - ya;   // 0 inside; -1 / +1: one column (row) of the cell is still in the map
+    if (sx != 0) {
+        const float l0 = (sx == -1) ? w01 : 0.f, l1 = (sx == -1) ? w11 : 0.f;
+        const float r0 = (sx == 1) ? w00 : 0.f, r1 = (sx == 1) ? w10 : 0.f;
+        w00 = l0; w10 = l1; w01 = r0; w11 = r1;
+    }
+    if (sy != 0) {
+        const float u0 = (sy == -1) ? w10 : 0.f, u1 = (sy == -1) ? w11 : 0.f;
+        const float d0 = (sy == 1) ? w00 : 0.f, d1 = (sy == 1) ? w01 : 0.f;
+        w00 = u0; w01 = u1; w10 = d0; w11 = d1;
+    }
+    PackedTaps t;
+    t.cell = ya * Ws + xa;
+    t.w00 = w00; t.w01 = w01; t.w10 = w10; t.w11 = w11;
+    return t;
+}
+
+// x / d for a divisor whose reciprocal r is known to within an ulp: one residual correction of x*r gives the correctly
+// rounded quotient for normal operands when r is the correctly rounded reciprocal (the epilogue's V, V^2 and the
+// coordinate normalisers, all computed once), and the IEEE quotient up to rare last-bit ties when r comes from
+// rcp_nr (the fast path of the division sequence without its range check and slow-path call; a zero, denormal or
+// non-finite divisor yields NaN or a huge value, which the callers' clamps turn into an out-of-map sample exactly
+// as the reference's +-inf would).
+__device__ __forceinline__ float div_by(float x, float d, float r)
+{
+    const float q = x * r;
+    return fmaf(fmaf(-q, d, x), r, q);
+}
+__device__ __forceinline__ float rcp_nr(float d)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return fmaf(fmaf(-d, r, 1.f), r, r);
 }
 
 // Packed fp32 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per instruction, same rounding
@@ -98,13 +114,20 @@ __device__ __forceinline__ PackedTaps pack_taps(const Taps &t)
 struct F8 {   // 8 channels of one lane
     float2 v[4];
 };
-__device__ __forceinline__ F8 ld8(const float *p)
+__device__ __forceinline__ F8 ld8(const float *p)   // 32-byte aligned, read-only path
 {
-    const float4 a = ldg4(p), b = ldg4(p + 4);
     F8 r;
-    r.v[0] = make_float2(a.x, a.y); r.v[1] = make_float2(a.z, a.w);
-    r.v[2] = make_float2(b.x, b.y); r.v[3] = make_float2(b.z, b.w);
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.v[0].x), "=f"(r.v[0].y), "=f"(r.v[1].x), "=f"(r.v[1].y), "=f"(r.v[2].x), "=f"(r.v[2].y), "=f"(r.v[3].x), "=f"(r.v[3].y)
+        : "l"(p));
     return r;
+}
+// streaming 256-bit store: the written volume is consumed by a later kernel, not by this one
+__device__ __forceinline__ void st8_stream(float *p, const float2 (&o)[4])
+{
+    asm volatile("st.global.cs.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+                 :: "f"(o[0].x), "f"(o[0].y), "f"(o[1].x), "f"(o[1].y), "f"(o[2].x), "f"(o[2].y), "f"(o[3].x), "f"(o[3].y), "l"(p)
+                 : "memory");
 }
 
 template <int C, int GEOM, int AGG>
@@ -117,20 +140,30 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_cost_volume_kernel(const K1P
     __shared__ float s_warp[MVSB200_MAX_SRC * 16];
 
     const int b = blockIdx.z;
-    const int d0 = blockIdx.y * K1_DCH;
     const long long HW = (long long)p.H * p.W;
     for (int i = threadIdx.x; i < p.S * 16; i += K1_THREADS) s_warp[i] = p.warp[(long long)b * p.S * 16 + i];
     __syncthreads();
 
+    // A block owns a (32/LPV) x 8 pixel tile (one warp per row: the taps of vertically adjacent pixels share cache
+    // lines) and walks `chunks` depth chunks one after the other (the taps of consecutive chunks are the same or
+    // neighbouring pixels, so they are served by L1).
+    constexpr int TW = 32 / LPV, TH = K1_THREADS / 32;
     const int sub = threadIdx.x % LPV;
-    const long long pix_raw = (long long)blockIdx.x * VPB + threadIdx.x / LPV;
-    const bool active = pix_raw < HW;                 // inactive groups shadow the last pixel and store nothing,
-    const long long pix = active ? pix_raw : HW - 1;  // so every shuffle below runs with the full warp
-    const int y = (int)(pix / p.W), x = (int)(pix % p.W);
+    const int tiles_x = (p.W + TW - 1) / TW;
+    const int x_raw = (int)(blockIdx.x % tiles_x) * TW + (threadIdx.x % 32) / LPV;
+    const int y_raw = (int)(blockIdx.x / tiles_x) * TH + threadIdx.x / 32;
+    const bool active = x_raw < p.W && y_raw < p.H;        // inactive groups shadow a border pixel and store nothing,
+    const int x = min(x_raw, p.W - 1), y = min(y_raw, p.H - 1);   // so every shuffle below runs with the full warp
+    const long long pix = (long long)y * p.W + x;
 
-    const F8 r = ld8(p.ref + ((long long)b * HW + pix) * C + sub * 8);
+    const float *refp = p.ref + ((long long)b * HW + pix) * C + sub * 8;
     const float interval = (p.depth_mode >= MVSB200_DEPTH_START) ? __ldg(p.interval + b) : 0.f;
+    const float temp = (AGG == MVSB200_AGG_SOFTMIN) ? __ldg(p.temp) : 0.f;
+    float vmax = 0.f;   // max |stored value| of this thread (abs-max tracking for the z-march conv engine)
 
+    const int d_end = min(p.D, (int)(blockIdx.y + 1) * p.chunks * K1_DCH);
+    for (int d0 = blockIdx.y * p.chunks * K1_DCH; d0 < d_end; d0 += K1_DCH) {
+    const F8 r = ld8(refp);
     // The projection of a (pixel, hypothesis, view) is the same for every channel: lane `sub` of the pixel group
     // computes it for hypotheses sub, sub+LPV, ... of the chunk and the group shares the taps by shuffle.
     float dv[KPL];
@@ -156,13 +189,14 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_cost_volume_kernel(const K1P
         }
         sum_exp[k] = 0.f;
     }
-    const float temp = (AGG == MVSB200_AGG_SOFTMIN) ? __ldg(p.temp) : 0.f;
-    float vmax = 0.f;   // max |stored value| of this thread (abs-max tracking for the z-march conv engine)
-
     for (int s = 0; s < p.S; s++) {
         const float *wp = s_warp + s * 16;
         const int Hs = p.src_h[s], Ws = p.src_w[s];
-        const float *map = p.src[s] + (long long)b * Hs * Ws * C;   // warp-uniform base, 32-bit element offsets below
+        // this lane's 8 channels of pixel 0 of the map; pinned so that the tap loads below do not re-derive it
+        const float *mapl = p.src[s] + (long long)b * Hs * Ws * C + sub * 8;
+        asm volatile("" : "+l"(mapl));
+        const unsigned row_bytes = (unsigned)(Ws * C) * 4u;
+        const float nx = p.nx[s], rnx = p.rnx[s], ny = p.ny[s], rny = p.rny[s];
         float ax, ay, az, np_ = 0.f;
         if (GEOM == MVSB200_GEOM_MVS) {
             const float fx = (float)x, fy = (float)y;
@@ -182,31 +216,32 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_cost_volume_kernel(const K1P
         for (int j = 0; j < KPL; j++) {
             float gx, gy;
             if (GEOM == MVSB200_GEOM_MVS) {
-                float qx = ax * dv[j] + bx, qy = ay * dv[j] + by, qz = az * dv[j] + bz;
-                float px = qx / qz, py = qy / qz;
+                const float qx = ax * dv[j] + bx, qy = ay * dv[j] + by, qz = az * dv[j] + bz;
+                const float rz = rcp_nr(qz);
+                float px = div_by(qx, qz, rz), py = div_by(qy, qz, rz);
                 if (qz <= 0.f) px = -10.f, py = -10.f;
-                gx = clampf(px / ((float)(Ws - 1) / 2.f) - 1.f, -10.f, 10.f);
-                gy = clampf(py / ((float)(Hs - 1) / 2.f) - 1.f, -10.f, 10.f);
+                gx = clampf(div_by(px, nx, rnx) - 1.f, -10.f, 10.f);
+                gy = clampf(div_by(py, ny, rny) - 1.f, -10.f, 10.f);
             } else {
-                float f = np_ / (dv[j] + 1e-9f);
-                float qx = ax - bx * f, qy = ay - by * f, qz = az - bz * f;
-                float zc = fmaxf(qz, 1e-9f);
-                float u = qx / zc, v = qy / zc;
+                const float dd = dv[j] + 1e-9f;
+                const float f = div_by(np_, dd, rcp_nr(dd));
+                const float qx = ax - bx * f, qy = ay - by * f, qz = az - bz * f;
+                const float zc = fmaxf(qz, 1e-9f), rz = rcp_nr(zc);
+                float u = div_by(qx, zc, rz), v = div_by(qy, zc, rz);
                 if (!(qz > 0.f)) u = -10.f, v = -10.f;
-                gx = clampf((u / (float)Ws) * 2.f - 1.f, -1.1f, 1.1f);
-                gy = clampf((v / (float)Hs) * 2.f - 1.f, -1.1f, 1.1f);
+                gx = clampf(div_by(u, nx, rnx) * 2.f - 1.f, -1.1f, 1.1f);
+                gy = clampf(div_by(v, ny, rny) * 2.f - 1.f, -1.1f, 1.1f);
             }
             // NaN coordinates (degenerate cameras) sample nothing
             if (!(gx == gx) || !(gy == gy)) gx = gy = -10.f;
-            own[j] = pack_taps(make_taps(gx, gy, Hs, Ws));
+            own[j] = make_taps(gx, gy, Hs, Ws);
         }
 
         // Consecutive hypotheses of a pixel move along the epipolar line by a fraction of a pixel, so they mostly
         // fall into the same 2x2 tap cell: the four 32-byte taps stay in registers until the cell changes.
-        int cur_cell = -1;
+        int cur_cell = 0;
         F8 ta, tb, tc, td;
-#pragma unroll
-        for (int q = 0; q < 4; q++) ta.v[q] = tb.v[q] = tc.v[q] = td.v[q] = make_float2(0.f, 0.f);
+        if (K1_DBG(p) & 4) ta = tb = tc = td = r;
 #pragma unroll
         for (int k = 0; k < K1_DCH; k++) {
             const int owner = k % LPV, j = k / LPV;
@@ -215,14 +250,14 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_cost_volume_kernel(const K1P
             const float w01 = __shfl_sync(0xffffffffu, own[j].w01, owner, LPV);
             const float w10 = __shfl_sync(0xffffffffu, own[j].w10, owner, LPV);
             const float w11 = __shfl_sync(0xffffffffu, own[j].w11, owner, LPV);
-            if (cell != cur_cell) {
+            if (!(K1_DBG(p) & 4) && (k == 0 || (cell != cur_cell && !(K1_DBG(p) & 2)))) {
                 cur_cell = cell;
-                const unsigned o00 = (unsigned)(cell & 0x1fffffff) * C + sub * 8;
-                const unsigned ox = ((cell >> 29) & 1) * C, oy = ((cell >> 30) & 1) * (unsigned)(Ws * C);
-                ta = ld8(map + o00);
-                tb = ld8(map + (o00 + ox));
-                tc = ld8(map + (o00 + oy));
-                td = ld8(map + (o00 + oy + ox));
+                const char *q0 = reinterpret_cast<const char *>(mapl) + (unsigned long long)(unsigned)cell * (C * 4);
+                const char *q1 = q0 + row_bytes;
+                ta = ld8(reinterpret_cast<const float *>(q0));
+                tb = ld8(reinterpret_cast<const float *>(q0) + C);
+                tc = ld8(reinterpret_cast<const float *>(q1));
+                td = ld8(reinterpret_cast<const float *>(q1) + C);
             }
             const float2 p00 = make_float2(w00, w00), p01 = make_float2(w01, w01), p10 = make_float2(w10, w10), p11 = make_float2(w11, w11);
             float2 w[4];
@@ -301,9 +336,9 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_cost_volume_kernel(const K1P
             vmax = fmaxf(vmax, fmaxf(fabsf(o[q].x), fabsf(o[q].y)));
         }
         float *dst = p.out + (((long long)b * p.D + d0 + k) * HW + pix) * C + sub * 8;
-        st4_stream(dst, make_float4(o[0].x, o[0].y, o[1].x, o[1].y));
-        st4_stream(dst + 4, make_float4(o[2].x, o[2].y, o[3].x, o[3].y));
+        if (!(K1_DBG(p) & 1)) st8_stream(dst, o);
     }
+    }   // depth chunks
     if (p.out_amax) {
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, m));
@@ -356,20 +391,40 @@ extern "C" int mvsb200_build_cost_volume(const mvsb200_cost_volume_desc *d, cons
     K1Params p;
     p.ref = ref;
     for (int s = 0; s < d->S; s++) {
-        MVSB200_REQUIRE(src[s] && d->src_h[s] > 0 && d->src_w[s] > 0, "build_cost_volume: source %d invalid", s);
+        MVSB200_REQUIRE(src[s] && d->src_h[s] > 1 && d->src_w[s] > 1, "build_cost_volume: source %d invalid (maps are at least 2x2)", s);
         MVSB200_REQUIRE((long long)d->src_h[s] * d->src_w[s] < (1ll << 29) && (long long)d->src_h[s] * d->src_w[s] * d->C < (1ll << 31),
                         "build_cost_volume: source %d too large (%dx%d)", s, d->src_h[s], d->src_w[s]);
         p.src[s] = src[s];
         p.src_h[s] = d->src_h[s];
         p.src_w[s] = d->src_w[s];
+        p.nx[s] = d->geom == MVSB200_GEOM_MVS ? (float)(d->src_w[s] - 1) / 2.f : (float)d->src_w[s];
+        p.ny[s] = d->geom == MVSB200_GEOM_MVS ? (float)(d->src_h[s] - 1) / 2.f : (float)d->src_h[s];
+        p.rnx[s] = 1.f / p.nx[s];
+        p.rny[s] = 1.f / p.ny[s];
     }
     p.warp = warp; p.depth = depth; p.interval = interval; p.temp = temp; p.out = out; p.out_amax = out_amax;
     p.out_view_stride = d->out_view_stride;
     p.B = d->B; p.S = d->S; p.D = d->D; p.H = d->H; p.W = d->W; p.depth_mode = d->depth_mode;
-    const long long HW = (long long)d->H * d->W;
-    const int vpb = K1_THREADS / (d->C / 8);
-    dim3 grid((unsigned)((HW + vpb - 1) / vpb), (unsigned)((d->D + K1_DCH - 1) / K1_DCH), (unsigned)d->B);
-    MVSB200_REQUIRE(grid.y <= 65535, "build_cost_volume: D too large");
+    // pixel tiles of (32/LPV) x 8; a block walks as many depth chunks as still leaves >= 8 blocks per SM in the grid
+    const int tw = 32 / (d->C / 8), th = K1_THREADS / 32;
+    const long long tiles = (long long)((d->W + tw - 1) / tw) * ((d->H + th - 1) / th);
+    const int nchunk = (d->D + K1_DCH - 1) / K1_DCH;
+    int sms = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int chunks = 1;
+    while (chunks < 8 && chunks * 2 <= nchunk && tiles * d->B * ((nchunk + chunks * 2 - 1) / (chunks * 2)) >= 8ll * sms) chunks *= 2;
+    p.chunks = chunks;
+#ifdef MVSB200_K1_EXPERIMENTS
+    {
+        const char *e = getenv("MVSB200_K1_DEBUG");
+        p.dbg = e ? atoi(e) : 0;
+    }
+#endif
+    MVSB200_REQUIRE(tiles < (1ll << 31), "build_cost_volume: image too large");
+    dim3 grid((unsigned)tiles, (unsigned)((nchunk + chunks - 1) / chunks), (unsigned)d->B);
     cudaStream_t st = (cudaStream_t)stream;
     switch (d->C) {
     case 8: return launch_geom<8>(p, d->geom, d->agg, grid, st);
