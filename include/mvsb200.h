@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MVSB200_ABI_VERSION 3
+#define MVSB200_ABI_VERSION 4
 
 #define MVSB200_OK 0
 #define MVSB200_E_INVALID (-1)  /* bad argument / unsupported shape */
@@ -102,6 +102,17 @@ typedef struct {
 MVSB200_API int mvsb200_build_cost_volume(const mvsb200_cost_volume_desc *desc, const float *ref, const float *const *src,
                               const float *warp, const float *depth, const float *interval, const float *temp,
                               float *out, float *out_amax, mvsb200_stream_t stream);
+
+/* Backward of mvsb200_build_cost_volume with respect to the feature maps (the reference computes the sampling grid
+ * under torch.no_grad(): models/MVSNet/module.py:127, VisMVSNet/homography.py:25,110 -- cameras and hypotheses get no
+ * gradient; this replaces grid_sampler_2d_backward + the autograd graph of models/MVSNet/model.py:113-173,
+ * VisMVSNet/model_cas.py:176-186, CVP modules.py:229-293).  Inputs as in the forward call; grad_out has the forward
+ * output's layout.  grad_ref [B,H,W,C], grad_src[s] [B,src_h[s],src_w[s],C] (HOST array of S device pointers) and
+ * grad_temp (device scalar, SOFTMIN only) must be ZEROED by the caller: the kernel adds into them (vector atomics). */
+MVSB200_API int mvsb200_build_cost_volume_backward(const mvsb200_cost_volume_desc *desc, const float *ref, const float *const *src,
+                                                   const float *warp, const float *depth, const float *interval,
+                                                   const float *temp, const float *grad_out, float *grad_ref,
+                                                   float *const *grad_src, float *grad_temp, mvsb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K2: 3-D convolution / transposed convolution with fused BN (scale,bias) + ReLU + skip.
@@ -203,6 +214,13 @@ MVSB200_API int mvsb200_conv3d_c1(const mvsb200_conv3d_desc *desc, const float *
 MVSB200_API int mvsb200_depth_regress(const float *score, int B, int D, int H, int W, int depth_mode, const float *depth,
                           const float *interval, int conf_mode, float *depth_out, float *conf_out,
                           float *entropy_out, float *prob_out, mvsb200_stream_t stream);
+
+/* Backward of the regression output: grad_score[b,d,y,x] = grad_depth[b,y,x] p_d (h_d - depth), p = softmax(score)
+ * (autograd of models/MVSNet/model.py:207-209, module.py:174-178, VisMVSNet/nn_utils.py:453-466; confidence and entropy
+ * are produced under no_grad in the reference).  grad_depth [B,H,W]; grad_score [B,D,H,W], fully written. */
+MVSB200_API int mvsb200_depth_regress_backward(const float *score, int B, int D, int H, int W, int depth_mode, const float *depth,
+                                               const float *interval, const float *grad_depth, float *grad_score,
+                                               mvsb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K5: the per-pixel part of CVP-MVSNet's calDepthHypo (models/CVP_MVSNet/models/modules.py:131-226), fp64 inside:

@@ -71,6 +71,39 @@ def mvsnet_cost_volume(ref, srcs, ref_proj, src_projs, depth, aggregation="varia
     raise NotImplementedError(aggregation)
 
 
+def mvsnet_cost_volume_train(ref, srcs, ref_proj, src_projs, depth, aggregation="variance", temp=None):
+    """The TRAINING flavour of build_cost_volume (models/MVSNet/model.py:124-126,151-156: out-of-place updates), the
+    graph torch.autograd differentiates in the reference.  Autograd through this function is the oracle of the K1
+    backward kernel; the sampling grid inside homo_warp carries no gradient (module.py:127 builds it under no_grad)."""
+    B, C, H, W = ref.shape
+    D = depth.shape[1]
+    V = len(srcs) + 1
+    if aggregation == "variance":
+        m1 = ref.unsqueeze(2).repeat(1, 1, D, 1, 1)
+        m2 = m1 ** 2
+        for s, p in zip(srcs, src_projs):
+            w = homo_warp(s, p, ref_proj, depth, (H, W))
+            m1 = m1 + w
+            m2 = m2 + w ** 2
+        return m2 / V - m1 ** 2 / (V ** 2)
+    if aggregation == "softmin":
+        r = ref.unsqueeze(2)
+        sum_e = torch.zeros(B, 1, D, H, W, device=ref.device)
+        sum_v = torch.zeros(B, C, D, H, W, device=ref.device)
+        for s, p in zip(srcs, src_projs):
+            diff = (r - homo_warp(s, p, ref_proj, depth, (H, W))) ** 2
+            e = torch.exp(-temp * diff.sum(dim=1, keepdim=True))
+            sum_e = sum_e + e
+            sum_v = sum_v + e * diff
+        return sum_v / (sum_e + 1e-6)
+    raise NotImplementedError(aggregation)
+
+
+def mvsnet_regress_train(reg, depth):
+    """softmax + depth_regression as differentiated in training (models/MVSNet/model.py:207-209, module.py:174-178)."""
+    return torch.sum(F.softmax(reg, dim=1) * depth.view(*depth.shape, *([1] * (reg.dim() - depth.dim()))), 1)
+
+
 # ---------------------------------------------------------------------------------------------
 # a4: CostRegNet -- models/MVSNet/model.py:43-84
 # ---------------------------------------------------------------------------------------------

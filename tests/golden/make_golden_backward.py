@@ -1,0 +1,121 @@
+"""Golden gradients for the backward kernels (row f2 of SURVEY.md 8), produced by autograd through the UNMODIFIED reference.
+
+Run in the BUILD container only (needs /root/reference):   python tests/golden/make_golden_backward.py
+
+tests/golden/backward.npz holds, on the inputs already stored in mvsnet_*.npz / vis.npz:
+  * `MVSNet.build_cost_volume` in training mode (models/MVSNet/model.py:109-176, variance and soft-min): the gradient of
+    sum(volume * G) for a seeded G with respect to the three feature maps (and `temp`);
+  * Vis-MVSNet `SingleStage.build_cost_volume` + `groupwise_correlation` (model_cas.py:176-186, nn_utils.py:473-490):
+    the same for the 8-group correlation volumes of both source views;
+  * softmax + `depth_regression` (model.py:207-209): gradient of sum(depth * Gd) with respect to the score volume;
+  * one training-mode `forward` + L1 loss of MVSNet-s (the reference's training configuration): the depth map and the
+    gradients of a few parameters across the whole model (`mvsnet_train.npz`, with the weights).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle.ref_import import import_reference  # noqa: E402
+from wild_deep_mvs_b200 import synth  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+T = torch.from_numpy
+
+
+def main():
+    ref = import_reference()
+    torch.set_num_threads(8)
+    out = {}
+
+    # ---- MVSNet cost volumes ---------------------------------------------------------------------------------------
+    for agg in ("variance", "softmin"):
+        g = dict(np.load(os.path.join(OUT, "mvsnet_%s.npz" % agg)))
+        net = ref.MVSNet(agg).train()
+        net.num_depth = g["depth_values"].shape[1]
+        if agg == "softmin":
+            with torch.no_grad():
+                net.temp.copy_(T(g["temp"]))
+        feats = [T(g["feat%d" % i]).clone().requires_grad_(True) for i in range(3)]
+        proj = T(g["proj"])
+        vol = net.build_cost_volume(feats[0], feats[1:], proj[:, 0], [proj[:, 1], proj[:, 2]], T(g["depth_values"]))
+        G = torch.randn(vol.shape, generator=torch.Generator().manual_seed(11))
+        (vol * G).sum().backward()
+        out["%s_G" % agg] = G.numpy()
+        for i in range(3):
+            out["%s_gfeat%d" % (agg, i)] = feats[i].grad.numpy()
+        if agg == "softmin":
+            out["softmin_gtemp"] = net.temp.grad.numpy()
+        print(agg, "train-mode volume vs eval golden:", float((vol.detach() - T(g["cost_volume"])).abs().max()))
+
+    # ---- Vis-MVSNet group correlation ------------------------------------------------------------------------------
+    g = dict(np.load(os.path.join(OUT, "vis.npz")))
+    net = ref.VisFrontend().train()
+    st1 = net.model.stage1
+    feats = [T(g["feat_v%d_s1" % v]).clone().requires_grad_(True) for v in range(3)]
+    ref_cam, src_cams = T(g["ref_cam"]), [T(g["src_cam1"]), T(g["src_cam2"])]
+    D = 8
+    interval = (T(g["depth_max"]) - T(g["depth_min"])) / 128
+    ds = ref_cam[:, 1:2, 3:4, 0:1]
+    di = interval[:, 0].view(1, 1, 1, 1) * 4
+    refvol = feats[0].unsqueeze(2).repeat(1, 1, D, 1, 1)
+    loss = 0
+    for v in range(2):
+        warped = st1.build_cost_volume(feats[0], ref_cam, feats[1 + v], src_cams[v], D, ds, di, 8, 1)
+        gc = ref.vis_nn.groupwise_correlation(refvol, warped, 8, 1)
+        G = torch.randn(gc.shape, generator=torch.Generator().manual_seed(20 + v))
+        out["vis_G%d" % v] = G.numpy()
+        loss = loss + (gc * G).sum()
+        if v == 0:
+            print("vis groupcorr vs golden:", float((gc.detach() - T(g["s1_groupcorr_pair0"])).abs().max()))
+    loss.backward()
+    for v in range(3):
+        out["vis_gfeat%d" % v] = feats[v].grad.numpy()
+
+    # ---- softmax + depth regression --------------------------------------------------------------------------------
+    gen = torch.Generator().manual_seed(3)
+    score = (4 * torch.randn(2, 12, 9, 21, generator=gen)).requires_grad_(True)
+    dvals = 425 + 480 * torch.sort(torch.rand(2, 12, generator=gen), 1)[0]
+    depth = ref.mvs_module.depth_regression(F.softmax(score, dim=1), dvals)
+    Gd = torch.randn(depth.shape, generator=gen)
+    (depth * Gd).sum().backward()
+    out.update({"reg_score": score.detach().numpy(), "reg_dvals": dvals.numpy(), "reg_Gd": Gd.numpy(),
+                "reg_depth": depth.detach().numpy(), "reg_gscore": score.grad.numpy()})
+    np.savez_compressed(os.path.join(OUT, "backward.npz"), **out)
+
+    # ---- one training step of MVSNet-s -----------------------------------------------------------------------------
+    torch.manual_seed(0)
+    net = ref.MVSNet("softmin")
+    synth.randomize_norm_stats(net, seed=1)
+    synth.scale_param(net.cost_regularization.prob.weight, 40.0)
+    with torch.no_grad():
+        net.temp.fill_(0.37)
+    net.num_depth = 8
+    sd = {k: v.detach().clone().numpy() for k, v in net.state_dict().items()}
+    net.train()
+    s = synth.make_sample(2, 3, 64, 96, seed=4)
+    res = net(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"])
+    target = 500 + 300 * torch.rand(res["depth"].shape, generator=torch.Generator().manual_seed(9))
+    loss = (res["depth"] - target).abs().mean()
+    loss.backward()
+    tr = {"sd." + k: v for k, v in sd.items()}
+    tr.update({"depth": res["depth"].detach().numpy(), "conf": res["photometric_confidence"].numpy(), "target": target.numpy(),
+               "loss": np.float32(loss.item()), "seed": np.int32(4)})
+    params = dict(net.named_parameters())
+    for k in ("temp", "feature.conv0.conv.weight", "feature.conv6.bn.weight", "feature.feature.bias",
+              "cost_regularization.conv0.conv.weight", "cost_regularization.conv6.bn.bias",
+              "cost_regularization.conv9.0.weight", "cost_regularization.prob.weight", "cost_regularization.prob.bias"):
+        tr["grad." + k] = params[k].grad.numpy()
+        print(k, "grad abs-max", float(params[k].grad.abs().max()))
+    np.savez_compressed(os.path.join(OUT, "mvsnet_train.npz"), **tr)
+    for f in ("backward.npz", "mvsnet_train.npz"):
+        print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

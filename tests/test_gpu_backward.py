@@ -1,0 +1,239 @@
+"""GPU: the backward kernels (row f2 of SURVEY.md 8) through the C ABI -- K1 backward (mvsb200_build_cost_volume_backward)
+and K3 backward (mvsb200_depth_regress_backward) against gradients autograd produced through the UNMODIFIED reference
+(tests/golden/backward.npz, mvsnet_train.npz), against autograd through the torch port at a BASELINE size, and through a
+size-independent property: for the aggregations that are polynomial in the features (variance: quadratic, group
+correlation: bilinear) the central difference of the FORWARD kernel along a random direction equals <gradient, direction>.
+
+Tolerances: relative L-inf 1e-4 on gradients (fp32, atomics in arbitrary order; measured ~1e-6)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_linf
+
+pytestmark = pytest.mark.gpu
+
+from oracle import torch_port as tp  # noqa: E402
+from wild_deep_mvs_b200 import _lib as L  # noqa: E402
+from wild_deep_mvs_b200 import ops, synth  # noqa: E402
+from wild_deep_mvs_b200.mvsnet import MVSNet, build_proj_matrices  # noqa: E402
+
+DEV = "cuda:0"
+GRAD_TOL = 1e-4
+
+
+def cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device=DEV)
+
+
+def nhwc(a):   # numpy [B,C,H,W] -> cuda [B,H,W,C]
+    return cu(np.transpose(a, (0, 2, 3, 1)))
+
+
+def nchw(t):   # cuda [B,H,W,C] -> numpy [B,C,H,W]
+    return t.permute(0, 3, 1, 2).contiguous().cpu().numpy()
+
+
+@pytest.mark.parametrize("agg", ["variance", "softmin"])
+def test_k1_backward_against_reference_gradients(golden, agg):
+    g, b = golden("mvsnet_" + agg), golden("backward")
+    D = g["depth_values"].shape[1]
+    warp = ops.mvs_relative_proj(cu(g["proj"][:, 0]), cu(g["proj"][:, 1:]))
+    temp = cu(g["temp"]) if agg == "softmin" else None
+    feats = [nhwc(g["feat%d" % i]) for i in range(3)]
+    G = cu(np.transpose(b[agg + "_G"], (0, 2, 3, 4, 1)))           # reference layout [B,C,D,H,W] -> [B,D,H,W,C]
+    code = L.AGG_VARIANCE if agg == "variance" else L.AGG_SOFTMIN
+    g_ref, g_srcs, g_temp = ops.build_cost_volume_backward(G, feats[0], feats[1:], warp, cu(g["depth_values"]), D, L.GEOM_MVS,
+                                                           code, temp=temp)
+    assert rel_linf(nchw(g_ref), b[agg + "_gfeat0"]) < GRAD_TOL
+    for s in range(2):
+        assert rel_linf(nchw(g_srcs[s]), b["%s_gfeat%d" % (agg, s + 1)]) < GRAD_TOL
+    if agg == "softmin":
+        assert rel_linf(g_temp.cpu().numpy(), b["softmin_gtemp"]) < GRAD_TOL
+    else:
+        assert g_temp is None
+        # CVP's rounding order of the same function has the same derivative
+        g2 = ops.build_cost_volume_backward(G, feats[0], feats[1:], warp, cu(g["depth_values"]), D, L.GEOM_MVS, L.AGG_VARIANCE_MEAN)
+        assert rel_linf(nchw(g2[0]), b[agg + "_gfeat0"]) < GRAD_TOL
+
+
+def test_k1_backward_groupcorr_against_reference_gradients(golden):
+    g, b = golden("vis"), golden("backward")
+    warp = ops.vis_homography_params(cu(g["ref_cam"]), cu(np.stack([g["src_cam1"], g["src_cam2"]], 1)), 1.0 / 8)
+    feats = [nhwc(g["feat_v%d_s1" % v]) for v in range(3)]
+    interval = np.float32((g["depth_max"][0, 0] - g["depth_min"][0, 0]) / np.float32(128)) * np.float32(4)
+    G = cu(np.stack([np.transpose(b["vis_G%d" % v], (0, 2, 3, 4, 1)) for v in range(2)]))      # [S,B,D,H,W,8]
+    g_ref, g_srcs, _ = ops.build_cost_volume_backward(G, feats[0], feats[1:], warp, cu(g["depth_min"][:, 0]), 8, L.GEOM_VIS,
+                                                      L.AGG_GROUPCORR, interval=cu(np.array([interval])), groups=8)
+    assert rel_linf(nchw(g_ref), b["vis_gfeat0"]) < GRAD_TOL
+    for s in range(2):
+        assert rel_linf(nchw(g_srcs[s]), b["vis_gfeat%d" % (s + 1)]) < GRAD_TOL
+
+
+CASES = [
+    # C, agg, geom, per-pixel hypotheses, S
+    (16, L.AGG_VARIANCE_MEAN, L.GEOM_MVS, True, 3),      # CVP proj_cost flavour: ragged sources, depth volume
+    (32, L.AGG_VARIANCE, L.GEOM_MVS, False, 4),
+    (8, L.AGG_VARIANCE, L.GEOM_MVS, False, 1),
+    (32, L.AGG_GROUPCORR, L.GEOM_VIS, True, 2),          # Vis stages 2/3: per-pixel depth start
+    (16, L.AGG_GROUPCORR, L.GEOM_MVS, False, 2),
+]
+
+
+@pytest.mark.parametrize("C,agg,geom,per_pixel,S", CASES)
+def test_k1_backward_is_the_derivative_of_the_forward_kernel(golden, C, agg, geom, per_pixel, S):
+    gen = torch.Generator(device="cpu").manual_seed(C + 10 * agg + S)
+    B, H, W, D = 2, 19, 27, 6                                     # nothing a multiple of the tile, D not of the chunk
+    rnd = lambda *s: torch.randn(*s, generator=gen).to(DEV)
+    ref = rnd(B, H, W, C)
+    srcs = [rnd(B, H - 2 * s, W + 3 * s, C) for s in range(S)]
+    if geom == L.GEOM_MVS:
+        K, R, t, _, _ = synth.make_cameras(B, S + 1, 4 * H, 4 * W)
+        K = K.clone()
+        K[:, :, :2] /= 4
+        proj = build_proj_matrices(K, R, t).to(DEV)
+        warp = ops.mvs_relative_proj(proj[:, 0].contiguous(), proj[:, 1:].contiguous())
+    else:
+        v = golden("vis")
+        cams = np.stack([v["src_cam1"], v["src_cam2"]], 1)[:, :S]
+        warp = ops.vis_homography_params(cu(np.repeat(v["ref_cam"], B, 0)), cu(np.repeat(cams, B, 0)), 1.0 / 8)
+    if geom == L.GEOM_VIS or agg == L.AGG_GROUPCORR:
+        depth = (450 + 200 * torch.rand(B, H, W, generator=gen)).to(DEV) if per_pixel else torch.tensor([450.0, 500.0], device=DEV)
+        interval = torch.tensor([30.0, 22.0], device=DEV)
+    else:
+        depth = (425 + 480 * torch.rand(*((B, D, H, W) if per_pixel else (B, D)), generator=gen)).to(DEV)
+        interval = None
+    fwd = lambda r, ss: ops.build_cost_volume(r, ss, warp, depth, D, geom, agg, interval=interval, groups=C // 4)
+    out = fwd(ref, srcs)
+    G = rnd(*out.shape)
+    g_ref, g_srcs, _ = ops.build_cost_volume_backward(G, ref, srcs, warp, depth, D, geom, agg, interval=interval, groups=C // 4)
+    assert all(torch.isfinite(x).all() for x in [g_ref] + g_srcs)
+    # <grad, direction> against the central difference of sum(G * forward): exact for polynomials of degree <= 2
+    d_ref, d_srcs = rnd(*ref.shape), [rnd(*s.shape) for s in srcs]
+    eps = 0.5
+    lp = (G.double() * fwd(ref + eps * d_ref, [s + eps * d for s, d in zip(srcs, d_srcs)]).double()).sum()
+    lm = (G.double() * fwd(ref - eps * d_ref, [s - eps * d for s, d in zip(srcs, d_srcs)]).double()).sum()
+    want = float((lp - lm) / (2 * eps))
+    got = float((g_ref.double() * d_ref.double()).sum() + sum((g.double() * d.double()).sum() for g, d in zip(g_srcs, d_srcs)))
+    scale = float((G.abs().double() * out.abs().double()).sum())
+    assert abs(got - want) < 2e-5 * scale, (got, want, scale)
+    # and per input: the gradient of a source nobody samples from the given direction is untouched by the others
+    lp = (G.double() * fwd(ref + eps * d_ref, srcs).double()).sum()
+    lm = (G.double() * fwd(ref - eps * d_ref, srcs).double()).sum()
+    assert abs(float((g_ref.double() * d_ref.double()).sum()) - float((lp - lm) / (2 * eps))) < 2e-5 * scale
+
+
+def test_k1_backward_softmin_at_cfg1_size_against_the_torch_port():
+    """BASELINE cfg1 (MVSNet-s: 1+2 views, 32ch 128x160, D=48): autograd through the port's training-flavour graph
+    (3 x 126 MB of warped volumes and their squares kept alive) vs one backward kernel."""
+    gen = torch.Generator().manual_seed(0)
+    B, C, H, W, D, S = 1, 32, 128, 160, 48, 2
+    feats = [(0.5 * torch.randn(B, C, H, W, generator=gen)).to(DEV).requires_grad_(True) for _ in range(S + 1)]
+    K, R, t, dmin, dmax = synth.make_cameras(B, S + 1, 4 * H, 4 * W)
+    K = K.clone()
+    K[:, :, :2] /= 4
+    proj = build_proj_matrices(K, R, t).to(DEV)
+    dv = (dmin[:, :1] + (dmax[:, :1] - dmin[:, :1]) / (D - 1) * torch.arange(D).view(1, -1)).to(DEV)
+    temp = torch.tensor([0.37], device=DEV, requires_grad=True)
+    vol = tp.mvsnet_cost_volume_train(feats[0], feats[1:], proj[:, 0], [proj[:, 1], proj[:, 2]], dv, "softmin", temp)
+    G = torch.randn(vol.shape, generator=gen).to(DEV)
+    (vol * G).sum().backward()
+    warp = ops.mvs_relative_proj(proj[:, 0].contiguous(), proj[:, 1:].contiguous())
+    f = [ops.to_nhwc(x.detach()) for x in feats]
+    g_ref, g_srcs, g_temp = ops.build_cost_volume_backward(G.permute(0, 2, 3, 4, 1).contiguous(), f[0], f[1:], warp, dv, D,
+                                                           L.GEOM_MVS, L.AGG_SOFTMIN, temp=temp.detach())
+    assert rel_linf(nchw(g_ref), feats[0].grad.cpu().numpy()) < GRAD_TOL
+    for s in range(S):
+        assert rel_linf(nchw(g_srcs[s]), feats[s + 1].grad.cpu().numpy()) < GRAD_TOL
+    assert rel_linf(g_temp.cpu().numpy(), temp.grad.cpu().numpy()) < 1e-3      # one scalar summed over 31 M terms
+
+
+def test_cost_volume_autograd_function():
+    """ops.cost_volume: torch.autograd sees K1 forward + backward as one op; inputs that need no gradient get None."""
+    gen = torch.Generator().manual_seed(2)
+    B, C, H, W, D = 1, 32, 16, 24, 8
+    ref = torch.randn(B, H, W, C, generator=gen).to(DEV).requires_grad_(True)
+    srcs = [torch.randn(B, H, W, C, generator=gen).to(DEV).requires_grad_(i == 0) for i in range(2)]
+    K, R, t, dmin, dmax = synth.make_cameras(B, 3, 4 * H, 4 * W)
+    K = K.clone()
+    K[:, :, :2] /= 4
+    proj = build_proj_matrices(K, R, t).to(DEV)
+    warp = ops.mvs_relative_proj(proj[:, 0].contiguous(), proj[:, 1:].contiguous())
+    dv = torch.linspace(425, 905, D, device=DEV).view(1, D)
+    temp = torch.tensor([0.2], device=DEV, requires_grad=True)
+    vol = ops.cost_volume(ref, srcs, warp, dv, D, L.GEOM_MVS, L.AGG_SOFTMIN, temp=temp)
+    assert vol.requires_grad and vol.shape == (B, D, H, W, C)
+    assert torch.equal(vol.detach(), ops.build_cost_volume(ref.detach(), [s.detach() for s in srcs], warp, dv, D, L.GEOM_MVS,
+                                                           L.AGG_SOFTMIN, temp=temp.detach()))
+    vol.square().sum().backward()
+    assert ref.grad is not None and srcs[0].grad is not None and srcs[1].grad is None and temp.grad.shape == (1,)
+    assert ref.grad.abs().max() > 0 and srcs[0].grad.abs().max() > 0
+
+
+def test_k3_backward_against_reference_gradient_and_autograd(golden):
+    b = golden("backward")
+    score = cu(b["reg_score"])
+    g = ops.depth_regress_backward(cu(b["reg_Gd"]), score, cu(b["reg_dvals"]))
+    assert rel_linf(g.cpu().numpy(), b["reg_gscore"]) < GRAD_TOL
+    # the autograd op, the three other hypothesis layouts, D not a multiple of the 8 depth lanes
+    gen = torch.Generator().manual_seed(1)
+    B, D, H, W = 2, 13, 7, 45
+    sc = (3 * torch.randn(B, D, H, W, generator=gen)).to(DEV)
+    vol = (425 + 480 * torch.rand(B, D, H, W, generator=gen)).to(DEV)
+    start, start_map = torch.tensor([430.0, 500.0], device=DEV), (450 + 50 * torch.rand(B, H, W, generator=gen)).to(DEV)
+    interval = torch.tensor([2.5, 4.0], device=DEV)
+    steps = torch.arange(D, device=DEV, dtype=torch.float32).view(1, D, 1, 1)
+    Gd = torch.randn(B, H, W, generator=gen).to(DEV)
+    for depth, iv, hyp in ((vol, None, vol), (start, interval, start.view(B, 1, 1, 1) + interval.view(B, 1, 1, 1) * steps),
+                           (start_map, interval, start_map.unsqueeze(1) + interval.view(B, 1, 1, 1) * steps)):
+        s1 = sc.clone().requires_grad_(True)
+        d1, conf = ops.regress_depth(s1, depth, iv, L.CONF_SUM4)
+        assert not conf.requires_grad and conf.shape == (B, H, W)
+        (d1 * Gd).sum().backward()
+        s2 = sc.clone().requires_grad_(True)
+        d2 = (torch.softmax(s2, 1) * hyp).sum(1)
+        (d2 * Gd).sum().backward()
+        assert rel_linf(d1.detach().cpu().numpy(), d2.detach().cpu().numpy()) < 1e-6
+        assert rel_linf(s1.grad.cpu().numpy(), s2.grad.cpu().numpy()) < GRAD_TOL
+
+
+def test_mvsnet_training_step_matches_the_reference(golden, monkeypatch):
+    """One training-mode forward + L1 loss + backward of MVSNet-s (the reference's training configuration,
+    models/trainer.py:96-206) with the reference's weights: depth map and parameter gradients across the whole model
+    (FeatureNet <- K1 backward <- regulariser <- K3 backward)."""
+    g = golden("mvsnet_train")
+    # the golden was computed in fp32 on the CPU: keep cuDNN (FeatureNet / regulariser modules) off TF32 for the comparison
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    net = MVSNet("softmin")
+    net.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}, strict=True)
+    net.num_depth = 8
+    net = net.to(DEV).train()
+    s = {k: v.to(DEV) for k, v in synth.make_sample(2, 3, 64, 96, seed=int(g["seed"])).items()}
+    out = net(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"])
+    assert out["depth"].requires_grad and not out["photometric_confidence"].requires_grad
+    err = np.abs(out["depth"].detach().cpu().numpy() - g["depth"]) / np.abs(g["depth"]).max()
+    assert err.max() < 1e-3       # north-star tolerance; measured 3e-5
+    loss = (out["depth"] - cu(g["target"])).abs().mean()
+    assert abs(loss.item() - float(g["loss"])) < 1e-3 * float(g["loss"])
+    loss.backward()
+    params = dict(net.named_parameters())
+    for k in [k[5:] for k in g if k.startswith("grad.")]:
+        want = g["grad." + k]
+        if np.abs(want).max() < 1e-5:          # prob.bias: softmax is shift invariant, the gradient is rounding noise
+            assert params[k].grad.abs().max().item() < 1e-4
+            continue
+        # measured 3e-5 ... 7e-5 (temp, one scalar summed over every voxel: 3e-3)
+        assert rel_linf(params[k].grad.cpu().numpy(), want) < (1e-2 if k == "temp" else 1e-3), k
+    # eval mode still runs the inference kernels, without a graph
+    out = net.eval()(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"])
+    assert not out["depth"].requires_grad
+
+
+def test_backward_errors_are_loud():
+    ref = torch.zeros(1, 8, 8, 32, device=DEV)
+    warp = torch.zeros(1, 1, 16, device=DEV)
+    dv = torch.ones(1, 4, device=DEV)
+    with pytest.raises(L.Mvsb200Error):
+        ops.build_cost_volume_backward(torch.zeros(1, 4, 8, 8, 16, device=DEV), ref, [ref], warp, dv, 4, L.GEOM_MVS, L.AGG_VARIANCE)
+    with pytest.raises(L.Mvsb200Error):
+        ops.depth_regress_backward(torch.zeros(1, 3, 3, device=DEV), torch.zeros(1, 4, 8, 8, device=DEV), dv)

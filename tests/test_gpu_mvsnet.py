@@ -69,8 +69,8 @@ def test_forward_api_and_state_dict_names():
     imgs = [s["imgs"][:, 0], s["imgs"][:, 1, :, :56, :80].contiguous(), s["imgs"][:, 2]]
     out2 = net(imgs, s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"])
     assert out2["depth"].shape == (2, 16, 24) and torch.isfinite(out2["depth"]).all()
-    with pytest.raises(NotImplementedError):
-        net.train()(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"])
+    out3 = net.train()(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"])   # training: tests/test_gpu_backward.py
+    assert out3["depth"].requires_grad and out3["depth"].shape == (2, 16, 24)
     with pytest.raises(NotImplementedError):
         MVSNet("nope").to(DEV).eval()(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"])
 

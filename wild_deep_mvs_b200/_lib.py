@@ -15,7 +15,7 @@ DEPTH_VALUES, DEPTH_VOLUME, DEPTH_START, DEPTH_START_MAP = 0, 1, 2, 3
 SKIP_NONE, SKIP_BEFORE_RELU, SKIP_AFTER_RELU = 0, 1, 2
 CONF_NONE, CONF_SUM4, CONF_WINDOW = 0, 1, 2
 PRECISION_3XTF32, PRECISION_TF32 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class Mvsb200Error(RuntimeError):
@@ -50,6 +50,9 @@ SIGNATURES = {
     "mvsb200_mvs_relative_proj": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "mvsb200_vis_homography_params": (_i, [_vp, _vp, ctypes.c_float, _vp, _i, _i, _vp]),
     "mvsb200_build_cost_volume": (_i, [ctypes.POINTER(CostVolumeDesc), _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvsb200_build_cost_volume_backward": (_i, [ctypes.POINTER(CostVolumeDesc), _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp,
+                                                ctypes.POINTER(_vp), _vp, _vp]),
+    "mvsb200_depth_regress_backward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "mvsb200_conv3d_out_shape": (_i, [ctypes.POINTER(Conv3dDesc)] + [ctypes.POINTER(_i)] * 3),
     "mvsb200_conv3d": (_i, [ctypes.POINTER(Conv3dDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvsb200_conv3d_tc_supported": (_i, [ctypes.POINTER(Conv3dDesc)]),

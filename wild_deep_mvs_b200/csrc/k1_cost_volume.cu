@@ -16,119 +16,10 @@
 //   MVS geometry  models/MVSNet/module.py:138-155   (integer pixel grid, z<=0 -> (-10,-10), clamp +-10)
 //   VIS geometry  models/VisMVSNet/homography.py:77-121 (pixel centres +0.5, normalise by size, clamp +-1.1)
 //   grid_sample(bilinear, zeros, align_corners=True): per-tap zero padding.
-#include "common.cuh"
+#include "k1_common.cuh"
 #include <cstdlib>
 
 namespace mvsb200 {
-
-constexpr int K1_DCH = 4;       // hypotheses per thread (x 8 channels x {M1, M2} = 64 accumulator registers)
-constexpr int K1_THREADS = 256;
-#ifdef MVSB200_K1_EXPERIMENTS
-#define K1_DBG(p) ((p).dbg)
-#else
-#define K1_DBG(p) 0
-#endif
-
-struct K1Params {
-    const float *ref;
-    const float *src[MVSB200_MAX_SRC];
-    int src_h[MVSB200_MAX_SRC], src_w[MVSB200_MAX_SRC];
-    // divisor that normalises a projected coordinate and its correctly rounded reciprocal (host, IEEE):
-    // MVS (Ws-1)/2, (Hs-1)/2 (module.py:151-152); VIS Ws, Hs (homography.py:93-94)
-    float nx[MVSB200_MAX_SRC], rnx[MVSB200_MAX_SRC], ny[MVSB200_MAX_SRC], rny[MVSB200_MAX_SRC];
-    const float *warp;
-    const float *depth;
-    const float *interval;
-    const float *temp;
-    float *out;
-    float *out_amax;
-    long long out_view_stride;
-    int B, S, D, H, W, depth_mode;
-    int chunks;   // depth chunks (of K1_DCH hypotheses) a block walks
-#ifdef MVSB200_K1_EXPERIMENTS
-    int dbg;      // MVSB200_K1_DEBUG experiment mask (profiles/k1_variants.py); compiled out of the product
-#endif
-};
-
-// The four taps of a sample as they travel between the lanes of a pixel group: `cell` = index of the north-west pixel
-// of the 2x2 block that is LOADED, and the weights of its four pixels.  The block is clamped into the map
-// (xa in [0, Ws-2], ya in [0, Hs-2]) so that its pixels sit at fixed offsets (+1 pixel, +1 row): where the sample's own
-// 2x2 cell straddles the border, the weights of its in-range taps move onto the loaded pixels they coincide with and
-// the out-of-range taps (zero padding) drop out.  A moved weight multiplies the same feature value and the vacated slot
-// contributes an exact 0, so the sum nw, ne, sw, se (ATen grid_sampler_2d order) is bit for bit the reference's.
-struct PackedTaps {
-    int cell;
-    float w00, w01, w10, w11;
-};
-
-// Normalised grid coordinate -> packed taps (grid_sample bilinear, zeros padding, align_corners=True).
-__device__ __forceinline__ PackedTaps make_taps(float gx, float gy, int Hs, int Ws)
-{
-    const float ix = ((gx + 1.f) / 2.f) * (float)(Ws - 1);
-    const float iy = ((gy + 1.f) / 2.f) * (float)(Hs - 1);
-    const float fx = floorf(ix), fy = floorf(iy);
-    const int x0 = (int)fx, y0 = (int)fy;
-    const float x1 = fx + 1.f, y1 = fy + 1.f;
-    float w00 = (x1 - ix) * (y1 - iy);
-    float w01 = (ix - fx) * (y1 - iy);
-    float w10 = (x1 - ix) * (iy - fy);
-    float w11 = (ix - fx) * (iy - fy);
-    const int xa = min(max(x0, 0), Ws - 2), ya = min(max(y0, 0), Hs - 2);
-    const int sx = x0 - xa, sy = y0 - ya;   // 0 inside; -1 / +1: one column (row) of the cell is still in the map
-    if (sx != 0) {
-        const float l0 = (sx == -1) ? w01 : 0.f, l1 = (sx == -1) ? w11 : 0.f;
-        const float r0 = (sx == 1) ? w00 : 0.f, r1 = (sx == 1) ? w10 : 0.f;
-        w00 = l0; w10 = l1; w01 = r0; w11 = r1;
-    }
-    if (sy != 0) {
-        const float u0 = (sy == -1) ? w10 : 0.f, u1 = (sy == -1) ? w11 : 0.f;
-        const float d0 = (sy == 1) ? w00 : 0.f, d1 = (sy == 1) ? w01 : 0.f;
-        w00 = u0; w01 = u1; w10 = d0; w11 = d1;
-    }
-    PackedTaps t;
-    t.cell = ya * Ws + xa;
-    t.w00 = w00; t.w01 = w01; t.w10 = w10; t.w11 = w11;
-    return t;
-}
-
-// x / d for a divisor whose reciprocal r is known to within an ulp: one residual correction of x*r gives the correctly
-// rounded quotient for normal operands when r is the correctly rounded reciprocal (the epilogue's V, V^2 and the
-// coordinate normalisers, all computed once), and the IEEE quotient up to rare last-bit ties when r comes from
-// rcp_nr (the fast path of the division sequence without its range check and slow-path call; a zero, denormal or
-// non-finite divisor yields NaN or a huge value, which the callers' clamps turn into an out-of-map sample exactly
-// as the reference's +-inf would).
-__device__ __forceinline__ float div_by(float x, float d, float r)
-{
-    const float q = x * r;
-    return fmaf(fmaf(-q, d, x), r, q);
-}
-__device__ __forceinline__ float rcp_nr(float d)
-{
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
-    return fmaf(fmaf(-d, r, 1.f), r, r);
-}
-
-// Packed fp32 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per instruction, same rounding
-// as the scalar forms) over the channel pairs a lane owns.
-struct F8 {   // 8 channels of one lane
-    float2 v[4];
-};
-__device__ __forceinline__ F8 ld8(const float *p)   // 32-byte aligned, read-only path
-{
-    F8 r;
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=f"(r.v[0].x), "=f"(r.v[0].y), "=f"(r.v[1].x), "=f"(r.v[1].y), "=f"(r.v[2].x), "=f"(r.v[2].y), "=f"(r.v[3].x), "=f"(r.v[3].y)
-        : "l"(p));
-    return r;
-}
-// streaming 256-bit store: the written volume is consumed by a later kernel, not by this one
-__device__ __forceinline__ void st8_stream(float *p, const float2 (&o)[4])
-{
-    asm volatile("st.global.cs.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
-                 :: "f"(o[0].x), "f"(o[0].y), "f"(o[1].x), "f"(o[1].y), "f"(o[2].x), "f"(o[2].y), "f"(o[3].x), "f"(o[3].y), "l"(p)
-                 : "memory");
-}
 
 template <int C, int GEOM, int AGG>
 __global__ void __launch_bounds__(K1_THREADS, 2) k1_cost_volume_kernel(const K1Params p)
@@ -196,46 +87,8 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_cost_volume_kernel(const K1P
         const float *mapl = p.src[s] + (long long)b * Hs * Ws * C + sub * 8;
         asm volatile("" : "+l"(mapl));
         const unsigned row_bytes = (unsigned)(Ws * C) * 4u;
-        const float nx = p.nx[s], rnx = p.rnx[s], ny = p.ny[s], rny = p.rny[s];
-        float ax, ay, az, np_ = 0.f;
-        if (GEOM == MVSB200_GEOM_MVS) {
-            const float fx = (float)x, fy = (float)y;
-            ax = wp[0] * fx + wp[1] * fy + wp[2];
-            ay = wp[3] * fx + wp[4] * fy + wp[5];
-            az = wp[6] * fx + wp[7] * fy + wp[8];
-        } else {
-            const float fx = (float)x + 0.5f, fy = (float)y + 0.5f;
-            ax = wp[0] * fx + wp[1] * fy + wp[2];
-            ay = wp[3] * fx + wp[4] * fy + wp[5];
-            az = wp[6] * fx + wp[7] * fy + wp[8];
-            np_ = wp[12] * fx + wp[13] * fy + wp[14];
-        }
-        const float bx = wp[9], by = wp[10], bz = wp[11];
         PackedTaps own[KPL];
-#pragma unroll
-        for (int j = 0; j < KPL; j++) {
-            float gx, gy;
-            if (GEOM == MVSB200_GEOM_MVS) {
-                const float qx = ax * dv[j] + bx, qy = ay * dv[j] + by, qz = az * dv[j] + bz;
-                const float rz = rcp_nr(qz);
-                float px = div_by(qx, qz, rz), py = div_by(qy, qz, rz);
-                if (qz <= 0.f) px = -10.f, py = -10.f;
-                gx = clampf(div_by(px, nx, rnx) - 1.f, -10.f, 10.f);
-                gy = clampf(div_by(py, ny, rny) - 1.f, -10.f, 10.f);
-            } else {
-                const float dd = dv[j] + 1e-9f;
-                const float f = div_by(np_, dd, rcp_nr(dd));
-                const float qx = ax - bx * f, qy = ay - by * f, qz = az - bz * f;
-                const float zc = fmaxf(qz, 1e-9f), rz = rcp_nr(zc);
-                float u = div_by(qx, zc, rz), v = div_by(qy, zc, rz);
-                if (!(qz > 0.f)) u = -10.f, v = -10.f;
-                gx = clampf(div_by(u, nx, rnx) * 2.f - 1.f, -1.1f, 1.1f);
-                gy = clampf(div_by(v, ny, rny) * 2.f - 1.f, -1.1f, 1.1f);
-            }
-            // NaN coordinates (degenerate cameras) sample nothing
-            if (!(gx == gx) || !(gy == gy)) gx = gy = -10.f;
-            own[j] = make_taps(gx, gy, Hs, Ws);
-        }
+        view_taps<GEOM, KPL>(p, s, wp, x, y, dv, own);
 
         // Consecutive hypotheses of a pixel move along the epipolar line by a fraction of a pixel, so they mostly
         // fall into the same 2x2 tap cell: the four 32-byte taps stay in registers until the cell changes.
@@ -387,44 +240,20 @@ extern "C" int mvsb200_build_cost_volume(const mvsb200_cost_volume_desc *d, cons
     MVSB200_REQUIRE(d->agg != MVSB200_AGG_SOFTMIN || temp, "build_cost_volume: softmin needs temp");
     MVSB200_REQUIRE(d->agg != MVSB200_AGG_GROUPCORR || d->groups * 4 == d->C,
                     "build_cost_volume: group correlation needs C == 4*groups (C=%d groups=%d)", d->C, d->groups);
-    MVSB200_REQUIRE(d->B <= 65535, "build_cost_volume: B too large");
     K1Params p;
     p.ref = ref;
-    for (int s = 0; s < d->S; s++) {
-        MVSB200_REQUIRE(src[s] && d->src_h[s] > 1 && d->src_w[s] > 1, "build_cost_volume: source %d invalid (maps are at least 2x2)", s);
-        MVSB200_REQUIRE((long long)d->src_h[s] * d->src_w[s] < (1ll << 29) && (long long)d->src_h[s] * d->src_w[s] * d->C < (1ll << 31),
-                        "build_cost_volume: source %d too large (%dx%d)", s, d->src_h[s], d->src_w[s]);
-        p.src[s] = src[s];
-        p.src_h[s] = d->src_h[s];
-        p.src_w[s] = d->src_w[s];
-        p.nx[s] = d->geom == MVSB200_GEOM_MVS ? (float)(d->src_w[s] - 1) / 2.f : (float)d->src_w[s];
-        p.ny[s] = d->geom == MVSB200_GEOM_MVS ? (float)(d->src_h[s] - 1) / 2.f : (float)d->src_h[s];
-        p.rnx[s] = 1.f / p.nx[s];
-        p.rny[s] = 1.f / p.ny[s];
-    }
+    if (int rc = k1_fill_sources(p, d, src, "build_cost_volume")) return rc;
     p.warp = warp; p.depth = depth; p.interval = interval; p.temp = temp; p.out = out; p.out_amax = out_amax;
     p.out_view_stride = d->out_view_stride;
     p.B = d->B; p.S = d->S; p.D = d->D; p.H = d->H; p.W = d->W; p.depth_mode = d->depth_mode;
-    // pixel tiles of (32/LPV) x 8; a block walks as many depth chunks as still leaves >= 8 blocks per SM in the grid
-    const int tw = 32 / (d->C / 8), th = K1_THREADS / 32;
-    const long long tiles = (long long)((d->W + tw - 1) / tw) * ((d->H + th - 1) / th);
-    const int nchunk = (d->D + K1_DCH - 1) / K1_DCH;
-    int sms = 148;
-    {
-        int dev = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    int chunks = 1;
-    while (chunks < 8 && chunks * 2 <= nchunk && tiles * d->B * ((nchunk + chunks * 2 - 1) / (chunks * 2)) >= 8ll * sms) chunks *= 2;
-    p.chunks = chunks;
+    dim3 grid;
+    if (int rc = k1_grid(p, d, grid, "build_cost_volume")) return rc;
 #ifdef MVSB200_K1_EXPERIMENTS
     {
         const char *e = getenv("MVSB200_K1_DEBUG");
         p.dbg = e ? atoi(e) : 0;
     }
 #endif
-    MVSB200_REQUIRE(tiles < (1ll << 31), "build_cost_volume: image too large");
-    dim3 grid((unsigned)tiles, (unsigned)((nchunk + chunks - 1) / chunks), (unsigned)d->B);
     cudaStream_t st = (cudaStream_t)stream;
     switch (d->C) {
     case 8: return launch_geom<8>(p, d->geom, d->agg, grid, st);

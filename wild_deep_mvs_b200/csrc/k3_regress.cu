@@ -82,6 +82,53 @@ __global__ void __launch_bounds__(K3_THREADS) k3_depth_regress_kernel(const K3Pa
     }
 }
 
+// K3 backward (row f2): depth = sum_d p_d h_d with p = softmax(score)  =>  dL/dscore_d = g p_d (h_d - depth).
+// The confidence / entropy outputs carry no gradient in the reference (torch.no_grad, models/MVSNet/model.py:211).
+// Same block shape as the forward kernel; the statistics are recomputed instead of stored.
+struct K3BwdParams {
+    const float *score, *depth, *interval, *gdepth;
+    float *gscore;
+    int B, D, depth_mode;
+    long long HW;
+};
+
+__global__ void __launch_bounds__(K3_THREADS) k3_depth_regress_backward_kernel(const K3BwdParams p)
+{
+    __shared__ float red[3][K3_DL][K3_PIX];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, dl = threadIdx.x >> 5;
+    const long long pix_raw = (long long)blockIdx.x * K3_PIX + lane;
+    const bool active = pix_raw < p.HW;
+    const long long pix = active ? pix_raw : p.HW - 1;
+    const float *s = p.score + (long long)b * p.D * p.HW + pix;
+    const int D = p.D;
+    const float interval = (p.depth_mode >= MVSB200_DEPTH_START) ? __ldg(p.interval + b) : 0.f;
+    auto hyp = [&](int d) { return hypothesis(p.depth_mode, p.depth, interval, b, d, D, p.HW, pix); };
+
+    float mx = -INFINITY;
+    for (int d = dl; d < D; d += K3_DL) mx = fmaxf(mx, __ldg(s + d * p.HW));
+    red[0][dl][lane] = mx;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K3_DL; k++) mx = fmaxf(mx, red[0][k][lane]);
+    float sum = 0.f, e_dep = 0.f;
+    for (int d = dl; d < D; d += K3_DL) {
+        const float e = expf(__ldg(s + d * p.HW) - mx);
+        sum += e;
+        e_dep += e * hyp(d);
+    }
+    red[1][dl][lane] = sum;
+    red[2][dl][lane] = e_dep;
+    __syncthreads();
+    sum = e_dep = 0.f;
+#pragma unroll
+    for (int k = 0; k < K3_DL; k++) { sum += red[1][k][lane]; e_dep += red[2][k][lane]; }
+    if (!active) return;
+    e_dep /= sum;
+    const float g = __ldg(p.gdepth + (long long)b * p.HW + pix) / sum;
+    float *gs = p.gscore + (long long)b * D * p.HW + pix;
+    for (int d = dl; d < D; d += K3_DL) gs[d * p.HW] = g * expf(__ldg(s + d * p.HW) - mx) * (hyp(d) - e_dep);
+}
+
 constexpr int K4_THREADS = 256;
 
 struct K4Params {
@@ -156,4 +203,20 @@ extern "C" int mvsb200_vis_fuse(const float *const *interm, const float *const *
     MVSB200_REQUIRE(blocks < (1ll << 31), "vis_fuse: volume too large");
     k4_vis_fuse_kernel<<<(unsigned)blocks, K4_THREADS, 0, (cudaStream_t)stream>>>(p);
     return check_launch("k4_vis_fuse_kernel");
+}
+
+extern "C" int mvsb200_depth_regress_backward(const float *score, int B, int D, int H, int W, int depth_mode, const float *depth,
+                                              const float *interval, const float *grad_depth, float *grad_score,
+                                              mvsb200_stream_t stream)
+{
+    MVSB200_REQUIRE(score && depth && grad_depth && grad_score, "depth_regress_backward: null pointer");
+    MVSB200_REQUIRE(B > 0 && B <= 65535 && D > 0 && H > 0 && W > 0, "depth_regress_backward: bad shape B=%d D=%d H=%d W=%d", B, D, H, W);
+    MVSB200_REQUIRE(depth_mode >= 0 && depth_mode <= 3, "depth_regress_backward: depth_mode=%d", depth_mode);
+    MVSB200_REQUIRE(depth_mode < MVSB200_DEPTH_START || interval, "depth_regress_backward: interval is null");
+    K3BwdParams p;
+    p.score = score; p.depth = depth; p.interval = interval; p.gdepth = grad_depth; p.gscore = grad_score;
+    p.B = B; p.D = D; p.depth_mode = depth_mode; p.HW = (long long)H * W;
+    dim3 grid((unsigned)((p.HW + K3_PIX - 1) / K3_PIX), (unsigned)B);
+    k3_depth_regress_backward_kernel<<<grid, K3_THREADS, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("k3_depth_regress_backward_kernel");
 }

@@ -10,7 +10,10 @@ What runs where:
   * build_cost_volume  -> K1 (mvsb200_build_cost_volume), fused warp + aggregation
   * cost_regularization -> K2 (mvsb200_conv3d), BN/ReLU/skip fused
   * softmax / depth regression / confidence -> K3 (mvsb200_depth_regress)
-Inference only (eval mode); the backward pass is SURVEY.md 8-f2.
+Training mode (row f2 of SURVEY.md 8, started): the warp + aggregation and the regression head run on the library forward AND
+backward (K1 / K3 backward kernels behind torch.autograd.Function, ops.cost_volume / ops.regress_depth); the 3-D
+regulariser and the 2-D FeatureNet run as the PyTorch modules that own the parameters (batch-statistics BatchNorm,
+cuDNN dgrad / wgrad) -- a K2 backward is the part of f2 not built yet.
 """
 import torch
 import torch.nn as nn
@@ -133,8 +136,25 @@ class CostRegNet(nn.Module):
         x = conv(x, "conv11", c0)
         return conv(x, "prob").squeeze(-1)
 
+    def forward_modules(self, x):
+        """The same network through the PyTorch modules that own the parameters (models/MVSNet/model.py:74-84):
+        training mode, where BatchNorm uses batch statistics and autograd needs the layer graph."""
+        def cbr(name, v):   # the modules hold the parameters; the stride-2 layers are listed in _STRIDES
+            m = getattr(self, name)
+            return F.relu(m.bn(F.conv3d(v, m.conv.weight, None, self._STRIDES.get(name, 1), 1)), inplace=True)
+        conv0 = cbr("conv0", x)
+        conv2 = cbr("conv2", cbr("conv1", conv0))
+        conv4 = cbr("conv4", cbr("conv3", conv2))
+        x = cbr("conv6", cbr("conv5", conv4))
+        x = conv4 + self.conv7(x)
+        x = conv2 + self.conv9(x)
+        x = conv0 + self.conv11(x)
+        return self.prob(x)
+
     def forward(self, x, down_ft=None):
         """Reference signature: x [B,32,D,H,W] -> [B,1,D,H,W] (models/MVSNet/model.py:74-84)."""
+        if self.training or (torch.is_grad_enabled() and x.requires_grad):
+            return self.forward_modules(x)
         return self.run(ops.to_ndhwc(x)).unsqueeze(1)
 
 
@@ -232,9 +252,11 @@ class MVSNet(nn.Module):
         self.num_depth = 192
 
     def extract_features(self, imgs):
+        # training: one call per view like the reference (model.py:100-107) -- BatchNorm's batch statistics are per call
+        views = (lambda f, ims: [f(im) for im in ims]) if self.training else ops.map_views
         if self.aggregation.startswith("norm"):
-            return [F.normalize(f, dim=1) for f in ops.map_views(self.feature, imgs)]
-        return ops.map_views(self.feature, imgs)
+            return [F.normalize(f, dim=1) for f in views(self.feature, imgs)]
+        return views(self.feature, imgs)
 
     # ---- channels-last engine entry (what forward uses) ------------------------------------------
     def cost_volume_cl(self, ref_nhwc, srcs_nhwc, ref_proj, src_projs, depth_values):
@@ -246,6 +268,9 @@ class MVSNet(nn.Module):
         else:
             raise NotImplementedError("Aggregation: " + self.aggregation)
         warp = ops.mvs_relative_proj(ref_proj, torch.stack(list(src_projs), 1))
+        if torch.is_grad_enabled() and (ref_nhwc.requires_grad or any(f.requires_grad for f in srcs_nhwc)
+                                        or (temp is not None and temp.requires_grad)):
+            return ops.cost_volume(ref_nhwc, srcs_nhwc, warp, depth_values, self.num_depth, L.GEOM_MVS, agg, temp=temp)
         return ops.build_cost_volume(ref_nhwc, srcs_nhwc, warp, depth_values, self.num_depth, L.GEOM_MVS, agg, temp=temp)
 
     def build_cost_volume(self, ref_feature, src_features, ref_proj, src_projs, depth_values):
@@ -266,6 +291,18 @@ class MVSNet(nn.Module):
         out = ops.depth_regress(score, depth_values, conf_mode=L.CONF_SUM4)
         return out["depth"], out["conf"]
 
+    def _forward_differentiable(self, imgs, proj_matrices, depth_values, reference_frame):
+        """Training path (models/trainer.py:96-206 calls forward with grad enabled): features -> K1 (autograd) ->
+        regulariser modules -> K3 (autograd).  Gradients reach the feature extractor, the regulariser and `temp`."""
+        features = self.extract_features(imgs)
+        ref = features[reference_frame]
+        srcs = features[:reference_frame] + features[reference_frame + 1:]
+        ref_proj = proj_matrices[reference_frame]
+        src_projs = proj_matrices[:reference_frame] + proj_matrices[reference_frame + 1:]
+        vol = self.cost_volume_cl(ops.to_nhwc(ref), [ops.to_nhwc(f) for f in srcs], ref_proj, src_projs, depth_values)
+        score = self.cost_regularization(ops.as_ncdhw(vol)).squeeze(1)
+        return ops.regress_depth(score, depth_values, conf_mode=L.CONF_SUM4)
+
     def graphed(self, feats_nhwc, proj_matrices, depth_values, reference_frame=0):
         """CUDA-graph version of depth_from_features for inputs of these shapes (see GraphedHotPath)."""
         return GraphedHotPath(self, feats_nhwc, proj_matrices, depth_values, reference_frame)
@@ -275,8 +312,6 @@ class MVSNet(nn.Module):
         return StreamedHotPath(self, feats_nhwc, proj_matrices, depth_values, reference_frame, slots)
 
     def forward(self, imgs, K, R, t, depth_min, depth_max, reference_frame=0, **kwargs):
-        if self.training:
-            raise NotImplementedError("libmvsb200 implements inference only; call .eval() (SURVEY.md 8-f2)")
         try:
             imgs = torch.unbind(imgs, 1)
         except TypeError:  # already a list (views of different sizes)
@@ -289,8 +324,12 @@ class MVSNet(nn.Module):
         depth_values = depth_min.unsqueeze(-1) + depth_range.unsqueeze(-1) * steps
         assert len(imgs) == len(proj_matrices), "Different number of images and projection matrices"
 
-        with torch.no_grad():
-            feats = [ops.to_nhwc(f) for f in self.extract_features(imgs)]
-            depth, conf = self.depth_from_features(list(feats), list(proj_matrices),
-                                                   depth_values[:, reference_frame].contiguous(), reference_frame)
+        if self.training:
+            depth, conf = self._forward_differentiable(imgs, list(proj_matrices), depth_values[:, reference_frame].contiguous(),
+                                                       reference_frame)
+        else:
+            with torch.no_grad():
+                feats = [ops.to_nhwc(f) for f in self.extract_features(imgs)]
+                depth, conf = self.depth_from_features(list(feats), list(proj_matrices),
+                                                       depth_values[:, reference_frame].contiguous(), reference_frame)
         return {"depth": depth, "depth_est_list": [depth], "depth_pair_list": [], "photometric_confidence": conf}

@@ -182,6 +182,85 @@ def build_cost_volume(ref, srcs, warp, depth, D, geom, agg, interval=None, temp=
     return out
 
 
+def _cost_volume_desc(ref, srcs, D, geom, agg, groups, depth, interval):
+    B, H, W, C = ref.shape
+    S = len(srcs)
+    if not 1 <= S <= L.MAX_SRC:
+        raise L.Mvsb200Error("number of source views %d not in [1,%d]" % (S, L.MAX_SRC))
+    desc = L.CostVolumeDesc()
+    desc.geom, desc.agg = geom, agg
+    desc.depth_mode = _depth_mode(depth, interval, B, D, H, W)
+    desc.B, desc.S, desc.C, desc.D, desc.H, desc.W = B, S, C, D, H, W
+    desc.groups = groups if agg == L.AGG_GROUPCORR else 0
+    ptrs = (ctypes.c_void_p * S)()
+    for i, s in enumerate(srcs):
+        _dev_f32(s, "src[%d]" % i)
+        if s.shape[0] != B or s.shape[3] != C:
+            raise L.Mvsb200Error("src[%d] has shape %s, expected [%d,*,*,%d]" % (i, tuple(s.shape), B, C))
+        ptrs[i] = s.data_ptr()
+        desc.src_h[i], desc.src_w[i] = s.shape[1], s.shape[2]
+    desc.out_view_stride = B * D * H * W * groups if agg == L.AGG_GROUPCORR else 0
+    return desc, ptrs
+
+
+def build_cost_volume_backward(grad_out, ref, srcs, warp, depth, D, geom, agg, interval=None, temp=None, groups=8):
+    """Gradient of build_cost_volume with respect to the feature maps (and `temp` for AGG_SOFTMIN): K1 backward
+    (mvsb200_build_cost_volume_backward).  Returns (grad_ref [B,H,W,C], [grad_src_s], grad_temp or None)."""
+    lib = L.load()
+    ref = _dev_f32(ref, "ref")
+    depth = _dev_f32(depth.contiguous(), "depth")
+    if interval is not None:
+        interval = _dev_f32(interval.contiguous().view(-1), "interval")
+    desc, ptrs = _cost_volume_desc(ref, srcs, D, geom, agg, groups, depth, interval)
+    B, H, W, C = ref.shape
+    shape = (len(srcs), B, D, H, W, groups) if agg == L.AGG_GROUPCORR else (B, D, H, W, C)
+    grad_out = grad_out.contiguous()
+    if tuple(_dev_f32(grad_out, "grad_out").shape) != shape:
+        raise L.Mvsb200Error("build_cost_volume_backward: grad_out has shape %s, expected %s" % (tuple(grad_out.shape), shape))
+    g_ref = torch.zeros_like(ref)
+    g_srcs = [torch.zeros_like(s) for s in srcs]
+    gptrs = (ctypes.c_void_p * len(srcs))(*[g.data_ptr() for g in g_srcs])
+    g_temp = None
+    if agg == L.AGG_SOFTMIN:
+        temp = _dev_f32(temp.detach().contiguous(), "temp")
+        g_temp = torch.zeros_like(temp)
+    L.check(lib.mvsb200_build_cost_volume_backward(ctypes.byref(desc), _ptr(ref), ptrs, _ptr(_dev_f32(warp, "warp")), _ptr(depth),
+                                                   _ptr(interval), _ptr(temp), _ptr(grad_out), _ptr(g_ref), gptrs, _ptr(g_temp),
+                                                   _stream()), "mvsb200_build_cost_volume_backward")
+    return g_ref, g_srcs, g_temp
+
+
+class _CostVolumeFn(torch.autograd.Function):
+    """build_cost_volume as a differentiable op: K1 forward, K1 backward.  Like the reference (sampling grid under
+    torch.no_grad(): models/MVSNet/module.py:127, VisMVSNet/homography.py:25,110) the gradient flows to the feature maps
+    (and the soft-min temperature) only."""
+
+    @staticmethod
+    def forward(ctx, cfg, warp, depth, interval, temp, ref, *srcs):
+        D, geom, agg, groups = cfg
+        ref = ref.contiguous()
+        srcs = [s.contiguous() for s in srcs]
+        out = build_cost_volume(ref, srcs, warp, depth, D, geom, agg, interval=interval, temp=temp, groups=groups)
+        ctx.cfg = cfg
+        ctx.save_for_backward(warp, depth, interval, temp, ref, *srcs)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        warp, depth, interval, temp, ref, *srcs = ctx.saved_tensors
+        D, geom, agg, groups = ctx.cfg
+        g_ref, g_srcs, g_temp = build_cost_volume_backward(grad_out, ref, list(srcs), warp, depth, D, geom, agg,
+                                                           interval=interval, temp=temp, groups=groups)
+        if g_temp is not None:
+            g_temp = g_temp.view(ctx.saved_tensors[3].shape)
+        return (None, None, None, None, g_temp, g_ref, *g_srcs)
+
+
+def cost_volume(ref, srcs, warp, depth, D, geom, agg, interval=None, temp=None, groups=8):
+    """Differentiable build_cost_volume (training, row f2): same arguments and result, autograd-aware."""
+    return _CostVolumeFn.apply((D, geom, agg, groups), warp, depth, interval, temp, ref, *srcs)
+
+
 # ------------------------------------------------------------------------------------------------
 # K2
 # ------------------------------------------------------------------------------------------------
@@ -370,6 +449,48 @@ def depth_regress(score, depth, interval=None, conf_mode=L.CONF_NONE, want_entro
                                       _ptr(out["depth"]), _ptr(out["conf"]), _ptr(out["entropy"]), _ptr(out["prob"]),
                                       _stream()), "mvsb200_depth_regress")
     return out
+
+
+def depth_regress_backward(grad_depth, score, depth, interval=None):
+    """grad_score [B,D,H,W] of depth_regress()["depth"] (K3 backward, mvsb200_depth_regress_backward)."""
+    lib = L.load()
+    score = _dev_f32(score, "score")
+    B, D, H, W = score.shape
+    depth = _dev_f32(depth.contiguous(), "depth")
+    if interval is not None:
+        interval = _dev_f32(interval.contiguous().view(-1), "interval")
+    mode = _depth_mode(depth, interval, B, D, H, W)
+    grad_depth = _dev_f32(grad_depth.contiguous(), "grad_depth")
+    if grad_depth.numel() != B * H * W:
+        raise L.Mvsb200Error("depth_regress_backward: grad_depth has shape %s" % (tuple(grad_depth.shape),))
+    g = torch.empty_like(score)
+    L.check(lib.mvsb200_depth_regress_backward(_ptr(score), B, D, H, W, mode, _ptr(depth), _ptr(interval), _ptr(grad_depth),
+                                               _ptr(g), _stream()), "mvsb200_depth_regress_backward")
+    return g
+
+
+class _DepthRegressFn(torch.autograd.Function):
+    """softmax over D + expectation of the hypotheses as a differentiable op (K3 forward / backward).  The confidence is
+    returned without a gradient, as in the reference (torch.no_grad(), models/MVSNet/model.py:211-215)."""
+
+    @staticmethod
+    def forward(ctx, score, depth, interval, conf_mode):
+        score = score.contiguous()
+        out = depth_regress(score, depth, interval, conf_mode=conf_mode)
+        ctx.save_for_backward(score, depth, interval)
+        conf = out["conf"] if out["conf"] is not None else out["depth"].new_zeros(())
+        ctx.mark_non_differentiable(conf)
+        return out["depth"], conf
+
+    @staticmethod
+    def backward(ctx, g_depth, _g_conf):
+        score, depth, interval = ctx.saved_tensors
+        return depth_regress_backward(g_depth, score, depth, interval), None, None, None
+
+
+def regress_depth(score, depth, interval=None, conf_mode=L.CONF_NONE):
+    """Differentiable depth regression (training, row f2): -> (depth [B,H,W], confidence [B,H,W] or a 0-d zero)."""
+    return _DepthRegressFn.apply(score, depth, interval, conf_mode)
 
 
 def vis_fuse(interms, uncerts):
