@@ -27,7 +27,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$KR
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_full_$TAG.log 2>&1
 echo "ncu full rc=$?"
 # memory checker over the kernel parity tests (every kernel of the library at small sizes)
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu \
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_backward.py tests/test_gpu_filter.py -x -q -m gpu -k "not cfg1_size and not training_step" \
     > $OUT/sanitizer_$TAG.log 2>&1
 echo "sanitizer rc=$?" | tee -a $OUT/sanitizer_$TAG.log
 tail -3 $OUT/sanitizer_$TAG.log

@@ -43,7 +43,8 @@ def test_depth_from_features_matches_reference(golden, agg):
     # the seam methods keep the reference's signatures and layouts
     vol = net.build_cost_volume(t(g["feat0"]), [t(g["feat1"]), t(g["feat2"])], projs[0], projs[1:], t(g["depth_values"]))
     assert vol.shape == g["cost_volume"].shape
-    assert rel_linf(vol.cpu().numpy(), g["cost_volume"]) < 1e-4
+    assert vol.requires_grad == (agg == "softmin")   # like the reference: `temp` is a Parameter, grad mode is on here
+    assert rel_linf(vol.detach().cpu().numpy(), g["cost_volume"]) < 1e-4
     reg = net.cost_regularization(t(g["cost_volume"]))
     assert rel_linf(reg[:, 0].cpu().numpy(), g["cost_reg"]) < 2e-5
 
