@@ -217,10 +217,13 @@ MVSB200_API int mvsb200_depth_regress(const float *score, int B, int D, int H, i
 
 /* Backward of the regression output: grad_score[b,d,y,x] = grad_depth[b,y,x] p_d (h_d - depth), p = softmax(score)
  * (autograd of models/MVSNet/model.py:207-209, module.py:174-178, VisMVSNet/nn_utils.py:453-466; confidence and entropy
- * are produced under no_grad in the reference).  grad_depth [B,H,W]; grad_score [B,D,H,W], fully written. */
+ * are produced under no_grad in the reference).  grad_depth [B,H,W]; grad_score [B,D,H,W], fully written.
+ * grad_hyp (optional, DEPTH_VOLUME only): [B,D,H,W] <- grad_depth p_d, the gradient with respect to per-voxel hypotheses
+ * (CVP-MVSNet's refinement levels regress over hypotheses built from the previous level's depth map:
+ * CVP_MVSNet/models/net.py:176-182,203, modules.py:362-365). */
 MVSB200_API int mvsb200_depth_regress_backward(const float *score, int B, int D, int H, int W, int depth_mode, const float *depth,
                                                const float *interval, const float *grad_depth, float *grad_score,
-                                               mvsb200_stream_t stream);
+                                               float *grad_hyp, mvsb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K5: the per-pixel part of CVP-MVSNet's calDepthHypo (models/CVP_MVSNet/models/modules.py:131-226), fp64 inside:

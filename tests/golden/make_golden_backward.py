@@ -9,7 +9,11 @@ tests/golden/backward.npz holds, on the inputs already stored in mvsnet_*.npz / 
     the same for the 8-group correlation volumes of both source views;
   * softmax + `depth_regression` (model.py:207-209): gradient of sum(depth * Gd) with respect to the score volume;
   * one training-mode `forward` + L1 loss of MVSNet-s (the reference's training configuration): the depth map and the
-    gradients of a few parameters across the whole model (`mvsnet_train.npz`, with the weights).
+    gradients of a few parameters across the whole model (`mvsnet_train.npz`, with the weights);
+  * the same for CVP-MVSNet with two pyramid levels (`cvp_train.npz`): training-mode hypotheses (net.py:126,176-182),
+    loss on both levels, so the gradient also runs through the refinement level's hypotheses into the coarse level.
+
+    python tests/golden/make_golden_backward.py [cvp]      # `cvp`: only cvp_train.npz
 """
 import os
 import sys
@@ -28,9 +32,39 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 T = torch.from_numpy
 
 
+def cvp_train(ref):
+    torch.manual_seed(0)
+    net = ref.CVPFrontend()
+    synth.randomize_norm_stats(net, seed=3)
+    synth.scale_param(net.model.cost_reg_refine.prob0.weight, 30.0)
+    net.model.nscale = 2
+    sd = {k: v.detach().clone().numpy() for k, v in net.state_dict().items()}
+    net.train()
+    s = synth.make_sample(2, 3, 32, 48, seed=6)
+    res = net(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"], nscale=2)
+    gen = torch.Generator().manual_seed(9)
+    ests = res["depth_est_list"]
+    targets = [500 + 300 * torch.rand(e.shape, generator=gen) for e in ests]
+    loss = sum((e - t).abs().mean() for e, t in zip(ests, targets))
+    loss.backward()
+    tr = {"sd." + k: v for k, v in sd.items()}
+    tr.update({"depth_est_0": ests[0].detach().numpy(), "depth_est_1": ests[1].detach().numpy(), "target_0": targets[0].numpy(),
+               "target_1": targets[1].numpy(), "conf": res["photometric_confidence"].numpy(), "loss": np.float32(loss.item()),
+               "seed": np.int32(6)})
+    params = dict(net.named_parameters())
+    for k in ("model.featurePyramid.conv0aa.0.weight", "model.featurePyramid.conv0bh.0.bias", "model.cost_reg_refine.conv0.conv.weight",
+              "model.cost_reg_refine.conv4a.bn.weight", "model.cost_reg_refine.conv6.0.weight", "model.cost_reg_refine.prob0.weight"):
+        tr["grad." + k] = params[k].grad.numpy()
+        print(k, "grad abs-max", float(params[k].grad.abs().max()))
+    np.savez_compressed(os.path.join(OUT, "cvp_train.npz"), **tr)
+    print("cvp_train.npz", os.path.getsize(os.path.join(OUT, "cvp_train.npz")) // 1024, "KiB")
+
+
 def main():
     ref = import_reference()
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["cvp"]:
+        return cvp_train(ref)
     out = {}
 
     # ---- MVSNet cost volumes ---------------------------------------------------------------------------------------
@@ -115,6 +149,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "mvsnet_train.npz"), **tr)
     for f in ("backward.npz", "mvsnet_train.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+    cvp_train(ref)
 
 
 if __name__ == "__main__":

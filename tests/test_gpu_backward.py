@@ -229,6 +229,55 @@ def test_mvsnet_training_step_matches_the_reference(golden, monkeypatch):
     assert not out["depth"].requires_grad
 
 
+def test_k3_backward_gradient_of_per_voxel_hypotheses():
+    """CVP's refinement levels regress over hypotheses built from the previous level's depth: dL/dh_d = g p_d."""
+    gen = torch.Generator().manual_seed(5)
+    B, D, H, W = 2, 8, 11, 37
+    sc = (2 * torch.randn(B, D, H, W, generator=gen)).to(DEV)
+    base = (500 + 100 * torch.rand(B, H, W, generator=gen)).to(DEV)
+    Gd = torch.randn(B, H, W, generator=gen).to(DEV)
+    steps = torch.arange(-4, 4, device=DEV, dtype=torch.float32).view(1, D, 1, 1)
+    grads = []
+    for mine in (True, False):
+        s1, b1 = sc.clone().requires_grad_(True), base.clone().requires_grad_(True)
+        hyp = b1.unsqueeze(1) + 2.5 * steps
+        d = ops.regress_depth(s1, hyp, None, L.CONF_NONE)[0] if mine else (torch.softmax(s1, 1) * hyp).sum(1)
+        (d * Gd).sum().backward()
+        grads.append((s1.grad, b1.grad))
+    assert rel_linf(grads[0][0].cpu().numpy(), grads[1][0].cpu().numpy()) < GRAD_TOL
+    assert rel_linf(grads[0][1].cpu().numpy(), grads[1][1].cpu().numpy()) < GRAD_TOL     # = Gd: the softmax sums to one
+    with pytest.raises(L.Mvsb200Error):       # a [B,D] table of hypotheses shared by all pixels cannot take a gradient here
+        dv = torch.linspace(1, 2, D, device=DEV).view(1, D).repeat(B, 1).requires_grad_(True)
+        ops.regress_depth(sc.clone().requires_grad_(True), dv, None, L.CONF_NONE)[0].sum().backward()
+
+
+def test_cvp_training_step_matches_the_reference(golden, monkeypatch):
+    """One training-mode forward + L1 loss on both pyramid levels + backward of CVP-MVSNet with the reference's weights
+    (net.py:96-229 with self.training: 48 initial hypotheses, fixed refinement intervals): K1 backward in its
+    VARIANCE_MEAN / per-pixel-hypotheses mode, K3 backward including the gradient through the refinement hypotheses."""
+    from wild_deep_mvs_b200.cvpmvsnet import Frontend
+    g = golden("cvp_train")
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)      # the golden is fp32 on the CPU
+    net = Frontend()
+    net.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}, strict=True)
+    net.model.nscale = 2
+    net = net.to(DEV).train()
+    s = {k: v.to(DEV) for k, v in synth.make_sample(2, 3, 32, 48, seed=int(g["seed"])).items()}
+    out = net(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"], nscale=2)
+    ests = out["depth_est_list"]
+    assert [tuple(e.shape) for e in ests] == [(2, 32, 48), (2, 16, 24)] and all(e.requires_grad for e in ests)
+    for i in range(2):
+        assert rel_linf(ests[i].detach().cpu().numpy(), g["depth_est_%d" % i]) < 1e-3
+    loss = sum((e - cu(g["target_%d" % i])).abs().mean() for i, e in enumerate(ests))
+    assert abs(loss.item() - float(g["loss"])) < 1e-3 * float(g["loss"])
+    loss.backward()
+    params = dict(net.named_parameters())
+    for k in [k[5:] for k in g if k.startswith("grad.")]:
+        err = rel_linf(params[k].grad.cpu().numpy(), g["grad." + k])
+        print(k, "grad rel err %.2e" % err)
+        assert err < 1e-2, k
+
+
 def test_backward_errors_are_loud():
     ref = torch.zeros(1, 8, 8, 32, device=DEV)
     warp = torch.zeros(1, 1, 16, device=DEV)

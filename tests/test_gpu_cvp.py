@@ -89,8 +89,8 @@ def test_forward_api(golden):
     out2 = net(list(torch.unbind(s["imgs"], 1)), s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"],
                reference_frame=1, nscale=2)
     assert out2["depth"].shape == (1, 32, 48) and torch.isfinite(out2["depth"]).all()
-    with pytest.raises(NotImplementedError):
-        net.train()(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"])
+    out3 = net.train()(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"], nscale=2)   # tests/test_gpu_backward.py
+    assert out3["depth"].requires_grad and out3["depth"].shape == (1, 32, 48)
 
 
 def test_full_size_properties():

@@ -2,18 +2,25 @@
 // models/MVSNet/model.py:72, models/VisMVSNet/model_cas.py:44,61, CVP_MVSNet/models/net.py:67) on the CUDA cores, fp32.
 //
 // A 1-column GEMM wastes 7/8 of the narrowest tensor-core tile, and the layer is tiny in FLOPs (216 FMA per voxel for
-// Cin = 8) but reads a full-resolution volume: it belongs on the FMA pipe, next to HBM.  One thread owns one (y,x)
-// output column of an 8 x 32 tile and marches along z with three rolling accumulators (the planes z-1, z, z+1 that
-// the current input plane contributes to), so every input plane is staged in shared memory exactly once per tile
-// (cp.async, double buffered, channel-quad-major so the 16-byte reads of a warp are conflict free) and every staged
-// value is used for three FMAs.  The 27*Cin weights travel as KERNEL PARAMETERS: the fully unrolled FMAs take them
-// straight from the constant bank, no weight loads at all.
+// Cin = 8) but reads a full-resolution volume: it belongs on the FMA pipe, next to HBM.  One thread owns TWO vertically
+// adjacent (y,x) output columns of a 16 x 32 tile (Cin = 8; one column of an 8 x 32 tile for wider inputs) and marches along z with three rolling accumulators per column (the
+// planes z-1, z, z+1 that the current input plane contributes to), so every input plane is staged in shared memory
+// exactly once per tile (cp.async, double buffered, channel-quad-major so the 16-byte reads of a warp are conflict
+// free), the two columns share two of their three tap rows (24 instead of 36 shared-memory reads per pair) and every
+// weight fetched from the constant bank feeds two FMAs.  The 27*Cin weights travel as KERNEL PARAMETERS, no weight
+// loads at all.  The kernel is bound by instruction issue, so the per-plane staging does no index arithmetic either:
+// a thread's (global offset, shared slot) pairs are the same for every plane and are computed once.
 #include "common.cuh"
 
 namespace mvsb200 {
 
-constexpr int C1_TY = 8, C1_TX = 32, C1_THREADS = C1_TY * C1_TX;
-constexpr int C1_EY = C1_TY + 2, C1_EX = C1_TX + 2, C1_NPOS = C1_EY * C1_EX;
+constexpr int C1_TX = 32, C1_THREADS = 8 * C1_TX, C1_EX = C1_TX + 2;
+// ROWS = vertically adjacent output columns per thread (rows ROWS*ly .. ROWS*ly + ROWS-1 of an 8*ROWS x 32 tile): 2 for
+// Cin = 8; wider inputs keep 1 (two columns of 16+ channels do not fit the register file at 3 CTAs / SM)
+template <int CIN> struct C1Tile {
+    static constexpr int ROWS = CIN == 8 ? 2 : 1;
+    static constexpr int TY = 8 * ROWS, EY = TY + 2, NPOS = EY * C1_EX;
+};
 
 template <int CIN> struct C1Params {
     const float *x;
@@ -34,9 +41,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int CIN>
-__global__ void __launch_bounds__(C1_THREADS) k2_conv3d_c1_kernel(const __grid_constant__ C1Params<CIN> p)
+__global__ void __launch_bounds__(C1_THREADS, 3) k2_conv3d_c1_kernel(const __grid_constant__ C1Params<CIN> p)
 {
-    constexpr int C4 = CIN / 4;
+    constexpr int C4 = CIN / 4, ROWS = C1Tile<CIN>::ROWS, C1_TY = C1Tile<CIN>::TY, C1_NPOS = C1Tile<CIN>::NPOS;
     extern __shared__ __align__(16) float4 c1_smem[];   // [2][C4][NPOS]
     int t = blockIdx.x;
     const int tx = t % p.tiles_x; t /= p.tiles_x;
@@ -47,22 +54,35 @@ __global__ void __launch_bounds__(C1_THREADS) k2_conv3d_c1_kernel(const __grid_c
     const int zb = sg * p.zseg, ze = min(zb + p.zseg, p.D);
     const int lx = threadIdx.x % C1_TX, ly = threadIdx.x / C1_TX;
 
+    // The pieces (16 bytes = 4 channels of one halo position) this thread stages are the same for every plane: element
+    // offset inside the plane (-1: outside the volume, zero filled) and shared-memory slot (-1: no piece).
+    constexpr int NIT = (C1_NPOS * C4 + C1_THREADS - 1) / C1_THREADS;
+    int goff[NIT], soff[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const int i = threadIdx.x + it * C1_THREADS;
+        const int c4 = i % C4, pos = i / C4;     // consecutive threads: consecutive 16-byte pieces in global memory
+        const int gy = y0 - 1 + pos / C1_EX, gx = x0 - 1 + pos % C1_EX;
+        const bool ok = (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W;
+        goff[it] = ok ? (gy * p.W + gx) * CIN + c4 * 4 : -1;
+        soff[it] = i < C1_NPOS * C4 ? c4 * C1_NPOS + pos : -1;
+    }
     // stage input plane z (with its 1-voxel (y,x) halo, zero filled outside the volume) into buffer `buf`
     auto stage = [&](int z, int buf) {
         if ((unsigned)z < (unsigned)p.D) {
             const float *plane = p.x + ((long long)b * p.D + z) * p.H * p.W * CIN;
-            for (int i = threadIdx.x; i < C1_NPOS * C4; i += C1_THREADS) {
-                const int c4 = i % C4, pos = i / C4;     // consecutive threads: consecutive 16-byte pieces in global memory
-                const int gy = y0 - 1 + pos / C1_EX, gx = x0 - 1 + pos % C1_EX;
-                const bool ok = (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W;
-                const float *src = ok ? plane + ((long long)gy * p.W + gx) * CIN + c4 * 4 : plane;
-                cp_async16_zfill(&c1_smem[(buf * C4 + c4) * C1_NPOS + pos], src, ok);
-            }
+            float4 *dst = c1_smem + buf * C4 * C1_NPOS;
+#pragma unroll
+            for (int it = 0; it < NIT; it++)
+                if (soff[it] >= 0) cp_async16_zfill(dst + soff[it], plane + max(goff[it], 0), goff[it] >= 0);
         }
         cp_async_commit();
     };
 
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;   // accumulators of output planes z-1, z, z+1 while input plane z is consumed
+    // acc[j][k]: output column j of this thread, output plane z-1+k, while input plane z is consumed
+    float acc[ROWS][3];
+#pragma unroll
+    for (int j = 0; j < ROWS; j++) acc[j][0] = acc[j][1] = acc[j][2] = 0.f;
     stage(zb - 1, 0);
     for (int z = zb - 1, it = 0; z <= ze; z++, it++) {
         const int buf = it & 1;
@@ -70,32 +90,44 @@ __global__ void __launch_bounds__(C1_THREADS) k2_conv3d_c1_kernel(const __grid_c
         cp_async_wait<1>();
         __syncthreads();
         if ((unsigned)z < (unsigned)p.D) {
-            const float4 *sp = c1_smem + buf * C4 * C1_NPOS + ly * C1_EX + lx;
+            const float4 *sp = c1_smem + buf * C4 * C1_NPOS + (ROWS * ly) * C1_EX + lx;
 #pragma unroll
-            for (int dy = 0; dy < 3; dy++)
+            for (int r = 0; r < ROWS + 2; r++)      // halo row ROWS*ly + r is tap row r - j of output column j
 #pragma unroll
                 for (int dx = 0; dx < 3; dx++)
 #pragma unroll
                     for (int c4 = 0; c4 < C4; c4++) {
-                        const float4 v = sp[c4 * C1_NPOS + dy * C1_EX + dx];
-                        const int w2 = ((2 * 3 + dy) * 3 + dx) * CIN + c4 * 4;   // kz = 2 -> output plane z-1
-                        const int w1 = ((1 * 3 + dy) * 3 + dx) * CIN + c4 * 4;   // kz = 1 -> output plane z
-                        const int w0 = ((0 * 3 + dy) * 3 + dx) * CIN + c4 * 4;   // kz = 0 -> output plane z+1
-                        a0 = fmaf(v.x, p.w[w2], a0); a0 = fmaf(v.y, p.w[w2 + 1], a0); a0 = fmaf(v.z, p.w[w2 + 2], a0); a0 = fmaf(v.w, p.w[w2 + 3], a0);
-                        a1 = fmaf(v.x, p.w[w1], a1); a1 = fmaf(v.y, p.w[w1 + 1], a1); a1 = fmaf(v.z, p.w[w1 + 2], a1); a1 = fmaf(v.w, p.w[w1 + 3], a1);
-                        a2 = fmaf(v.x, p.w[w0], a2); a2 = fmaf(v.y, p.w[w0 + 1], a2); a2 = fmaf(v.z, p.w[w0 + 2], a2); a2 = fmaf(v.w, p.w[w0 + 3], a2);
+                        const float4 v = sp[c4 * C1_NPOS + r * C1_EX + dx];
+#pragma unroll
+                        for (int j = 0; j < ROWS; j++) {
+                            const int dy = r - j;
+                            if (dy < 0 || dy > 2) continue;
+#pragma unroll
+                            for (int k = 0; k < 3; k++) {   // kz = 2 - k feeds output plane z-1+k
+                                const int w = (((2 - k) * 3 + dy) * 3 + dx) * CIN + c4 * 4;
+                                acc[j][k] = fmaf(v.x, p.w[w], acc[j][k]);
+                                acc[j][k] = fmaf(v.y, p.w[w + 1], acc[j][k]);
+                                acc[j][k] = fmaf(v.z, p.w[w + 2], acc[j][k]);
+                                acc[j][k] = fmaf(v.w, p.w[w + 3], acc[j][k]);
+                            }
+                        }
                     }
         }
         const int zo = z - 1;   // complete now
         if (zo >= zb && zo < ze) {
-            const int oy = y0 + ly, ox = x0 + lx;
-            if (oy < p.H && ox < p.W) {
-                float r = fmaf(a0, p.scale, p.bias);
-                if (p.relu) r = fmaxf(r, 0.f);
-                p.y[(((long long)b * p.D + zo) * p.H + oy) * p.W + ox] = r;
+            const int oy = y0 + ROWS * ly, ox = x0 + lx;
+            if (ox < p.W) {
+                float *dst = p.y + (((long long)b * p.D + zo) * p.H + oy) * p.W + ox;
+#pragma unroll
+                for (int j = 0; j < ROWS; j++) {
+                    float r = fmaf(acc[j][0], p.scale, p.bias);
+                    if (p.relu) r = fmaxf(r, 0.f);
+                    if (oy + j < p.H) dst[(long long)j * p.W] = r;
+                }
             }
         }
-        a0 = a1; a1 = a2; a2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < ROWS; j++) { acc[j][0] = acc[j][1]; acc[j][1] = acc[j][2]; acc[j][2] = 0.f; }
         __syncthreads();   // the buffer just read is refilled by the next iteration's prefetch
     }
 }
@@ -109,20 +141,27 @@ static int launch_c1(const mvsb200_conv3d_desc *d, const float *x, const float *
     p.scale = scale; p.bias = bias; p.relu = d->relu;
     for (int i = 0; i < 27 * CIN; i++) p.w[i] = w_host[i];
     p.tiles_x = (d->W + C1_TX - 1) / C1_TX;
-    p.tiles_y = (d->H + C1_TY - 1) / C1_TY;
-    // depth segments: enough CTAs to fill the machine several times over, at most ~1/8 z-halo overhead when possible
+    p.tiles_y = (d->H + C1Tile<CIN>::TY - 1) / C1Tile<CIN>::TY;
+    // depth segments: trade the z-halo (2 extra planes per segment) against the balance of the last wave of CTAs
+    const size_t smem = (size_t)2 * (CIN / 4) * C1Tile<CIN>::NPOS * sizeof(float4);
     const long long base = (long long)p.tiles_x * p.tiles_y * d->B;
-    int nseg = (int)((148 * 8 + base - 1) / base);
-    if (nseg > (d->D + 15) / 16) nseg = (d->D + 15) / 16;
-    if (nseg < 1) nseg = 1;
-    p.zseg = (d->D + nseg - 1) / nseg;
+    int resident = (int)((220 * 1024) / smem);
+    if (resident > 3) resident = 3;   // __launch_bounds__(C1_THREADS, 3)
+    const long long slots = 148ll * resident;
+    double best = -1.0;
+    p.zseg = d->D;
+    for (int zseg = d->D < 4 ? d->D : 4; zseg <= d->D; zseg++) {
+        const int nseg = (d->D + zseg - 1) / zseg;
+        const long long ctas = base * nseg;
+        const double eff = (double)ctas / (double)((ctas + slots - 1) / slots * slots) * (double)d->D / (double)(nseg * (zseg + 2));
+        if (eff > best) { best = eff; p.zseg = zseg; }
+    }
     p.nseg = (d->D + p.zseg - 1) / p.zseg;
     const long long blocks = base * p.nseg;
     if (blocks >= (1ll << 31)) {
         set_error("conv3d_c1: volume too large");
         return MVSB200_E_INVALID;
     }
-    const size_t smem = (size_t)2 * (CIN / 4) * C1_NPOS * sizeof(float4);
     if (smem > 48 * 1024)
         if (int rc = ensure_dynamic_smem(k2_conv3d_c1_kernel<CIN>, smem, "conv3d_c1")) return rc;
     k2_conv3d_c1_kernel<CIN><<<(unsigned)blocks, C1_THREADS, smem, st>>>(p);
@@ -147,6 +186,7 @@ extern "C" int mvsb200_conv3d_c1(const mvsb200_conv3d_desc *d, const float *x, c
     MVSB200_REQUIRE(d && x && w_host && y, "conv3d_c1: null pointer");
     MVSB200_REQUIRE(c1_shape_ok(d), "conv3d_c1: needs a 3x3x3 stride-1 conv with Cout == 1, Cin in {8,16,24,32}, one input, no skip");
     MVSB200_REQUIRE(d->B > 0 && d->D > 0 && d->H > 0 && d->W > 0, "conv3d_c1: bad shape B=%d D=%d H=%d W=%d", d->B, d->D, d->H, d->W);
+    MVSB200_REQUIRE((long long)d->H * d->W * d->Cin < (1ll << 31), "conv3d_c1: plane too large (%dx%dx%d)", d->H, d->W, d->Cin);
     cudaStream_t st = (cudaStream_t)stream;
     switch (d->Cin) {
     case 8: return launch_c1<8>(d, x, w_host, scale, bias, y, st);

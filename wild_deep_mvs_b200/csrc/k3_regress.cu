@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_depth_regress_kernel(const K3Pa
 // Same block shape as the forward kernel; the statistics are recomputed instead of stored.
 struct K3BwdParams {
     const float *score, *depth, *interval, *gdepth;
-    float *gscore;
+    float *gscore, *ghyp;
     int B, D, depth_mode;
     long long HW;
 };
@@ -126,7 +126,12 @@ __global__ void __launch_bounds__(K3_THREADS) k3_depth_regress_backward_kernel(c
     e_dep /= sum;
     const float g = __ldg(p.gdepth + (long long)b * p.HW + pix) / sum;
     float *gs = p.gscore + (long long)b * D * p.HW + pix;
-    for (int d = dl; d < D; d += K3_DL) gs[d * p.HW] = g * expf(__ldg(s + d * p.HW) - mx) * (hyp(d) - e_dep);
+    float *gh = p.ghyp ? p.ghyp + (long long)b * D * p.HW + pix : nullptr;   // per-voxel hypotheses: dL/dh_d = g p_d
+    for (int d = dl; d < D; d += K3_DL) {
+        const float gp = g * expf(__ldg(s + d * p.HW) - mx);
+        gs[d * p.HW] = gp * (hyp(d) - e_dep);
+        if (gh) gh[d * p.HW] = gp;
+    }
 }
 
 constexpr int K4_THREADS = 256;
@@ -207,14 +212,15 @@ extern "C" int mvsb200_vis_fuse(const float *const *interm, const float *const *
 
 extern "C" int mvsb200_depth_regress_backward(const float *score, int B, int D, int H, int W, int depth_mode, const float *depth,
                                               const float *interval, const float *grad_depth, float *grad_score,
-                                              mvsb200_stream_t stream)
+                                              float *grad_hyp, mvsb200_stream_t stream)
 {
     MVSB200_REQUIRE(score && depth && grad_depth && grad_score, "depth_regress_backward: null pointer");
+    MVSB200_REQUIRE(!grad_hyp || depth_mode == MVSB200_DEPTH_VOLUME, "depth_regress_backward: grad_hyp needs per-voxel hypotheses (DEPTH_VOLUME)");
     MVSB200_REQUIRE(B > 0 && B <= 65535 && D > 0 && H > 0 && W > 0, "depth_regress_backward: bad shape B=%d D=%d H=%d W=%d", B, D, H, W);
     MVSB200_REQUIRE(depth_mode >= 0 && depth_mode <= 3, "depth_regress_backward: depth_mode=%d", depth_mode);
     MVSB200_REQUIRE(depth_mode < MVSB200_DEPTH_START || interval, "depth_regress_backward: interval is null");
     K3BwdParams p;
-    p.score = score; p.depth = depth; p.interval = interval; p.gdepth = grad_depth; p.gscore = grad_score;
+    p.score = score; p.depth = depth; p.interval = interval; p.gdepth = grad_depth; p.gscore = grad_score; p.ghyp = grad_hyp;
     p.B = B; p.D = D; p.depth_mode = depth_mode; p.HW = (long long)H * W;
     dim3 grid((unsigned)((p.HW + K3_PIX - 1) / K3_PIX), (unsigned)B);
     k3_depth_regress_backward_kernel<<<grid, K3_THREADS, 0, (cudaStream_t)stream>>>(p);

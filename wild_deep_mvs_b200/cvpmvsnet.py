@@ -111,8 +111,21 @@ class CostRegNet(nn.Module):
         del c5, c0
         return ops.conv3d(c6, pk["prob0"]).squeeze(-1)
 
+    def forward_modules(self, x):
+        """The same network through the PyTorch modules that own the parameters (net.py:76-85): training mode, where
+        BatchNorm uses batch statistics and autograd needs the layer graph."""
+        cbr = lambda m, v: F.relu(m.bn(m.conv(v)), inplace=True)
+        conv0 = cbr(self.conv0a, cbr(self.conv0, x))
+        conv2 = cbr(self.conv2a, cbr(self.conv2, cbr(self.conv1, conv0)))
+        conv4 = cbr(self.conv4a, cbr(self.conv4, cbr(self.conv3, conv2)))
+        conv5 = conv2 + self.conv5(conv4)
+        conv6 = conv0 + self.conv6(conv5)
+        return self.prob0(conv6).squeeze(1)
+
     def forward(self, x):
         """Reference signature: x [B,16,D,H,W] -> [B,D,H,W] (net.py:76-85)."""
+        if self.training or (torch.is_grad_enabled() and x.requires_grad):
+            return self.forward_modules(x)
         return self.run(ops.to_ndhwc(x))
 
 
@@ -204,10 +217,42 @@ class network(nn.Module):
             ests.append(depth)
         return ests, out["conf"], seams
 
+    def _forward_train(self, ref_img, src_imgs, ref_in, src_in, ref_ex, src_ex, depth_min, depth_max, nscale):
+        """Training path (net.py:96-229 with self.training): 48 initial hypotheses, refinement hypotheses at fixed
+        intervals halved per level (net.py:176-182) instead of calDepthHypo.  The cost volumes and the regression run on
+        K1 / K3 forward + backward (autograd Functions), the pyramid and the regulariser as PyTorch modules.  Gradients:
+        features and regulariser at every level, and through each level's hypotheses (built from the up-sampled depth
+        of the level before) into the coarser levels -- the sampling grids carry none (modules.py:88,242)."""
+        pyrs = [self.featurePyramid(im, nscale) for im in [ref_img] + list(src_imgs)]
+        ref_pyr, src_pyrs = pyrs[0], pyrs[1:]
+        S = len(src_pyrs)
+        ref_in_ms = condition_intrinsics(ref_in, ref_img.shape, [f.shape for f in ref_pyr])
+        src_in_ms = torch.stack([condition_intrinsics(src_in[:, i], ref_img.shape, [f.shape for f in src_pyrs[i]])
+                                 for i in range(S)]).permute(1, 0, 2, 3, 4)
+
+        def level_depth(level, hypos, last):
+            warp = ops.mvs_relative_proj(self._projs(ref_in_ms[:, level], ref_ex), self._projs(src_in_ms[:, :, level], src_ex))
+            vol = ops.cost_volume(ops.to_nhwc(ref_pyr[level]), [ops.to_nhwc(src_pyrs[v][level]) for v in range(S)], warp,
+                                  hypos.detach().contiguous(), hypos.shape[1], L.GEOM_MVS, L.AGG_VARIANCE_MEAN)
+            score = self.cost_reg_refine(ops.as_ncdhw(vol))
+            return ops.regress_depth(score, hypos.contiguous(), None, L.CONF_SUM4 if last else L.CONF_NONE)
+
+        hypos = sweeping_depth_hypos(depth_min, depth_max, 48).float()
+        depth, conf = level_depth(nscale - 1, hypos, nscale == 1)
+        ests = [depth]
+        for id_level, level in enumerate(range(nscale - 2, -1, -1)):
+            depth_up = F.interpolate(depth[None, :], size=None, scale_factor=2, mode="bicubic", align_corners=None).squeeze(0)
+            interval = (depth_max - depth_min) / 48 / 2 ** (id_level + 1)
+            hypos = torch.stack([depth_up + i * interval.view(-1, 1, 1) for i in range(-4, 4)], dim=1)
+            depth, conf = level_depth(level, hypos, level == 0)
+            ests.append(depth)
+        ests.reverse()
+        return {"depth_est_list": ests, "prob_confidence": conf}
+
     def forward(self, ref_img, src_imgs, ref_in, src_in, ref_ex, src_ex, depth_min, depth_max, **kwargs):
-        if self.training:
-            raise NotImplementedError("libmvsb200 implements inference only; call .eval() (SURVEY.md 8-f2)")
         nscale = kwargs["nscale"] if "nscale" in kwargs else self.nscale
+        if self.training:
+            return self._forward_train(ref_img, src_imgs, ref_in, src_in, ref_ex, src_ex, depth_min, depth_max, nscale)
         with torch.no_grad():
             pyrs = ops.map_views(lambda im: self.featurePyramid(im, nscale), [ref_img] + list(src_imgs))
             ref_pyr, src_pyrs = pyrs[0], pyrs[1:]

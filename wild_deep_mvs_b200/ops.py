@@ -451,8 +451,9 @@ def depth_regress(score, depth, interval=None, conf_mode=L.CONF_NONE, want_entro
     return out
 
 
-def depth_regress_backward(grad_depth, score, depth, interval=None):
-    """grad_score [B,D,H,W] of depth_regress()["depth"] (K3 backward, mvsb200_depth_regress_backward)."""
+def depth_regress_backward(grad_depth, score, depth, interval=None, want_grad_hyp=False):
+    """grad_score [B,D,H,W] of depth_regress()["depth"] (K3 backward, mvsb200_depth_regress_backward); with
+    `want_grad_hyp` (per-voxel hypotheses [B,D,H,W] only) -> (grad_score, grad_hypotheses)."""
     lib = L.load()
     score = _dev_f32(score, "score")
     B, D, H, W = score.shape
@@ -464,9 +465,10 @@ def depth_regress_backward(grad_depth, score, depth, interval=None):
     if grad_depth.numel() != B * H * W:
         raise L.Mvsb200Error("depth_regress_backward: grad_depth has shape %s" % (tuple(grad_depth.shape),))
     g = torch.empty_like(score)
+    gh = torch.empty_like(score) if want_grad_hyp else None
     L.check(lib.mvsb200_depth_regress_backward(_ptr(score), B, D, H, W, mode, _ptr(depth), _ptr(interval), _ptr(grad_depth),
-                                               _ptr(g), _stream()), "mvsb200_depth_regress_backward")
-    return g
+                                               _ptr(g), _ptr(gh), _stream()), "mvsb200_depth_regress_backward")
+    return (g, gh) if want_grad_hyp else g
 
 
 class _DepthRegressFn(torch.autograd.Function):
@@ -485,6 +487,11 @@ class _DepthRegressFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_depth, _g_conf):
         score, depth, interval = ctx.saved_tensors
+        if ctx.needs_input_grad[1]:    # per-voxel hypotheses that depend on an earlier depth map (CVP refinement levels)
+            if depth.dim() != 4 or interval is not None:
+                raise L.Mvsb200Error("regress_depth: only per-voxel hypotheses [B,D,H,W] can receive a gradient")
+            g, gh = depth_regress_backward(g_depth, score, depth, None, want_grad_hyp=True)
+            return g, gh, None, None
         return depth_regress_backward(g_depth, score, depth, interval), None, None, None
 
 
