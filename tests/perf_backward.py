@@ -1,7 +1,7 @@
 """K1 / K3 backward timings next to torch.autograd through the torch port on the same GPU (the existing Blackwell path of
 the reference: grid_sample forward + grid_sampler_2d_backward and the materialised per-view volumes).  GPU box only.
 
-    python profiles/bench_backward.py [out.json]
+    python tests/perf_backward.py [out.json]
 """
 import json
 import os
@@ -10,7 +10,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import torch_port as tp  # noqa: E402  (checker / baseline leg only)
+from oracle import torch_port as tp  # noqa: E402  (baseline leg; lives under tests/ because it times the oracle next to the kernels)
 from wild_deep_mvs_b200 import _lib as L, ops, synth  # noqa: E402
 from wild_deep_mvs_b200.mvsnet import build_proj_matrices  # noqa: E402
 
