@@ -13,7 +13,9 @@ tests/golden/backward.npz holds, on the inputs already stored in mvsnet_*.npz / 
   * the same for CVP-MVSNet with two pyramid levels (`cvp_train.npz`): training-mode hypotheses (net.py:126,176-182),
     loss on both levels, so the gradient also runs through the refinement level's hypotheses into the coarse level.
 
-    python tests/golden/make_golden_backward.py [cvp]      # `cvp`: only cvp_train.npz
+  * the same for Vis-MVSNet with a [8,4,4] cascade (`vis_train.npz`).
+
+    python tests/golden/make_golden_backward.py [cvp|vis]      # only cvp_train.npz / vis_train.npz
 """
 import os
 import sys
@@ -60,11 +62,67 @@ def cvp_train(ref):
     print("cvp_train.npz", os.path.getsize(os.path.join(OUT, "cvp_train.npz")) // 1024, "KiB")
 
 
+def vis_train(ref):
+    """Vis-MVSNet, training mode, cascade [8,4,4]: a loss over every output the reference's loss touches (stage depths,
+    pair depths weighted by their uncertainties, the uncertainties themselves, the probability map of the last stage)."""
+    # Shim 3 (training only): UncertNet.forward adds its input IN PLACE to the output of a ReLU (`out += x`,
+    # models/VisMVSNet/model_cas.py:96), which torch >= 1.5 refuses to differentiate (ReLU's backward needs that
+    # output; the pinned torch 1.4 let it pass).  The out-of-place form computes the same numbers.
+    import models.VisMVSNet.model_cas as model_cas
+
+    def uncert_forward(self, x):
+        out = self.conv2(self.conv1(x))
+        out = out + x
+        return [conv(out) for conv in self.head_convs]
+
+    model_cas.UncertNet.forward = uncert_forward
+    torch.manual_seed(0)
+    net = ref.VisFrontend()
+    synth.randomize_norm_stats(net, seed=2)
+    for st in (net.model.stage1, net.model.stage2, net.model.stage3):
+        synth.scale_param(st.reg_fuse.final_conv.weight, 30.0)
+        synth.scale_param(st.reg_pair.final_conv.weight, 30.0)
+    nums, scales = [8, 4, 4], [4, 2, 1]
+    net.depth_nums, net.interval_scales = nums, scales
+    sd = {k: v.detach().clone().numpy() for k, v in net.state_dict().items()}
+    net.train()
+    s = synth.make_sample(2, 3, 64, 80, seed=8)
+    res = net(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"], depth_nums=nums, interval_scales=scales)
+    gen = torch.Generator().manual_seed(9)
+    loss = 0
+    tr = {}
+    for k, e in enumerate(res["depth_est_list"]):
+        tgt = 500 + 300 * torch.rand(e.shape, generator=gen)
+        tr["target_%d" % k] = tgt.numpy()
+        tr["depth_est_%d" % k] = e.detach().numpy()
+        loss = loss + (e - tgt).abs().mean()
+        for v, (pd, heads) in enumerate(res["depth_pair_list"][k]):
+            u = heads[0]
+            loss = loss + ((pd.squeeze(1) - tgt).abs() * (-u.squeeze(1)).exp() + u.squeeze(1)).mean() * 0.5
+            tr["pair_depth_%d_%d" % (k, v)] = pd.detach().numpy()
+            tr["pair_uncert_%d_%d" % (k, v)] = u.detach().numpy()
+    loss = loss + res["photometric_confidence"][:, 2].mean()
+    loss.backward()
+    tr.update({"sd." + k: v for k, v in sd.items()})
+    tr.update({"conf": res["photometric_confidence"].detach().numpy(), "loss": np.float32(loss.item()), "seed": np.int32(8)})
+    params = dict(net.named_parameters())
+    for k in ("model.feat_ext.init_conv.0.weight", "model.feat_ext.final_conv_1.weight", "model.feat_ext.final_conv_3.weight",
+              "model.stage1.reg.unet.enc_blocks.reg14_0.0.conv1.weight", "model.stage1.uncert_net.conv1.0.weight",
+              "model.stage2.reg_fuse.final_conv.weight", "model.stage3.reg.unet.dec_blocks.reg116_2.1.weight",
+              "model.stage3.reg_pair.final_conv.weight", "model.stage3.uncert_net.head_convs.0.weight"):
+        tr["grad." + k] = params[k].grad.numpy()
+        print(k, "grad abs-max", float(params[k].grad.abs().max()))
+    np.savez_compressed(os.path.join(OUT, "vis_train.npz"), **tr)
+    print("vis_train.npz", os.path.getsize(os.path.join(OUT, "vis_train.npz")) // 1024, "KiB")
+
+
 def main():
     ref = import_reference()
     torch.set_num_threads(8)
     if sys.argv[1:] == ["cvp"]:
         return cvp_train(ref)
+    if sys.argv[1:] == ["vis"]:
+        return vis_train(ref)
     out = {}
 
     # ---- MVSNet cost volumes ---------------------------------------------------------------------------------------
@@ -150,6 +208,7 @@ def main():
     for f in ("backward.npz", "mvsnet_train.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
     cvp_train(ref)
+    vis_train(ref)
 
 
 if __name__ == "__main__":

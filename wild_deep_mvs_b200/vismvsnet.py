@@ -201,6 +201,13 @@ class _RegUNet(nn.Module):
             "post": ops.PackedConv(dec[1].weight, None),
         }
 
+    def forward(self, x):
+        """PyTorch execution (training: batch-statistics BatchNorm, autograd): UNet.forward, nn_utils.py:256-278."""
+        e0 = self.enc_blocks[self.tag + "4_0"](x)
+        e1 = self.enc_blocks[self.tag + "8_1"](e0)
+        dec = self.dec_blocks[self.tag + "16_2"]
+        return dec[1](torch.cat([dec[0](e1), e0], 1))
+
     @staticmethod
     def run(pk, x, am):
         """am: ops.AmaxPool -- abs-max scalars of the layer outputs (one fill for the whole stage)."""
@@ -238,6 +245,12 @@ class UncertNet(nn.Module):
         self.conv2 = nn.Sequential(nn.Conv2d(8, 8, 3, 1, 1, bias=False), nn.BatchNorm2d(8), nn.ReLU())
         self.head_convs = _Named([(0, nn.Conv2d(8, 1, 3, 1, 1, bias=False))])
 
+    def forward(self, x):
+        """PyTorch execution (training), model_cas.py:93-98."""
+        out = self.conv2(self.conv1(x))
+        out = out + x
+        return [conv(out) for conv in self.head_convs]
+
 
 class SingleStage(nn.Module):
     def __init__(self):
@@ -270,7 +283,7 @@ class SingleStage(nn.Module):
         """ref [B,H,W,32], srcs list of [B,Hs,Ws,32]; cams [B,2,4,4] / [B,S,2,4,4]; depth_start [B] or [B,H,W];
         depth_interval [B].  Returns est_depth [B,H,W], prob_map [B,H,W], pair list [(depth, uncert)]."""
         if self.training:
-            raise NotImplementedError("libmvsb200 implements inference only (SURVEY.md 8-f2)")
+            return self._run_train(ref, srcs, ref_cam, src_cams, depth_num, depth_start, depth_interval, s_scale)
         pk = self._pack()
         B, H, W, _ = ref.shape
         S = len(srcs)
@@ -299,6 +312,41 @@ class SingleStage(nn.Module):
         fscore = ops.conv3d(_RegUNet.run(pk["fuse"], fused, am), pk["fuse_head"]).squeeze(-1)
         out = ops.depth_regress(fscore, depth_start, interval=depth_interval, conf_mode=L.CONF_WINDOW)
         return out["depth"], out["conf"], pairs
+
+
+    def _run_train(self, ref, srcs, ref_cam, src_cams, depth_num, depth_start, depth_interval, s_scale):
+        """Training mode (SingleStage.forward with mode='soft', model_cas.py:303-420): the per-pair group-correlation
+        volumes come from K1 forward + backward (ops.cost_volume: no warped 32-channel volumes, no homography tensors),
+        everything downstream runs as the PyTorch modules / ops of the reference so that every output -- pair depths,
+        uncertainties, fused depth, probability map -- carries the reference's gradient."""
+        B, H, W, _ = ref.shape
+        S, D = len(srcs), depth_num
+        warp = ops.vis_homography_params(ref_cam, src_cams, 1.0 / s_scale)
+        cost = ops.cost_volume(ref, srcs, warp, depth_start.detach().contiguous(), D, L.GEOM_VIS, L.AGG_GROUPCORR,
+                               interval=depth_interval, groups=8)                      # [S,B,D,H,W,8]
+        start = depth_start.view(B, 1, 1, 1) if depth_start.dim() == 1 else depth_start.view(B, 1, H, W)
+        interval = depth_interval.view(B, 1, 1, 1)
+        index = torch.arange(D, dtype=ref.dtype, device=ref.device).view(1, D, 1, 1)
+
+        def soft_argmin(score):   # nn_utils.py:453-466
+            prob = torch.softmax(score, dim=1)
+            return prob, torch.sum(index * prob, dim=1, keepdim=True)
+
+        weight_sum, fused, pairs = 0, 0, []
+        for s in range(S):
+            interm = self.reg.unet(cost[s].permute(0, 4, 1, 2, 3))                      # [B,8,D,H,W]
+            prob, cls = soft_argmin(self.reg_pair.final_conv(interm).squeeze(1))
+            est = cls * interval + start
+            ent = torch.sum(-prob * prob.clamp(1e-9, 1.).log(), dim=1, keepdim=True)    # nn_utils.py:469-470
+            heads = self.uncert_net(ent)
+            pairs.append([est, heads])
+            weight = (-heads[0]).exp().unsqueeze(2)
+            weight_sum = weight_sum + weight
+            fused = fused + interm * weight
+        fused = fused / weight_sum
+        prob, cls = soft_argmin(self.reg_fuse.final_conv(self.reg_fuse.unet(fused)).squeeze(1))
+        prob_map = torch.sum(prob * ((index - cls).abs() <= 2).to(prob.dtype), dim=1)
+        return (cls * interval + start).squeeze(1), prob_map, pairs
 
 
 class Model(nn.Module):
@@ -366,7 +414,7 @@ class Frontend(nn.Module):
         for k, (stage, s_scale) in enumerate(zip(stages, (8, 4, 2))):
             ref = feats[0][k]
             if k > 0:
-                up = F.interpolate(ests[-1].unsqueeze(1), size=(ref.shape[1], ref.shape[2]), mode="bilinear",
+                up = F.interpolate(ests[-1].detach().unsqueeze(1), size=(ref.shape[1], ref.shape[2]), mode="bilinear",
                                    align_corners=False).squeeze(1)
                 # the reference reads self.interval_scales here, not the kwarg override (frontend.py:76-78)
                 start = (up - depth_nums[k] * depth_interval.view(-1, 1, 1) * self.interval_scales[k] / 2).contiguous()
@@ -385,8 +433,6 @@ class Frontend(nn.Module):
         return _GraphedCascade(self, feats, ref_cam, src_cams, depth_min, depth_interval, depth_nums, interval_scales)
 
     def forward(self, imgs, K, R, t, depth_min, depth_max, reference_frame=0, **kwargs):
-        if self.training:
-            raise NotImplementedError("libmvsb200 implements inference only; call .eval() (SURVEY.md 8-f2)")
         depth_interval = (depth_max - depth_min) / 128
         interval_scales = kwargs.get("interval_scales", self.interval_scales)
         depth_nums = kwargs.get("depth_nums", self.depth_nums)
@@ -394,13 +440,16 @@ class Frontend(nn.Module):
             imgs = list(torch.unbind(imgs, dim=1))
         v = len(imgs)
         src_idx = list(range(reference_frame)) + list(range(reference_frame + 1, v))
-        with torch.no_grad():
+        # training (row f2): autograd graph over K1 forward / backward + the reference's modules; one feature-extractor call
+        # per view (BatchNorm batch statistics are per call, frontend.py:59-62)
+        views = (lambda f, ims: [f(im) for im in ims]) if self.training else ops.map_views
+        with torch.enable_grad() if self.training else torch.no_grad():
             ref_cam = self.fill_cam_array(K[:, reference_frame], R[:, reference_frame], t[:, reference_frame],
                                           depth_min[:, reference_frame], depth_interval[:, reference_frame])
             src_cams = torch.stack([self.fill_cam_array(K[:, i], R[:, i], t[:, i], depth_min[:, i], depth_interval[:, i])
                                     for i in src_idx], 1)
             feats = [[ops.to_nhwc(f) for f in fv]
-                     for fv in ops.map_views(self.model.feat_ext, [imgs[i] for i in [reference_frame] + src_idx])]
+                     for fv in views(self.model.feat_ext, [imgs[i] for i in [reference_frame] + src_idx])]
             ests, probs, pairs = self.depth_from_features(feats, ref_cam, src_cams, depth_min[:, reference_frame],
                                                           depth_interval[:, reference_frame].contiguous(), depth_nums,
                                                           interval_scales)
