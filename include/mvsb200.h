@@ -199,6 +199,15 @@ MVSB200_API int mvsb200_conv3d_c1_supported(const mvsb200_conv3d_desc *desc);
 MVSB200_API int mvsb200_conv3d_c1(const mvsb200_conv3d_desc *desc, const float *x, const float *w_host, float scale, float bias,
                                   float *y, mvsb200_stream_t stream);
 
+/* Weight gradient of a 3x3x3 layer (training, row f2): R[ca][cb][27] += sum_v a[v,ca] * b[stride*v + tap - 1, cb], zero
+ * outside the volume.  Conv3d(k=3,p=1,stride): a = grad_out [B,Da,Ha,Wa,Cout], b = input [B,Db,Hb,Wb,Cin] -> R = dW
+ * [Cout,Cin,3,3,3]; ConvTranspose3d(k=3,p=1,stride,output_padding=stride-1): a = input, b = grad_out -> R = dW
+ * [Cin,Cout,3,3,3] (autograd of models/MVSNet/module.py:41-48, MVSNet/model.py:59-72, VisMVSNet/nn_utils.py:123-278,
+ * CVP net.py:50-74).  R must be ZEROED by the caller (blocks add partial sums).  The input gradient of the same layers is
+ * a forward call of mvsb200_conv3d_zm / mvsb200_conv3d with re-packed weights (no symbol of its own). */
+MVSB200_API int mvsb200_conv3d_wgrad(const float *a, const float *b, int B, int Da, int Ha, int Wa, int Ca, int Db, int Hb, int Wb,
+                                     int Cb, int stride, float *r, mvsb200_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * K3: softmax over D + depth regression + confidence (+ entropy, + probability volume).
  * Replaces F.softmax + depth_regression (+ photometric confidence): models/MVSNet/model.py:207-215,

@@ -67,7 +67,32 @@ def case(name, agg, V, D, H=128, W=160, C=32):
     return res
 
 
+def regulariser_step(D=48, H=128, W=160):
+    """Forward + backward of MVSNet's CostRegNet in training mode at the cfg1 volume: the PyTorch modules on cuDNN against
+    MVSB200_TRAIN_K2=lib (K2 engines forward / input gradient, mvsb200_conv3d_wgrad)."""
+    from wild_deep_mvs_b200.mvsnet import CostRegNet
+    torch.manual_seed(0)
+    net = CostRegNet().to(DEV).train()
+    x = torch.randn(1, D, H, W, 32, device=DEV).permute(0, 4, 1, 2, 3)      # channels-last volume, reference view [B,C,D,H,W]
+    res = {"case": "CostRegNet training step, volume %dx%dx%dx32" % (D, H, W)}
+    for name, env, tf32 in (("cudnn_tf32_ms", None, True), ("cudnn_fp32_ms", None, False), ("lib_ms", "lib", False)):
+        os.environ.pop("MVSB200_TRAIN_K2", None)
+        if env:
+            os.environ["MVSB200_TRAIN_K2"] = env
+        torch.backends.cudnn.allow_tf32 = tf32
+
+        def step():
+            net.zero_grad(set_to_none=True)
+            xi = x.detach().requires_grad_(True)
+            net(xi).square().mean().backward()
+        res[name] = round(timed(step, reps=3, warmup=2), 3)
+    os.environ.pop("MVSB200_TRAIN_K2", None)
+    print(json.dumps(res), flush=True)
+    return res
+
+
 if __name__ == "__main__":
-    out = [case("cfg1 MVSNet-s soft-min 1+2 views D=48", "softmin", 3, 48), case("cfg2 MVSNet variance 1+4 views D=192", "variance", 5, 192)]
+    out = [case("cfg1 MVSNet-s soft-min 1+2 views D=48", "softmin", 3, 48), case("cfg2 MVSNet variance 1+4 views D=192", "variance", 5, 192),
+           regulariser_step()]
     if len(sys.argv) > 1:
         json.dump(out, open(sys.argv[1], "w"), indent=1)

@@ -8,6 +8,7 @@ Tolerances: relative L-inf 1e-4 on gradients (fp32, atomics in arbitrary order; 
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from conftest import rel_linf
 
@@ -331,3 +332,71 @@ def test_backward_errors_are_loud():
         ops.build_cost_volume_backward(torch.zeros(1, 4, 8, 8, 16, device=DEV), ref, [ref], warp, dv, 4, L.GEOM_MVS, L.AGG_VARIANCE)
     with pytest.raises(L.Mvsb200Error):
         ops.depth_regress_backward(torch.zeros(1, 3, 3, device=DEV), torch.zeros(1, 4, 8, 8, device=DEV), dv)
+
+
+# ------------------------------------------------------------------------------------------------
+# K2 in training: forward + input gradient on the K2 engines, weight gradient on mvsb200_conv3d_wgrad
+# ------------------------------------------------------------------------------------------------
+K2_TRAIN_CASES = [
+    # cin, cout, stride, transposed, bias, input dims (D,H,W)
+    (32, 8, 1, False, False, (6, 10, 36)),
+    (8, 16, 2, False, False, (8, 12, 40)),
+    (16, 16, 1, False, False, (4, 9, 33)),
+    (64, 64, 1, False, False, (2, 5, 7)),
+    (16, 8, 2, True, False, (3, 5, 34)),
+    (64, 32, 2, True, False, (2, 3, 5)),
+    (64, 32, 1, True, False, (4, 6, 9)),      # CVP conv5: ConvTranspose3d with stride 1
+    (8, 1, 1, False, True, (6, 10, 36)),      # the `prob` head, with bias
+]
+
+
+@pytest.mark.parametrize("cin,cout,stride,transposed,bias,dims", K2_TRAIN_CASES)
+def test_k2_training_conv_against_torch_autograd(cin, cout, stride, transposed, bias, dims, monkeypatch):
+    """ops.conv3d_train (K2 engine forward, K2 engine input gradient with re-packed weights, wgrad kernel) against
+    torch.autograd through F.conv3d / F.conv_transpose3d in fp32 -- the calls the reference's modules make."""
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    gen = torch.Generator().manual_seed(cin + cout + stride)
+    B = 2
+    x = torch.randn(B, cin, *dims, generator=gen).to(DEV)
+    w = (torch.randn((cin, cout, 3, 3, 3) if transposed else (cout, cin, 3, 3, 3), generator=gen) / (cin * 27) ** 0.5).to(DEV)
+    b = torch.randn(cout, generator=gen).to(DEV) if bias else None
+    x1, w1 = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    b1 = b.clone().requires_grad_(True) if bias else None
+    y1 = F.conv_transpose3d(x1, w1, b1, stride, 1, stride - 1) if transposed else F.conv3d(x1, w1, b1, stride, 1)
+    G = torch.randn(y1.shape, generator=torch.Generator().manual_seed(1)).to(DEV)
+    (y1 * G).sum().backward()
+    x2, w2 = ops.to_ndhwc(x).requires_grad_(True), w.clone().requires_grad_(True)
+    b2 = b.clone().requires_grad_(True) if bias else None
+    y2 = ops.conv3d_train(x2, w2, b2, stride, transposed)
+    assert rel_linf(ops.as_ncdhw(y2).detach().cpu().numpy(), y1.detach().cpu().numpy()) < 2e-5
+    (ops.as_ncdhw(y2) * G).sum().backward()
+    assert rel_linf(ops.as_ncdhw(x2.grad).cpu().numpy(), x1.grad.cpu().numpy()) < 2e-5
+    assert rel_linf(w2.grad.cpu().numpy(), w1.grad.cpu().numpy()) < 2e-5
+    if bias:
+        assert rel_linf(b2.grad.cpu().numpy(), b1.grad.cpu().numpy()) < 2e-5
+
+
+def test_mvsnet_training_step_with_the_regulariser_on_the_library(golden, monkeypatch):
+    """The MVSNet-s training step of test_mvsnet_training_step_matches_the_reference with MVSB200_TRAIN_K2=lib: every
+    3x3x3 layer of the regulariser forward and backward on the library (K2 engines + wgrad kernel)."""
+    monkeypatch.setenv("MVSB200_TRAIN_K2", "lib")
+    g = golden("mvsnet_train")
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    net = MVSNet("softmin")
+    net.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}, strict=True)
+    net.num_depth = 8
+    net = net.to(DEV).train()
+    s = {k: v.to(DEV) for k, v in synth.make_sample(2, 3, 64, 96, seed=int(g["seed"])).items()}
+    out = net(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"])
+    err = np.abs(out["depth"].detach().cpu().numpy() - g["depth"]) / np.abs(g["depth"]).max()
+    assert err.max() < 1e-3
+    loss = (out["depth"] - cu(g["target"])).abs().mean()
+    loss.backward()
+    params = dict(net.named_parameters())
+    for k in [k[5:] for k in g if k.startswith("grad.")]:
+        want = g["grad." + k]
+        if np.abs(want).max() < 1e-5:
+            continue
+        e = rel_linf(params[k].grad.cpu().numpy(), want)
+        print(k, "grad rel err %.2e" % e)
+        assert e < (1e-2 if k == "temp" else 1e-3), k

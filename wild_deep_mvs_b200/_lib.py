@@ -52,6 +52,7 @@ SIGNATURES = {
     "mvsb200_build_cost_volume": (_i, [ctypes.POINTER(CostVolumeDesc), _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvsb200_build_cost_volume_backward": (_i, [ctypes.POINTER(CostVolumeDesc), _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp,
                                                 ctypes.POINTER(_vp), _vp, _vp]),
+    "mvsb200_conv3d_wgrad": (_i, [_vp, _vp] + [_i] * 10 + [_vp, _vp]),
     "mvsb200_depth_regress_backward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvsb200_conv3d_out_shape": (_i, [ctypes.POINTER(Conv3dDesc)] + [ctypes.POINTER(_i)] * 3),
     "mvsb200_conv3d": (_i, [ctypes.POINTER(Conv3dDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -15,6 +15,8 @@ backward (K1 / K3 backward kernels behind torch.autograd.Function, ops.cost_volu
 regulariser and the 2-D FeatureNet run as the PyTorch modules that own the parameters (batch-statistics BatchNorm,
 cuDNN dgrad / wgrad) -- a K2 backward is the part of f2 not built yet.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -138,18 +140,34 @@ class CostRegNet(nn.Module):
 
     def forward_modules(self, x):
         """The same network through the PyTorch modules that own the parameters (models/MVSNet/model.py:74-84):
-        training mode, where BatchNorm uses batch statistics and autograd needs the layer graph."""
+        training mode, where BatchNorm uses batch statistics and autograd needs the layer graph.  The convolutions run
+        on cuDNN by default; with MVSB200_TRAIN_K2=lib they run on the library forward AND backward (ops.conv3d_train:
+        K2 engines for the layer and its input gradient, mvsb200_conv3d_wgrad for the weight gradient), BatchNorm / ReLU
+        stay PyTorch ops on the channels-last volumes."""
+        lib = os.environ.get("MVSB200_TRAIN_K2") == "lib" and x.is_cuda
+
+        def conv(v, weight, bias=None, stride=1, transposed=False):
+            if lib:
+                return ops.as_ncdhw(ops.conv3d_train(ops.to_ndhwc(v), weight, bias, stride, transposed))
+            if transposed:
+                return F.conv_transpose3d(v, weight, bias, stride, 1, stride - 1)
+            return F.conv3d(v, weight, bias, stride, 1)
+
         def cbr(name, v):   # the modules hold the parameters; the stride-2 layers are listed in _STRIDES
             m = getattr(self, name)
-            return F.relu(m.bn(F.conv3d(v, m.conv.weight, None, self._STRIDES.get(name, 1), 1)), inplace=True)
+            return F.relu(m.bn(conv(v, m.conv.weight, None, self._STRIDES.get(name, 1))), inplace=True)
+
+        def dbr(m, v):
+            return m[2](m[1](conv(v, m[0].weight, None, 2, True)))
+
         conv0 = cbr("conv0", x)
         conv2 = cbr("conv2", cbr("conv1", conv0))
         conv4 = cbr("conv4", cbr("conv3", conv2))
         x = cbr("conv6", cbr("conv5", conv4))
-        x = conv4 + self.conv7(x)
-        x = conv2 + self.conv9(x)
-        x = conv0 + self.conv11(x)
-        return self.prob(x)
+        x = conv4 + dbr(self.conv7, x)
+        x = conv2 + dbr(self.conv9, x)
+        x = conv0 + dbr(self.conv11, x)
+        return conv(x, self.prob.weight, self.prob.bias)
 
     def forward(self, x, down_ft=None):
         """Reference signature: x [B,32,D,H,W] -> [B,1,D,H,W] (models/MVSNet/model.py:74-84)."""

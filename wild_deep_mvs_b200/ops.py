@@ -430,6 +430,68 @@ def conv3d(x, layer, x2=None, skip=None, engine=None, out=None, amax=None):
     return y
 
 
+# ---- K2 in training (row f2): forward and input gradient on the K2 engines, weight gradient on mvsb200_conv3d_wgrad ----
+def conv3d_wgrad(a, b, stride):
+    """R[ca][cb][3,3,3] = sum_v a[v,ca] * b[stride*v + tap - 1, cb]   (a [B,Da,Ha,Wa,Ca] the low-resolution side, b
+    [B,Db,Hb,Wb,Cb] the high-resolution side).  Conv3d: a = grad_out, b = input -> dW [Cout,Cin,3,3,3];
+    ConvTranspose3d: a = input, b = grad_out -> dW [Cin,Cout,3,3,3]."""
+    a, b = _dev_f32(a.contiguous(), "a"), _dev_f32(b.contiguous(), "b")
+    B, Da, Ha, Wa, Ca = a.shape
+    Bb, Db, Hb, Wb, Cb = b.shape
+    if B != Bb:
+        raise L.Mvsb200Error("conv3d_wgrad: batch sizes %d and %d" % (B, Bb))
+    r = torch.zeros(Ca, Cb, 3, 3, 3, device=a.device, dtype=torch.float32)
+    L.check(L.load().mvsb200_conv3d_wgrad(_ptr(a), _ptr(b), B, Da, Ha, Wa, Ca, Db, Hb, Wb, Cb, stride, _ptr(r), _stream()),
+            "mvsb200_conv3d_wgrad")
+    return r
+
+
+def conv3d_input_grad(grad_out, weight, stride, transposed):
+    """Input gradient of a 3x3x3 layer as a FORWARD call of the K2 engines with the weights re-packed:
+      Conv3d stride 1            -> conv with the kernel flipped and the channel axes swapped
+      Conv3d stride 2            -> ConvTranspose3d(stride 2, output_padding 1) with the same weight tensor
+      ConvTranspose3d stride 1/2 -> Conv3d of that stride with the same weight tensor ([Cin,Cout] read as [out,in])
+    grad_out [B,Do,Ho,Wo,Cout_of_the_layer] channels-last; weight in its nn.Module layout."""
+    w = weight.detach()
+    if transposed:
+        layer = PackedConv(w, None, stride=stride)
+    elif stride == 1:
+        layer = PackedConv(w.flip(2, 3, 4).transpose(0, 1), None)
+    else:
+        layer = PackedConv(w, None, stride=stride, transposed=True)
+    return conv3d(grad_out.contiguous(), layer)
+
+
+class _Conv3dFn(torch.autograd.Function):
+    """A 3x3x3 Conv3d / ConvTranspose3d (+ bias) of the regularisers as a differentiable op on channels-last volumes:
+    forward and input gradient on the K2 engines (tcgen05), weight gradient on the wgrad kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, transposed):
+        x = x.contiguous()
+        y = conv3d(x, PackedConv(weight, None, conv_bias=bias, stride=stride, transposed=transposed))
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (stride, transposed, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        stride, transposed, has_bias = ctx.cfg
+        gy = gy.contiguous()
+        gx = conv3d_input_grad(gy, weight, stride, transposed) if ctx.needs_input_grad[0] else None
+        gw = None
+        if ctx.needs_input_grad[1]:
+            gw = conv3d_wgrad(x, gy, stride) if transposed else conv3d_wgrad(gy, x, stride)
+        gb = gy.sum(dim=(0, 1, 2, 3)) if has_bias and ctx.needs_input_grad[2] else None
+        return gx, gw, gb, None, None
+
+
+def conv3d_train(x, weight, bias=None, stride=1, transposed=False):
+    """Differentiable 3x3x3 conv on a channels-last volume x [B,D,H,W,Cin] (training, row f2) -> [B,Do,Ho,Wo,Cout]."""
+    return _Conv3dFn.apply(x, weight, bias, stride, transposed)
+
+
 # ------------------------------------------------------------------------------------------------
 # K3 / K4
 # ------------------------------------------------------------------------------------------------
