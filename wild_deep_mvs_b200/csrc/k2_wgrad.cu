@@ -8,39 +8,57 @@
 //                                                                  a = input,    b = grad_out -> R = dW
 // (autograd of models/MVSNet/module.py:41-48, MVSNet/model.py:59-72, VisMVSNet/nn_utils.py:123-278, CVP net.py:50-74).
 //
-// First version, on the CUDA cores in fp32: a block owns an 8 x 32 tile of (ca, cb) pairs -- one pair per thread, 27
-// tap accumulators in registers -- and walks rows (b, z, y) of `a`; the row of `a` and the nine rows of `b` it touches
-// are staged in shared memory in x segments, so a warp reads 32 consecutive cb of one staged position (conflict free)
-// and one broadcast value of `a` per FMA group.  Blocks add their partial sums into R with atomics (R zeroed by the
-// caller).  The dgrad of the same layers needs no kernel of its own: it is a forward call of the K2 engines with the
-// weights re-packed (ops.conv3d_input_grad).
+// On the CUDA cores in fp32.  A thread owns NCA channels of `a`, one channel of `b` and all 27 taps (27 * NCA accumulators
+// in registers): per staged x position it reads 27 values of `b` and NCA values of `a` from shared memory for 27 * NCA
+// FMAs (one pair per thread is bound 4 : 1 by shared-memory reads; NCA = 2 halves that and still fits two blocks per SM).  The 256 threads of a block split into (x lanes) x (groups of NCA `a`
+// channels) x (lanes over the `b` channels); the split is chosen per layer so that layers with few channel pairs (the
+// 8 -> 1 head, 32 -> 8) spread over x instead of idling.  A block walks rows (b, z, y) of `a`; the row of `a` and the
+// nine rows of `b` it touches are staged in x segments.  Blocks add their partial sums into R with atomics (R zeroed
+// by the caller).  The dgrad of the same layers needs no kernel of its own: it is a forward call of the K2 engines
+// with the weights re-packed (ops.conv3d_input_grad).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace mvsb200 {
 
-constexpr int WG_CA = 8, WG_CB = 32, WG_THREADS = WG_CA * WG_CB;
+constexpr int WG_THREADS = 256, WG_CAT = 32, WG_CBL = 32;   // largest channel tile of a block: 32 (a) x 32 (b)
 
 struct WgradParams {
     const float *a, *b;
     float *r;
-    int B, Da, Ha, Wa, Db, Hb, Wb, Ca, Cb, stride;
+    int B, Da, Ha, Wa, Db, Hb, Wb, Ca, Cb;
+    int cbl, cag, xl;          // lanes over b channels, groups of NCA a channels, x lanes: cbl * cag * xl == 256
+    int cbl_sh, cat_sh;        // log2(cbl), log2(cag * NCA): every split is a power of two, index arithmetic by shifts
     int tiles_a, tiles_b;
     long long rows;
 };
 
-template <int S>
+// 4-byte asynchronous copy into shared memory, zero filled when !valid: the staging phase keeps dozens of loads per
+// thread in flight without holding registers (the register-tiled kernel runs at one block per SM)
+__device__ __forceinline__ void wg_cp_async4(float *smem, const float *gmem, bool valid)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gmem), "r"(bytes) : "memory");
+}
+
+template <int S, int NCA>
 __global__ void __launch_bounds__(WG_THREADS) k2_wgrad_kernel(const WgradParams p)
 {
     constexpr int WG_XS = S == 1 ? 32 : 16;              // x positions of `a` per staged segment (38 KB of b either way)
     constexpr int XB = S * (WG_XS - 1) + 3;              // staged x extent of `b` for one segment
-    __shared__ float s_a[WG_XS][WG_CA];
-    __shared__ float s_b[9][XB][WG_CB];
+    __shared__ float s_a[WG_XS * WG_CAT];                // [x][cat]
+    __shared__ float s_b[9 * XB * WG_CBL];               // [(dz,dy)][x][cbl], compact in cbl
+    const int cbl = p.cbl, cat = p.cag * NCA;
     const int ta = blockIdx.y % p.tiles_a, tb = blockIdx.y / p.tiles_a;
-    const int ca0 = ta * WG_CA, cb0 = tb * WG_CB;
-    const int la = threadIdx.x / WG_CB, lb = threadIdx.x % WG_CB;
-    float acc[27];
+    const int ca0 = ta * cat, cb0 = tb * cbl;
+    const int csh = p.cbl_sh, ash = p.cat_sh;
+    const int lb = threadIdx.x & (cbl - 1), g = (threadIdx.x >> csh) & (p.cag - 1), xlane = threadIdx.x / (cbl * p.cag);
+    float acc[NCA][27];
 #pragma unroll
-    for (int t = 0; t < 27; t++) acc[t] = 0.f;
+    for (int j = 0; j < NCA; j++)
+#pragma unroll
+        for (int t = 0; t < 27; t++) acc[j][t] = 0.f;
 
     for (long long row = blockIdx.x; row < p.rows; row += gridDim.x) {
         const int ya = (int)(row % p.Ha);
@@ -49,37 +67,46 @@ __global__ void __launch_bounds__(WG_THREADS) k2_wgrad_kernel(const WgradParams 
         for (int x0 = 0; x0 < p.Wa; x0 += WG_XS) {
             __syncthreads();
             // stage a[bb, za, ya, x0 .. x0+XS) for the tile's channels (zero beyond the row / the channel count)
-            for (int i = threadIdx.x; i < WG_XS * WG_CA; i += WG_THREADS) {
-                const int c = i % WG_CA, x = i / WG_CA;
-                float v = 0.f;
-                if (x0 + x < p.Wa && ca0 + c < p.Ca)
-                    v = __ldg(p.a + ((((long long)bb * p.Da + za) * p.Ha + ya) * p.Wa + x0 + x) * p.Ca + ca0 + c);
-                s_a[x][c] = v;
+            for (int i = threadIdx.x; i < WG_XS * cat; i += WG_THREADS) {
+                const int c = i & (cat - 1), x = i >> ash;
+                const bool ok = x0 + x < p.Wa && ca0 + c < p.Ca;
+                wg_cp_async4(&s_a[x * cat + c], ok ? p.a + ((((long long)bb * p.Da + za) * p.Ha + ya) * p.Wa + x0 + x) * p.Ca + ca0 + c : p.a, ok);
             }
             // stage the nine (dz, dy) rows of b, x from S*x0 - 1
-            for (int i = threadIdx.x; i < 9 * XB * WG_CB; i += WG_THREADS) {
-                const int c = i % WG_CB, x = (i / WG_CB) % XB, rr = i / (WG_CB * XB);
+            for (int i = threadIdx.x; i < 9 * XB * cbl; i += WG_THREADS) {
+                const int c = i & (cbl - 1), x = (i >> csh) % XB, rr = (i >> csh) / XB;
                 const int zb = S * za + rr / 3 - 1, yb = S * ya + rr % 3 - 1, xb = S * x0 - 1 + x;
-                float v = 0.f;
-                if ((unsigned)zb < (unsigned)p.Db && (unsigned)yb < (unsigned)p.Hb && (unsigned)xb < (unsigned)p.Wb && cb0 + c < p.Cb)
-                    v = __ldg(p.b + ((((long long)bb * p.Db + zb) * p.Hb + yb) * p.Wb + xb) * p.Cb + cb0 + c);
-                s_b[rr][x][c] = v;
+                const bool ok = (unsigned)zb < (unsigned)p.Db && (unsigned)yb < (unsigned)p.Hb && (unsigned)xb < (unsigned)p.Wb && cb0 + c < p.Cb;
+                wg_cp_async4(&s_b[i], ok ? p.b + ((((long long)bb * p.Db + zb) * p.Hb + yb) * p.Wb + xb) * p.Cb + cb0 + c : p.b, ok);
             }
+            asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
             const int nx = min(WG_XS, p.Wa - x0);
-            for (int x = 0; x < nx; x++) {
-                const float av = s_a[x][la];
+            for (int x = xlane; x < nx; x += p.xl) {
+                float av[NCA];
+#pragma unroll
+                for (int j = 0; j < NCA; j++) av[j] = s_a[x * cat + g * NCA + j];
+                const float *sb = s_b + (S * x) * cbl + lb;
 #pragma unroll
                 for (int rr = 0; rr < 9; rr++)
 #pragma unroll
-                    for (int dx = 0; dx < 3; dx++) acc[rr * 3 + dx] = fmaf(av, s_b[rr][S * x + dx][lb], acc[rr * 3 + dx]);
+                    for (int dx = 0; dx < 3; dx++) {
+                        const float bv = sb[(rr * XB + dx) * cbl];
+#pragma unroll
+                        for (int j = 0; j < NCA; j++) acc[j][rr * 3 + dx] = fmaf(av[j], bv, acc[j][rr * 3 + dx]);
+                    }
             }
         }
     }
-    if (ca0 + la < p.Ca && cb0 + lb < p.Cb) {
-        float *dst = p.r + ((long long)(ca0 + la) * p.Cb + cb0 + lb) * 27;
+    if (cb0 + lb < p.Cb) {
 #pragma unroll
-        for (int t = 0; t < 27; t++) atomicAdd(dst + t, acc[t]);
+        for (int j = 0; j < NCA; j++) {
+            const int ca = ca0 + g * NCA + j;
+            if (ca >= p.Ca) continue;
+            float *dst = p.r + ((long long)ca * p.Cb + cb0 + lb) * 27;
+#pragma unroll
+            for (int t = 0; t < 27; t++) atomicAdd(dst + t, acc[j][t]);
+        }
     }
 }
 
@@ -98,17 +125,36 @@ extern "C" int mvsb200_conv3d_wgrad(const float *a, const float *b, int B, int D
                     "conv3d_wgrad: a is %dx%dx%d, b is %dx%dx%d, stride %d", Da, Ha, Wa, Db, Hb, Wb, stride);
     WgradParams p;
     p.a = a; p.b = b; p.r = r;
-    p.B = B; p.Da = Da; p.Ha = Ha; p.Wa = Wa; p.Db = Db; p.Hb = Hb; p.Wb = Wb; p.Ca = Ca; p.Cb = Cb; p.stride = stride;
-    p.tiles_a = (Ca + WG_CA - 1) / WG_CA;
-    p.tiles_b = (Cb + WG_CB - 1) / WG_CB;
+    p.B = B; p.Da = Da; p.Ha = Ha; p.Wa = Wa; p.Db = Db; p.Hb = Hb; p.Wb = Wb; p.Ca = Ca; p.Cb = Cb;
+    // thread split: lanes over b channels (8, 16 or 32), groups of NCA a channels (tile of at most 32), the rest over x
+    // NCA = 2 measured best on B200 (two blocks per SM overlap staging and FMAs; NCA = 4 runs one block of 156 registers
+    // per SM and waits on its own staging): conv0 of MVSNet at the cfg1 volume 1.47 ms against 1.84 (NCA = 4), 1.33 (NCA = 1)
+    int nca = Ca >= 2 ? 2 : 1;
+    if (const char *e = getenv("MVSB200_WG_NCA")) { const int v = atoi(e); if ((v == 2 || v == 4) && Ca >= v) nca = v; }
+    p.cbl = Cb <= 8 ? 8 : Cb <= 16 ? 16 : 32;
+    int cag = (Ca + nca - 1) / nca;
+    if (cag > WG_CAT / nca) cag = WG_CAT / nca;
+    while (cag & (cag - 1)) cag++;                       // power of two, so that the split divides 256
+    if (cag * p.cbl > WG_THREADS) cag = WG_THREADS / p.cbl;
+    p.cag = cag;
+    p.xl = WG_THREADS / (p.cbl * p.cag);
+    p.cbl_sh = p.cbl == 8 ? 3 : p.cbl == 16 ? 4 : 5;
+    p.cat_sh = 0;
+    while ((1 << p.cat_sh) < cag * nca) p.cat_sh++;
+    p.tiles_a = (Ca + cag * nca - 1) / (cag * nca);
+    p.tiles_b = (Cb + p.cbl - 1) / p.cbl;
     p.rows = (long long)B * Da * Ha;
     const int ctiles = p.tiles_a * p.tiles_b;
-    long long gx = (148ll * 4 + ctiles - 1) / ctiles;      // about four blocks per SM over all channel tiles
+    long long gx = (148ll * (nca == 1 ? 2 : 4) + ctiles - 1) / ctiles;      // two to four blocks per SM over all channel tiles
     if (gx > p.rows) gx = p.rows;
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, (unsigned)ctiles);
     cudaStream_t st = (cudaStream_t)stream;
-    if (stride == 1) k2_wgrad_kernel<1><<<grid, WG_THREADS, 0, st>>>(p);
-    else k2_wgrad_kernel<2><<<grid, WG_THREADS, 0, st>>>(p);
+    if (stride == 1 && nca == 4) k2_wgrad_kernel<1, 4><<<grid, WG_THREADS, 0, st>>>(p);
+    else if (stride == 1 && nca == 2) k2_wgrad_kernel<1, 2><<<grid, WG_THREADS, 0, st>>>(p);
+    else if (stride == 1) k2_wgrad_kernel<1, 1><<<grid, WG_THREADS, 0, st>>>(p);
+    else if (nca == 4) k2_wgrad_kernel<2, 4><<<grid, WG_THREADS, 0, st>>>(p);
+    else if (nca == 2) k2_wgrad_kernel<2, 2><<<grid, WG_THREADS, 0, st>>>(p);
+    else k2_wgrad_kernel<2, 1><<<grid, WG_THREADS, 0, st>>>(p);
     return check_launch("k2_wgrad_kernel");
 }
