@@ -13,7 +13,7 @@
 // FMAs (one pair per thread is bound 4 : 1 by shared-memory reads; NCA = 2 halves that and still fits two blocks per SM).  The 256 threads of a block split into (x lanes) x (groups of NCA `a`
 // channels) x (lanes over the `b` channels); the split is chosen per layer so that layers with few channel pairs (the
 // 8 -> 1 head, 32 -> 8) spread over x instead of idling.  A block walks rows (b, z, y) of `a`; the row of `a` and the
-// nine rows of `b` it touches are staged in x segments.  Blocks add their partial sums into R with atomics (R zeroed
+// nine rows of `b` it touches are staged in x segments, double buffered with cp.async (segment q + 1 lands while q is consumed).  Blocks add their partial sums into R with atomics (R zeroed
 // by the caller).  The dgrad of the same layers needs no kernel of its own: it is a forward call of the K2 engines
 // with the weights re-packed (ops.conv3d_input_grad).
 #include "common.cuh"
@@ -28,6 +28,7 @@ struct WgradParams {
     float *r;
     int B, Da, Ha, Wa, Db, Hb, Wb, Ca, Cb;
     int cbl, cag, xl;          // lanes over b channels, groups of NCA a channels, x lanes: cbl * cag * xl == 256
+    int b_vec4;                // Cb % 4 == 0 and b 16-byte aligned: stage b in 16-byte pieces
     int cbl_sh, cat_sh;        // log2(cbl), log2(cag * NCA): every split is a power of two, index arithmetic by shifts
     int tiles_a, tiles_b;
     long long rows;
@@ -42,13 +43,25 @@ __device__ __forceinline__ void wg_cp_async4(float *smem, const float *gmem, boo
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gmem), "r"(bytes) : "memory");
 }
 
+__device__ __forceinline__ void wg_cp_async16(float *smem, const float *gmem, bool valid)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(bytes) : "memory");
+}
+
+template <int S> struct WgTile {
+    static constexpr int XS = S == 1 ? 32 : 16;          // x positions of `a` per staged segment (38 KB of b either way)
+    static constexpr int XB = S * (XS - 1) + 3;          // staged x extent of `b` for one segment
+    static constexpr int SA = XS * WG_CAT, SB = 9 * XB * WG_CBL;     // floats per buffer: a [x][cat], b [(dz,dy)][x][cbl]
+    static constexpr size_t SMEM = (size_t)2 * (SA + SB) * sizeof(float);
+};
+
 template <int S, int NCA>
 __global__ void __launch_bounds__(WG_THREADS) k2_wgrad_kernel(const WgradParams p)
 {
-    constexpr int WG_XS = S == 1 ? 32 : 16;              // x positions of `a` per staged segment (38 KB of b either way)
-    constexpr int XB = S * (WG_XS - 1) + 3;              // staged x extent of `b` for one segment
-    __shared__ float s_a[WG_XS * WG_CAT];                // [x][cat]
-    __shared__ float s_b[9 * XB * WG_CBL];               // [(dz,dy)][x][cbl], compact in cbl
+    constexpr int WG_XS = WgTile<S>::XS, XB = WgTile<S>::XB, SA = WgTile<S>::SA, SB = WgTile<S>::SB;
+    extern __shared__ __align__(16) float wg_smem[];     // two buffers: segment q + 1 is staged while segment q is consumed
     const int cbl = p.cbl, cat = p.cag * NCA;
     const int ta = blockIdx.y % p.tiles_a, tb = blockIdx.y / p.tiles_a;
     const int ca0 = ta * cat, cb0 = tb * cbl;
@@ -60,43 +73,66 @@ __global__ void __launch_bounds__(WG_THREADS) k2_wgrad_kernel(const WgradParams 
 #pragma unroll
         for (int t = 0; t < 27; t++) acc[j][t] = 0.f;
 
-    for (long long row = blockIdx.x; row < p.rows; row += gridDim.x) {
+    const int nsx = (p.Wa + WG_XS - 1) / WG_XS;
+    const long long my_rows = blockIdx.x < p.rows ? (p.rows - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long nseg = my_rows * nsx;
+
+    // stage segment q (row blockIdx.x + (q / nsx) * gridDim.x, x from (q % nsx) * XS) into buffer buf
+    auto stage = [&](long long q, int buf) {
+        const long long row = blockIdx.x + (q / nsx) * gridDim.x;
+        const int x0 = (int)(q % nsx) * WG_XS;
         const int ya = (int)(row % p.Ha);
         const int za = (int)((row / p.Ha) % p.Da);
         const int bb = (int)(row / ((long long)p.Ha * p.Da));
-        for (int x0 = 0; x0 < p.Wa; x0 += WG_XS) {
-            __syncthreads();
-            // stage a[bb, za, ya, x0 .. x0+XS) for the tile's channels (zero beyond the row / the channel count)
-            for (int i = threadIdx.x; i < WG_XS * cat; i += WG_THREADS) {
-                const int c = i & (cat - 1), x = i >> ash;
-                const bool ok = x0 + x < p.Wa && ca0 + c < p.Ca;
-                wg_cp_async4(&s_a[x * cat + c], ok ? p.a + ((((long long)bb * p.Da + za) * p.Ha + ya) * p.Wa + x0 + x) * p.Ca + ca0 + c : p.a, ok);
+        float *s_a = wg_smem + buf * (SA + SB), *s_b = s_a + SA;
+        for (int i = threadIdx.x; i < WG_XS * cat; i += WG_THREADS) {      // a[bb, za, ya, x0 .. x0+XS), the tile's channels
+            const int c = i & (cat - 1), x = i >> ash;
+            const bool ok = x0 + x < p.Wa && ca0 + c < p.Ca;
+            wg_cp_async4(&s_a[x * cat + c], ok ? p.a + ((((long long)bb * p.Da + za) * p.Ha + ya) * p.Wa + x0 + x) * p.Ca + ca0 + c : p.a, ok);
+        }
+        if (p.b_vec4) {      // Cb % 4 == 0: 16-byte pieces (4 channels), a quarter of the copies and of their index arithmetic
+            const int q4 = cbl >> 2, qsh = csh - 2;
+            for (int i = threadIdx.x; i < 9 * XB * q4; i += WG_THREADS) {
+                const int c = (i & (q4 - 1)) << 2, x = (i >> qsh) % XB, rr = (i >> qsh) / XB;
+                const int zb = S * za + rr / 3 - 1, yb = S * ya + rr % 3 - 1, xb = S * x0 - 1 + x;
+                const bool ok = (unsigned)zb < (unsigned)p.Db && (unsigned)yb < (unsigned)p.Hb && (unsigned)xb < (unsigned)p.Wb && cb0 + c < p.Cb;
+                wg_cp_async16(&s_b[(rr * XB + x) * cbl + c], ok ? p.b + ((((long long)bb * p.Db + zb) * p.Hb + yb) * p.Wb + xb) * p.Cb + cb0 + c : p.b, ok);
             }
-            // stage the nine (dz, dy) rows of b, x from S*x0 - 1
-            for (int i = threadIdx.x; i < 9 * XB * cbl; i += WG_THREADS) {
+        } else {
+            for (int i = threadIdx.x; i < 9 * XB * cbl; i += WG_THREADS) {     // the nine (dz, dy) rows of b, x from S*x0 - 1
                 const int c = i & (cbl - 1), x = (i >> csh) % XB, rr = (i >> csh) / XB;
                 const int zb = S * za + rr / 3 - 1, yb = S * ya + rr % 3 - 1, xb = S * x0 - 1 + x;
                 const bool ok = (unsigned)zb < (unsigned)p.Db && (unsigned)yb < (unsigned)p.Hb && (unsigned)xb < (unsigned)p.Wb && cb0 + c < p.Cb;
                 wg_cp_async4(&s_b[i], ok ? p.b + ((((long long)bb * p.Db + zb) * p.Hb + yb) * p.Wb + xb) * p.Cb + cb0 + c : p.b, ok);
             }
-            asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
-            __syncthreads();
-            const int nx = min(WG_XS, p.Wa - x0);
-            for (int x = xlane; x < nx; x += p.xl) {
-                float av[NCA];
-#pragma unroll
-                for (int j = 0; j < NCA; j++) av[j] = s_a[x * cat + g * NCA + j];
-                const float *sb = s_b + (S * x) * cbl + lb;
-#pragma unroll
-                for (int rr = 0; rr < 9; rr++)
-#pragma unroll
-                    for (int dx = 0; dx < 3; dx++) {
-                        const float bv = sb[(rr * XB + dx) * cbl];
-#pragma unroll
-                        for (int j = 0; j < NCA; j++) acc[j][rr * 3 + dx] = fmaf(av[j], bv, acc[j][rr * 3 + dx]);
-                    }
-            }
         }
+    };
+
+    if (nseg > 0) stage(0, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (long long q = 0; q < nseg; q++) {
+        const int buf = (int)(q & 1);
+        if (q + 1 < nseg) stage(q + 1, buf ^ 1);
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const float *s_a = wg_smem + buf * (SA + SB), *s_b = s_a + SA;
+        const int x0 = (int)(q % nsx) * WG_XS;
+        const int nx = min(WG_XS, p.Wa - x0);
+        for (int x = xlane; x < nx; x += p.xl) {
+            float av[NCA];
+#pragma unroll
+            for (int j = 0; j < NCA; j++) av[j] = s_a[x * cat + g * NCA + j];
+            const float *sb = s_b + (S * x) * cbl + lb;
+#pragma unroll
+            for (int rr = 0; rr < 9; rr++)
+#pragma unroll
+                for (int dx = 0; dx < 3; dx++) {
+                    const float bv = sb[(rr * XB + dx) * cbl];
+#pragma unroll
+                    for (int j = 0; j < NCA; j++) acc[j][rr * 3 + dx] = fmaf(av[j], bv, acc[j][rr * 3 + dx]);
+                }
+        }
+        __syncthreads();   // the buffer just read is refilled by the next iteration's prefetch
     }
     if (cb0 + lb < p.Cb) {
 #pragma unroll
@@ -108,6 +144,14 @@ __global__ void __launch_bounds__(WG_THREADS) k2_wgrad_kernel(const WgradParams 
             for (int t = 0; t < 27; t++) atomicAdd(dst + t, acc[j][t]);
         }
     }
+}
+
+template <int S, int NCA>
+static int launch_wgrad(const WgradParams &p, dim3 grid, cudaStream_t st)
+{
+    if (int rc = ensure_dynamic_smem(k2_wgrad_kernel<S, NCA>, WgTile<S>::SMEM, "conv3d_wgrad")) return rc;
+    k2_wgrad_kernel<S, NCA><<<grid, WG_THREADS, WgTile<S>::SMEM, st>>>(p);
+    return check_launch("k2_wgrad_kernel");
 }
 
 }  // namespace mvsb200
@@ -139,6 +183,7 @@ extern "C" int mvsb200_conv3d_wgrad(const float *a, const float *b, int B, int D
     p.cag = cag;
     p.xl = WG_THREADS / (p.cbl * p.cag);
     p.cbl_sh = p.cbl == 8 ? 3 : p.cbl == 16 ? 4 : 5;
+    p.b_vec4 = (Cb % 4 == 0 && ((unsigned long long)b & 15) == 0) ? 1 : 0;
     p.cat_sh = 0;
     while ((1 << p.cat_sh) < cag * nca) p.cat_sh++;
     p.tiles_a = (Ca + cag * nca - 1) / (cag * nca);
@@ -150,11 +195,6 @@ extern "C" int mvsb200_conv3d_wgrad(const float *a, const float *b, int B, int D
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, (unsigned)ctiles);
     cudaStream_t st = (cudaStream_t)stream;
-    if (stride == 1 && nca == 4) k2_wgrad_kernel<1, 4><<<grid, WG_THREADS, 0, st>>>(p);
-    else if (stride == 1 && nca == 2) k2_wgrad_kernel<1, 2><<<grid, WG_THREADS, 0, st>>>(p);
-    else if (stride == 1) k2_wgrad_kernel<1, 1><<<grid, WG_THREADS, 0, st>>>(p);
-    else if (nca == 4) k2_wgrad_kernel<2, 4><<<grid, WG_THREADS, 0, st>>>(p);
-    else if (nca == 2) k2_wgrad_kernel<2, 2><<<grid, WG_THREADS, 0, st>>>(p);
-    else k2_wgrad_kernel<2, 1><<<grid, WG_THREADS, 0, st>>>(p);
-    return check_launch("k2_wgrad_kernel");
+    if (stride == 1) return nca == 4 ? launch_wgrad<1, 4>(p, grid, st) : nca == 2 ? launch_wgrad<1, 2>(p, grid, st) : launch_wgrad<1, 1>(p, grid, st);
+    return nca == 4 ? launch_wgrad<2, 4>(p, grid, st) : nca == 2 ? launch_wgrad<2, 2>(p, grid, st) : launch_wgrad<2, 1>(p, grid, st);
 }
