@@ -252,13 +252,18 @@ def test_k3_backward_gradient_of_per_voxel_hypotheses():
         ops.regress_depth(sc.clone().requires_grad_(True), dv, None, L.CONF_NONE)[0].sum().backward()
 
 
-def test_cvp_training_step_matches_the_reference(golden, monkeypatch):
+@pytest.mark.parametrize("k2", ["cudnn", "lib"])
+def test_cvp_training_step_matches_the_reference(golden, monkeypatch, k2):
     """One training-mode forward + L1 loss on both pyramid levels + backward of CVP-MVSNet with the reference's weights
     (net.py:96-229 with self.training: 48 initial hypotheses, fixed refinement intervals): K1 backward in its
     VARIANCE_MEAN / per-pixel-hypotheses mode, K3 backward including the gradient through the refinement hypotheses."""
     from wild_deep_mvs_b200.cvpmvsnet import Frontend
     g = golden("cvp_train")
     monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)      # the golden is fp32 on the CPU
+    if k2 == "lib":      # the regulariser's 3x3x3 layers forward + backward on the library (K2 engines + wgrad kernel)
+        monkeypatch.setenv("MVSB200_TRAIN_K2", "lib")
+    else:
+        monkeypatch.delenv("MVSB200_TRAIN_K2", raising=False)
     net = Frontend()
     net.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}, strict=True)
     net.model.nscale = 2

@@ -14,6 +14,8 @@ FeaturePyramid (2-D CNN), the bicubic x2 depth up-sampling (net.py:169-170) and 
 `calDepthHypo` (modules.py:131-226) stay in PyTorch on the device ("next" rows f1 / f4 of SURVEY.md 8-f).
 Inference only.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -113,14 +115,23 @@ class CostRegNet(nn.Module):
 
     def forward_modules(self, x):
         """The same network through the PyTorch modules that own the parameters (net.py:76-85): training mode, where
-        BatchNorm uses batch statistics and autograd needs the layer graph."""
-        cbr = lambda m, v: F.relu(m.bn(m.conv(v)), inplace=True)
+        BatchNorm uses batch statistics and autograd needs the layer graph.  Convolutions on cuDNN by default; with
+        MVSB200_TRAIN_K2=lib on the library forward and backward (ops.conv3d_train), BatchNorm / ReLU stay PyTorch ops."""
+        lib = os.environ.get("MVSB200_TRAIN_K2") == "lib" and x.is_cuda
+
+        def conv(v, m, stride=1, transposed=False):
+            if lib:
+                return ops.as_ncdhw(ops.conv3d_train(ops.to_ndhwc(v), m.weight, m.bias, stride, transposed))
+            return m(v)
+
+        cbr = lambda m, v: F.relu(m.bn(conv(v, m.conv, m.conv.stride[0])), inplace=True)
+        dbr = lambda m, v, stride: m[2](m[1](conv(v, m[0], stride, True)))
         conv0 = cbr(self.conv0a, cbr(self.conv0, x))
         conv2 = cbr(self.conv2a, cbr(self.conv2, cbr(self.conv1, conv0)))
         conv4 = cbr(self.conv4a, cbr(self.conv4, cbr(self.conv3, conv2)))
-        conv5 = conv2 + self.conv5(conv4)
-        conv6 = conv0 + self.conv6(conv5)
-        return self.prob0(conv6).squeeze(1)
+        conv5 = conv2 + dbr(self.conv5, conv4, 1)
+        conv6 = conv0 + dbr(self.conv6, conv5, 2)
+        return conv(conv6, self.prob0).squeeze(1)
 
     def forward(self, x):
         """Reference signature: x [B,16,D,H,W] -> [B,D,H,W] (net.py:76-85)."""
