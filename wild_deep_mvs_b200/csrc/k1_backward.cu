@@ -87,7 +87,7 @@ __device__ __forceinline__ void sweep_view(const float *mapl, unsigned row_bytes
 }
 
 template <int C, int GEOM, int AGG>
-__global__ void __launch_bounds__(K1_THREADS, 2) k1_backward_kernel(const K1Params p, const K1BwdParams bp)
+__global__ void __launch_bounds__(K1_THREADS, 4) k1_backward_kernel(const K1Params p, const K1BwdParams bp)
 {
     constexpr int LPV = C / 8;
     constexpr int KPL = K1_DCH / LPV;

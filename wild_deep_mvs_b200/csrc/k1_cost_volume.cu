@@ -22,7 +22,7 @@
 namespace mvsb200 {
 
 template <int C, int GEOM, int AGG>
-__global__ void __launch_bounds__(K1_THREADS, 2) k1_cost_volume_kernel(const K1Params p)
+__global__ void __launch_bounds__(K1_THREADS, 4) k1_cost_volume_kernel(const K1Params p)
 {
     constexpr int LPV = C / 8;              // lanes per voxel, each owning 8 channels (two 16-byte vectors per tap)
     constexpr int VPB = K1_THREADS / LPV;   // pixels per block
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_cost_volume_kernel(const K1P
     for (int i = threadIdx.x; i < p.S * 16; i += K1_THREADS) s_warp[i] = p.warp[(long long)b * p.S * 16 + i];
     __syncthreads();
 
-    // A block owns a (32/LPV) x 8 pixel tile (one warp per row: the taps of vertically adjacent pixels share cache
+    // A block owns a (32/LPV) x 4 pixel tile (one warp per row: the taps of vertically adjacent pixels share cache
     // lines) and walks `chunks` depth chunks one after the other (the taps of consecutive chunks are the same or
     // neighbouring pixels, so they are served by L1).
     constexpr int TW = 32 / LPV, TH = K1_THREADS / 32;
