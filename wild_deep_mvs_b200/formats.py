@@ -10,7 +10,6 @@ and reads before it.  Host code (numpy), byte-compatible with the reference's ow
 The quirks of the reference are part of the format and are kept (each noted where it happens).  Pinned by files the
 UNMODIFIED reference functions wrote (tests/golden/make_golden_formats.py -> tests/golden/formats/).
 """
-import re
 import struct
 
 import numpy as np
@@ -145,25 +144,27 @@ def read_colmap_array(path):
 # PFM
 # ------------------------------------------------------------------------------------------------
 def read_pfm(path):
-    """-> (data [h,w] or [h,w,3] float32 top row first, scale) (data/MVSDataset.py:152-187).  Header `PF`|`Pf`,
-    `width height`, signed scale (negative = little endian); rows are stored bottom-up."""
+    """-> (data [h,w] or [h,w,3] float32 top row first, scale) (data/MVSDataset.py:152-187).  Header: magic `PF` (colour)
+    or `Pf` (grey), `width height` separated by ONE whitespace character, then a signed scale whose sign gives the byte
+    order (negative = little endian); the rows follow bottom-up.  Same exceptions as the reference's reader."""
     with open(path, "rb") as f:
-        header = f.readline().decode("utf-8").rstrip()
-        if header == "PF":
-            color = True
-        elif header == "Pf":
-            color = False
-        else:
+        magic = f.readline().decode("utf-8").rstrip()
+        channels = {"PF": 3, "Pf": 1}.get(magic)
+        if channels is None:
             raise Exception("Not a PFM file.")
-        m = re.match(r"^(\d+)\s(\d+)\s$", f.readline().decode("utf-8"))
-        if not m:
+        dims = f.readline().decode("utf-8")          # digits, one whitespace character, digits, one whitespace character
+        body = dims[:-1]
+        i = 0
+        while i < len(body) and body[i].isdigit():
+            i += 1
+        if not (0 < i < len(body) - 1 and body[i].isspace() and body[i + 1:].isdigit() and dims[-1:].isspace()):
             raise Exception("Malformed PFM header.")
-        w, h = map(int, m.groups())
+        parts = (body[:i], body[i + 1:])
+        w, h = int(parts[0]), int(parts[1])
         scale = float(f.readline().rstrip())
-        endian = "<" if scale < 0 else ">"
-        data = np.frombuffer(f.read(), dtype=endian + "f4")
-    data = np.flipud(data.reshape((h, w, 3) if color else (h, w)))
-    return data, abs(scale)
+        data = np.frombuffer(f.read(), dtype=("<" if scale < 0 else ">") + "f4")
+    shape = (h, w, 3) if channels == 3 else (h, w)
+    return np.flipud(data.reshape(shape)), abs(scale)
 
 
 def write_pfm(path, image, scale=1.0):
