@@ -284,7 +284,8 @@ def test_cvp_training_step_matches_the_reference(golden, monkeypatch, k2):
         assert err < 1e-2, k
 
 
-def test_vis_training_step_matches_the_reference(golden, monkeypatch):
+@pytest.mark.parametrize("k2", ["cudnn", "lib"])
+def test_vis_training_step_matches_the_reference(golden, monkeypatch, k2):
     """One training-mode forward of Vis-MVSNet (cascade [8,4,4]) with the reference's weights, a loss over every output
     the reference's loss touches (stage depths, pair depths weighted by their uncertainties, the uncertainties, the last
     probability map) and its backward: K1 backward in its group-correlation / start-map mode under the reference's own
@@ -292,6 +293,10 @@ def test_vis_training_step_matches_the_reference(golden, monkeypatch):
     from wild_deep_mvs_b200.vismvsnet import Frontend
     g = golden("vis_train")
     monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)      # the golden is fp32 on the CPU
+    if k2 == "lib":      # the 3x3x3 layers of Reg / RegPair / RegFuse forward + backward on the library
+        monkeypatch.setenv("MVSB200_TRAIN_K2", "lib")
+    else:
+        monkeypatch.delenv("MVSB200_TRAIN_K2", raising=False)
     nums, scales = [8, 4, 4], [4, 2, 1]
     net = Frontend()
     net.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}, strict=True)

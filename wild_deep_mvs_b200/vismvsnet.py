@@ -37,6 +37,15 @@ class _Named(nn.Module):
         return iter(self._modules.values())
 
 
+def _conv_train(m, x, transposed=False):
+    """A conv module of the PyTorch execution path.  3x3x3 layers of the regularisers go to the library forward AND
+    backward (ops.conv3d_train: K2 engines + wgrad kernel) when MVSB200_TRAIN_K2=lib; everything else (2-D layers, the
+    1x1x1 shortcuts) is the module itself."""
+    if (os.environ.get("MVSB200_TRAIN_K2") == "lib" and x.is_cuda and x.dim() == 5 and tuple(m.kernel_size) == (3, 3, 3)):
+        return ops.as_ncdhw(ops.conv3d_train(ops.to_ndhwc(x), m.weight, m.bias, m.stride[0], transposed))
+    return m(x)
+
+
 class _Block(nn.Module):
     """Parameters of BasicBlock (models/VisMVSNet/nn_utils.py:123-171)."""
 
@@ -53,9 +62,9 @@ class _Block(nn.Module):
             self.downsample = nn.Sequential(conv(cin, cout, 1, stride, bias=False), bn(cout))
         self.stride = stride
 
-    def forward(self, x):  # PyTorch execution, used by the 2-D feature extractor only
-        y = F.relu(self.bn1(self.conv1(x)), inplace=True)
-        y = self.bn2(self.conv2(y))
+    def forward(self, x):  # PyTorch execution: the 2-D feature extractor, and the 3-D regularisers in training mode
+        y = F.relu(self.bn1(_conv_train(self.conv1, x)), inplace=True)
+        y = self.bn2(_conv_train(self.conv2, y))
         r = x if self.downsample is None else self.downsample(x)
         return F.relu(y + r, inplace=True)
 
@@ -206,7 +215,7 @@ class _RegUNet(nn.Module):
         e0 = self.enc_blocks[self.tag + "4_0"](x)
         e1 = self.enc_blocks[self.tag + "8_1"](e0)
         dec = self.dec_blocks[self.tag + "16_2"]
-        return dec[1](torch.cat([dec[0](e1), e0], 1))
+        return _conv_train(dec[1], torch.cat([_conv_train(dec[0], e1, transposed=True), e0], 1))
 
     @staticmethod
     def run(pk, x, am):
@@ -335,7 +344,7 @@ class SingleStage(nn.Module):
         weight_sum, fused, pairs = 0, 0, []
         for s in range(S):
             interm = self.reg.unet(cost[s].permute(0, 4, 1, 2, 3))                      # [B,8,D,H,W]
-            prob, cls = soft_argmin(self.reg_pair.final_conv(interm).squeeze(1))
+            prob, cls = soft_argmin(_conv_train(self.reg_pair.final_conv, interm).squeeze(1))
             est = cls * interval + start
             ent = torch.sum(-prob * prob.clamp(1e-9, 1.).log(), dim=1, keepdim=True)    # nn_utils.py:469-470
             heads = self.uncert_net(ent)
@@ -344,7 +353,7 @@ class SingleStage(nn.Module):
             weight_sum = weight_sum + weight
             fused = fused + interm * weight
         fused = fused / weight_sum
-        prob, cls = soft_argmin(self.reg_fuse.final_conv(self.reg_fuse.unet(fused)).squeeze(1))
+        prob, cls = soft_argmin(_conv_train(self.reg_fuse.final_conv, self.reg_fuse.unet(fused)).squeeze(1))
         prob_map = torch.sum(prob * ((index - cls).abs() <= 2).to(prob.dtype), dim=1)
         return (cls * interval + start).squeeze(1), prob_map, pairs
 
