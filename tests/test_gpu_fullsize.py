@@ -1,0 +1,143 @@
+"""GPU: BASELINE-size parity (cfg2, cfg3 in both settings, cfg4) against the UNMODIFIED reference executed on the same
+GPU in fp32 (TF32 off) through stock PyTorch / cuDNN.
+
+The reference comes from oracle/_ref/ref_hotpath.zip (oracle/make_ref.py packs the hot-path files of /root/reference,
+byte for byte, in the build container; the archive is git-ignored and travels to the GPU box with the snapshot).  Weights:
+seeded random init + randomised BatchNorm statistics + a gained head conv (peaked softmax), loaded with
+strict=True from the drop-in's state_dict into the reference's modules -- the key names are the boundary.
+
+Tolerance: the north-star bar, depth maps within 1e-3 relative L-inf of the reference PyTorch path -- at EVERY stage /
+pyramid level, on the whole map.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ref_import  # noqa: E402
+from wild_deep_mvs_b200 import synth  # noqa: E402
+
+DEV = "cuda:0"
+DEPTH_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if ref_import.reference_location() is None:
+        pytest.skip("oracle/_ref/ref_hotpath.zip missing: run `python oracle/make_ref.py` where /root/reference exists")
+    return ref_import.import_reference(cuda_shim=False)
+
+
+@pytest.fixture(autouse=True)
+def fp32_reference():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+
+
+def sample(views, h, w):
+    return {k: v.to(DEV) for k, v in synth.make_sample(1, views, h, w, seed=0).items()}
+
+
+def report(name, got, want):
+    d = (got.double() - want.double()).abs() / want.double().abs().max()
+    q = torch.quantile(d.flatten()[:: max(1, d.numel() // 1_000_000)], torch.tensor([0.5, 0.999], device=d.device, dtype=torch.float64))
+    print("%s: rel L-inf %.2e  (median %.1e, 99.9%% %.1e, spread of reference map %.1f..%.1f)"
+          % (name, d.max(), q[0], q[1], want.min(), want.max()))
+    return float(d.max())
+
+
+def test_cfg2_mvsnet_full_size_against_reference(ref):
+    """MVSNet variance, 1+4 views, 640x512, D=192: forward(imgs, ...) of the drop-in against the reference's forward.
+    The 2-D FeatureNet runs on K7 in the drop-in and on cuDNN in the reference, so the reference's own feature maps are
+    also fed to the drop-in's hot path (isolates section 8-a: a1, a2, a4, a5, a6, a7)."""
+    from oracle import ref_run
+    from wild_deep_mvs_b200 import ops
+    from wild_deep_mvs_b200.mvsnet import MVSNet, build_proj_matrices
+    torch.manual_seed(0)
+    net = MVSNet("variance")
+    synth.randomize_norm_stats(net, seed=1)
+    synth.scale_param(net.cost_regularization.prob.weight, 40.0)
+    net = net.to(DEV).eval()
+    rnet = ref_run.reference_mvsnet(ref, net.state_dict(), "variance", 192, DEV)
+    s = sample(5, 512, 640)
+    with torch.no_grad():
+        want = rnet(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"])
+        got = net(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"])
+        assert report("cfg2 forward depth", got["depth"], want["depth"]) < DEPTH_TOL
+        # hot path alone on the reference's own features
+        feats = rnet.extract_features(torch.unbind(s["imgs"], 1))
+        K4 = s["K"].clone()
+        K4[:, :, :2] /= 4
+        projs = list(torch.unbind(build_proj_matrices(K4, s["R"], s["t"]), 1))
+        dv = s["depth_min"][:, :1] + (s["depth_max"][:, :1] - s["depth_min"][:, :1]) / 191 * torch.arange(192, device=DEV).view(1, -1)
+        depth, conf = net.depth_from_features([ops.to_nhwc(f) for f in feats], projs, dv.contiguous())
+        assert report("cfg2 hot path depth", depth, want["depth"]) < DEPTH_TOL
+        # confidence: sum of 4 probabilities around floor(expected index) -- differs only where the expected index sits
+        # on an integer boundary (the .long() truncation flips); everywhere else it matches to fp32 accuracy
+        bad = (conf - want["photometric_confidence"]).abs() > 1e-4
+        assert bad.float().mean() < 5e-3, bad.float().mean()
+
+
+@pytest.mark.parametrize("nums,scales", [([32, 16, 8], [4, 2, 1]), ([64, 32, 16], [2, 1, 0.5])], ids=["default", "eval"])
+def test_cfg3_full_size_against_reference(ref, nums, scales):
+    """Vis-MVSNet, 1+4 views, 640x512, both BASELINE settings: every stage's fused depth, every pair depth and the
+    probability maps against the reference run on the same GPU (a8-a13: GEOM_VIS / GROUPCORR / DEPTH_START_MAP K1 paths,
+    the batched-pairs regularisers, K3 entropy / CONF_WINDOW, K6, K4 at 64x80 ... 256x320 maps)."""
+    from wild_deep_mvs_b200.vismvsnet import Frontend
+    torch.manual_seed(0)
+    net = Frontend()
+    synth.randomize_norm_stats(net, seed=2)
+    for st in (net.model.stage1, net.model.stage2, net.model.stage3):
+        synth.scale_param(st.reg_fuse.final_conv.weight, 30.0)
+        synth.scale_param(st.reg_pair.final_conv.weight, 30.0)
+    net = net.to(DEV).eval()
+    rnet = ref.VisFrontend()
+    rnet.load_state_dict(net.state_dict(), strict=True)
+    rnet = rnet.to(DEV).eval()
+    for m in (net, rnet):
+        m.depth_nums, m.interval_scales = nums, scales
+    s = sample(5, 512, 640)
+    with torch.no_grad():
+        want = rnet(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"], depth_nums=nums, interval_scales=scales)
+        got = net(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"], depth_nums=nums, interval_scales=scales)
+    errs = []
+    for k in range(3):
+        errs.append(report("cfg3 %s stage %d depth" % (nums, 3 - k), got["depth_est_list"][k], want["depth_est_list"][k]))
+        for v in range(4):
+            errs.append(report("   pair %d" % v, got["depth_pair_list"][k][v][0], want["depth_pair_list"][k][v][0]))
+    assert max(errs) < DEPTH_TOL, errs
+    bad = (got["photometric_confidence"] - want["photometric_confidence"]).abs() > 1e-3
+    assert bad.float().mean() < 5e-3, bad.float().mean()
+
+
+def test_cfg4_full_size_against_reference(ref):
+    """CVP-MVSNet, 1+4 views, 1600x1184, nscale=5 (eval mode: D0 = 96, calDepthHypo intervals): every pyramid level's depth
+    map against the reference run on the same GPU (a14-a19: AGG_VARIANCE_MEAN, DEPTH_VOLUME K1 path, K5, the shared
+    regulariser on volumes up to 970 MB, bicubic up-sampling, per-pixel regression)."""
+    from wild_deep_mvs_b200.cvpmvsnet import Frontend
+    torch.manual_seed(0)
+    net = Frontend()
+    synth.randomize_norm_stats(net, seed=3)
+    synth.scale_param(net.model.cost_reg_refine.prob0.weight, 30.0)
+    net = net.to(DEV).eval()
+    rnet = ref.CVPFrontend()
+    rnet.load_state_dict(net.state_dict(), strict=True)
+    rnet = rnet.to(DEV).eval()
+    s = sample(5, 1184, 1600)
+    with torch.no_grad():
+        want = rnet(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"], nscale=5)
+        want = {"depth_est_list": [d.clone() for d in want["depth_est_list"]], "conf": want["photometric_confidence"].clone()}
+        del rnet
+        torch.cuda.empty_cache()
+        got = net(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"], nscale=5)
+    errs = [report("cfg4 level %d depth" % k, got["depth_est_list"][k], want["depth_est_list"][k]) for k in range(5)]
+    assert max(errs) < DEPTH_TOL, errs
+    bad = (got["photometric_confidence"] - want["conf"]).abs() > 1e-3
+    assert bad.float().mean() < 2e-2, bad.float().mean()

@@ -210,3 +210,32 @@ def test_feature_net_k7_against_reference_golden_and_module_path(golden):
         torch.backends.cudnn.allow_tf32 = old
     assert k7.shape == plain.shape == (3, 32, 50, 82)
     assert rel_linf(k7.cpu().numpy(), plain.cpu().numpy()) < 1e-4
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_net_on_second_gpu_while_first_is_current(golden):
+    """Every library call runs on the OPERANDS' device (ops._on_operand_device), not on whatever device is current:
+    a net moved to cuda:1 gives the same depth map as on cuda:0 while cuda:0 stays the current device."""
+    from wild_deep_mvs_b200 import _lib as L
+    assert torch.cuda.current_device() == 0
+    g = golden("mvsnet_variance")
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        net = MVSNet("variance")
+        sd = net.state_dict()
+        for k, v in g.items():
+            if k.startswith("cost_regularization."):
+                sd[k] = torch.from_numpy(v)
+        net.load_state_dict(sd)
+        net.num_depth = g["depth_values"].shape[1]
+        net = net.to(dev).eval()
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        feats = [ops.to_nhwc(t(g["feat%d" % i])) for i in range(3)]
+        projs = [t(g["proj"][:, i]) for i in range(3)]
+        depth, conf = net.depth_from_features(feats, projs, t(g["depth_values"]))
+        assert depth.device == torch.device(dev)
+        outs.append(depth.cpu())
+    assert torch.cuda.current_device() == 0
+    assert torch.equal(outs[0], outs[1])
+    with pytest.raises(L.Mvsb200Error):
+        ops.depth_regress(torch.zeros(1, 8, 8, 8, device="cuda:0"), torch.zeros(1, 8, device="cuda:1"))

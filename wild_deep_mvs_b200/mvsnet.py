@@ -192,19 +192,27 @@ class GraphedHotPath:
     Inputs are copied into the captured buffers; the returned tensors are the captured outputs (overwritten by the
     next replay -- clone them to keep them)."""
 
-    def __init__(self, net, feats_nhwc, proj_matrices, depth_values, reference_frame=0, warmup=2):
+    def __init__(self, net, feats_nhwc, proj_matrices, depth_values, reference_frame=0, warmup=2, gather=None):
+        """`gather` (shard.DepthGather, optional): K3 writes the depth map into this rank's slice of the gather buffer and
+        the in-place all-gather is part of the captured graph; `self.gathered` is then the [world * B, h, w] result."""
         self.feats = [f.clone() for f in feats_nhwc]
         self.projs = [p.clone() for p in proj_matrices]
         self.depth_values = depth_values.clone()
+        self.gather = gather
+        out_depth = gather.local if gather is not None else None
+        run = lambda: net.depth_from_features(self.feats, self.projs, self.depth_values, reference_frame, out_depth=out_depth)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):   # first calls pack weights and set kernel attributes: keep them out of the capture
             for _ in range(warmup):
-                net.depth_from_features(self.feats, self.projs, self.depth_values, reference_frame)
+                run()
+                if gather is not None:
+                    gather.all_gather()   # the communicator's first collective (connection setup) cannot be captured
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.depth, self.conf = net.depth_from_features(self.feats, self.projs, self.depth_values, reference_frame)
+            self.depth, self.conf = run()
+            self.gathered = gather.all_gather() if gather is not None else None
 
     def __call__(self, feats_nhwc=None, proj_matrices=None, depth_values=None):
         if feats_nhwc is not None:
@@ -219,6 +227,32 @@ class GraphedHotPath:
         return self.depth, self.conf
 
 
+class GraphedForward:
+    """MVSNet.forward (eval) as one CUDA graph; see MVSNet.graphed_forward."""
+
+    def __init__(self, net, imgs, K, R, t, depth_min, depth_max, reference_frame=0, warmup=2):
+        if net.training or not isinstance(imgs, torch.Tensor):
+            raise L.Mvsb200Error("graphed_forward: eval mode and same-sized views (a [B,V,3,H,W] tensor) only")
+        self.inputs = [x.clone() for x in (imgs, K, R, t, depth_min, depth_max)]
+        run = lambda: net(*self.inputs, reference_frame=reference_frame)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                run()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = run()
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.inputs, inputs):
+            if src is not None:
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 class StreamedHotPath:
     """A stream of samples whose inputs sit in PINNED HOST memory (the reconstruction pipeline's loop over the reference
     views of a scene, evaluation/run_depthmaps.py:53-68): `slots` graph instances are used round-robin, the H2D copies of
@@ -226,15 +260,19 @@ class StreamedHotPath:
     to pinned host buffers.  submit() returns (host_depth, host_conf, event); the buffers are valid once the event has
     completed and until the slot is reused (`slots` submissions later)."""
 
-    def __init__(self, net, feats_nhwc, proj_matrices, depth_values, reference_frame=0, slots=2):
-        self.slots = [GraphedHotPath(net, feats_nhwc, proj_matrices, depth_values, reference_frame) for _ in range(slots)]
+    def __init__(self, net, feats_nhwc, proj_matrices, depth_values, reference_frame=0, slots=2, gathers=None):
+        """`gathers`: one shard.DepthGather per slot -- every sample's depth map is then all-gathered inside its graph
+        and `submit` copies the GATHERED maps of all ranks back to the host."""
+        self.slots = [GraphedHotPath(net, feats_nhwc, proj_matrices, depth_values, reference_frame,
+                                     gather=gathers[k] if gathers else None) for k in range(slots)]
         self.copy_stream = torch.cuda.Stream()
         self.ready = [torch.cuda.Event() for _ in range(slots)]
         self.done = [torch.cuda.Event() for _ in range(slots)]
         for e in self.done:
             e.record()
         g = self.slots[0]
-        self.out_depth = [torch.empty(g.depth.shape, dtype=g.depth.dtype).pin_memory() for _ in range(slots)]
+        dshape = g.gathered.shape if g.gathered is not None else g.depth.shape
+        self.out_depth = [torch.empty(dshape, dtype=g.depth.dtype).pin_memory() for _ in range(slots)]
         self.out_conf = [torch.empty(g.conf.shape, dtype=g.conf.dtype).pin_memory() for _ in range(slots)]
         self.count = 0
 
@@ -253,7 +291,7 @@ class StreamedHotPath:
             self.ready[k].record(self.copy_stream)
         main.wait_event(self.ready[k])
         g.graph.replay()
-        self.out_depth[k].copy_(g.depth, non_blocking=True)
+        self.out_depth[k].copy_(g.gathered if g.gathered is not None else g.depth, non_blocking=True)
         self.out_conf[k].copy_(g.conf, non_blocking=True)
         self.done[k].record(main)
         return self.out_depth[k], self.out_conf[k], self.done[k]
@@ -297,8 +335,9 @@ class MVSNet(nn.Module):
                                   src_projs, depth_values)
         return ops.as_ncdhw(vol)
 
-    def depth_from_features(self, feats_nhwc, proj_matrices, depth_values, reference_frame=0):
-        """The hot path proper: channels-last features -> (depth, confidence).  feats_nhwc: list of V maps."""
+    def depth_from_features(self, feats_nhwc, proj_matrices, depth_values, reference_frame=0, out_depth=None, out_conf=None):
+        """The hot path proper: channels-last features -> (depth, confidence).  feats_nhwc: list of V maps.
+        `out_depth` / `out_conf` [B,h,w]: caller-owned output buffers (e.g. shard.DepthGather.local)."""
         ref = feats_nhwc[reference_frame]
         srcs = feats_nhwc[:reference_frame] + feats_nhwc[reference_frame + 1:]
         ref_proj = proj_matrices[reference_frame]
@@ -306,7 +345,7 @@ class MVSNet(nn.Module):
         vol = self.cost_volume_cl(ref, srcs, ref_proj, src_projs, depth_values)
         score = self.cost_regularization.run(vol)
         del vol
-        out = ops.depth_regress(score, depth_values, conf_mode=L.CONF_SUM4)
+        out = ops.depth_regress(score, depth_values, conf_mode=L.CONF_SUM4, out_depth=out_depth, out_conf=out_conf)
         return out["depth"], out["conf"]
 
     def _forward_differentiable(self, imgs, proj_matrices, depth_values, reference_frame):
@@ -321,13 +360,20 @@ class MVSNet(nn.Module):
         score = self.cost_regularization(ops.as_ncdhw(vol)).squeeze(1)
         return ops.regress_depth(score, depth_values, conf_mode=L.CONF_SUM4)
 
-    def graphed(self, feats_nhwc, proj_matrices, depth_values, reference_frame=0):
+    def graphed(self, feats_nhwc, proj_matrices, depth_values, reference_frame=0, gather=None):
         """CUDA-graph version of depth_from_features for inputs of these shapes (see GraphedHotPath)."""
-        return GraphedHotPath(self, feats_nhwc, proj_matrices, depth_values, reference_frame)
+        return GraphedHotPath(self, feats_nhwc, proj_matrices, depth_values, reference_frame, gather=gather)
 
-    def streamed(self, feats_nhwc, proj_matrices, depth_values, reference_frame=0, slots=2):
+    def streamed(self, feats_nhwc, proj_matrices, depth_values, reference_frame=0, slots=2, gathers=None):
         """Double-buffered, copy-overlapped version for a stream of pinned-host samples (see StreamedHotPath)."""
-        return StreamedHotPath(self, feats_nhwc, proj_matrices, depth_values, reference_frame, slots)
+        return StreamedHotPath(self, feats_nhwc, proj_matrices, depth_values, reference_frame, slots, gathers)
+
+    def graphed_forward(self, imgs, K, R, t, depth_min, depth_max, reference_frame=0):
+        """The whole eval-mode `forward` (images -> dict) captured into ONE CUDA graph for inputs of these shapes: K7
+        feature extractor, geometry, K1, K2, K3 and the PyTorch glue between them replay as a single launch.  Returns a
+        callable taking the same tensors (copied into the captured buffers; None = keep the captured values) and
+        returning the captured output dict (overwritten by the next replay)."""
+        return GraphedForward(self, imgs, K, R, t, depth_min, depth_max, reference_frame)
 
     def forward(self, imgs, K, R, t, depth_min, depth_max, reference_frame=0, **kwargs):
         try:

@@ -6,6 +6,7 @@ Layouts (include/mvsb200.h): feature maps [B,H,W,C], volumes [B,D,H,W,C], single
 copy when the tensor is already channels-last in memory.
 """
 import ctypes
+import functools
 import os
 
 import torch
@@ -24,6 +25,34 @@ DEFAULT_ENGINE = os.environ.get("MVSB200_K2_ENGINE", "zm")
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _tensors(objs):
+    for o in objs:
+        if isinstance(o, torch.Tensor):
+            yield o
+        elif isinstance(o, (list, tuple)):
+            yield from _tensors(o)
+
+
+def _on_operand_device(fn):
+    """Every library call launches on the CURRENT device's current stream (and `cudaGetDevice` picks the kernel
+    attributes / grid sizes).  This guard makes the operands' device current for the duration of the call and refuses
+    operands that live on different devices, so a net moved to cuda:1 works while cuda:0 is current."""
+    @functools.wraps(fn)
+    def guarded(*args, **kwargs):
+        dev = None
+        for t in _tensors(list(args) + list(kwargs.values())):
+            if t.is_cuda:
+                if dev is None:
+                    dev = t.device
+                elif t.device != dev:
+                    raise L.Mvsb200Error("%s: operands on different devices (%s and %s)" % (fn.__name__, dev, t.device))
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return guarded
 
 
 def _ptr(t):
@@ -53,16 +82,27 @@ class AmaxPool:
         return v
 
 
+@_on_operand_device
 def absmax(t):
     """max|t| as a 1-element device tensor: the value its producer tracked (attribute `_mvs_amax`, set by
-    build_cost_volume / conv3d / vis_fuse) or, for tensors from elsewhere, one reduction pass (mvsb200_absmax)."""
+    build_cost_volume / conv3d / vis_fuse) or, for tensors from elsewhere, one reduction pass (mvsb200_absmax).
+    The tracked value is tied to the tensor's autograd version counter (`_mvs_amax_version`): an in-place torch write
+    (`vol.copy_(new)`) after the value was taken invalidates it and the maximum is recomputed."""
     a = getattr(t, "_mvs_amax", None)
-    if a is not None:
+    if a is not None and getattr(t, "_mvs_amax_version", t._version) == t._version:
         return a
     a = torch.empty(1, device=t.device, dtype=torch.float32)
     L.check(L.load().mvsb200_absmax(_ptr(t), t.numel(), _ptr(a), _stream()), "mvsb200_absmax")
     t._mvs_amax = a
+    t._mvs_amax_version = t._version
     return a
+
+
+def set_absmax(t, a):
+    """Attach a producer-tracked abs-max scalar to `t` (valid until the next in-place torch write to `t`)."""
+    t._mvs_amax = a
+    t._mvs_amax_version = t._version
+    return t
 
 
 def map_views(extract, imgs):
@@ -101,6 +141,7 @@ def as_ncdhw(v):
 # ------------------------------------------------------------------------------------------------
 # geometry prologues
 # ------------------------------------------------------------------------------------------------
+@_on_operand_device
 def mvs_relative_proj(ref_proj, src_projs):
     """ref_proj [B,4,4], src_projs [B,S,4,4] -> warp [B,S,16]; replaces MVSNet/module.py:128."""
     ref_proj = _dev_f32(ref_proj.contiguous(), "ref_proj")
@@ -112,6 +153,7 @@ def mvs_relative_proj(ref_proj, src_projs):
     return warp
 
 
+@_on_operand_device
 def vis_homography_params(ref_cam, src_cams, scale):
     """ref_cam [B,2,4,4], src_cams [B,S,2,4,4] -> warp [B,S,16]; replaces VisMVSNet/homography.py:23-74."""
     ref_cam = _dev_f32(ref_cam.contiguous(), "ref_cam")
@@ -140,6 +182,7 @@ def _depth_mode(depth, interval, B, D, H, W):
     return L.DEPTH_START_MAP
 
 
+@_on_operand_device
 def build_cost_volume(ref, srcs, warp, depth, D, geom, agg, interval=None, temp=None, groups=8, out=None, amax=None):
     """ref [B,H,W,C]; srcs list of [B,Hs,Ws,C]; warp [B,S,16]; depth/interval see mvsb200.h.
     Returns [B,D,H,W,C] or, for AGG_GROUPCORR, [S,B,D,H,W,groups].  `amax` (zeroed device scalar, optional) receives
@@ -178,7 +221,7 @@ def build_cost_volume(ref, srcs, warp, depth, D, geom, agg, interval=None, temp=
     L.check(lib.mvsb200_build_cost_volume(ctypes.byref(desc), _ptr(ref), ptrs, _ptr(_dev_f32(warp, "warp")), _ptr(depth),
                                           _ptr(interval), _ptr(temp), _ptr(out), _ptr(amax), _stream()),
             "mvsb200_build_cost_volume")
-    out._mvs_amax = amax
+    set_absmax(out, amax)
     return out
 
 
@@ -203,6 +246,7 @@ def _cost_volume_desc(ref, srcs, D, geom, agg, groups, depth, interval):
     return desc, ptrs
 
 
+@_on_operand_device
 def build_cost_volume_backward(grad_out, ref, srcs, warp, depth, D, geom, agg, interval=None, temp=None, groups=8):
     """Gradient of build_cost_volume with respect to the feature maps (and `temp` for AGG_SOFTMIN): K1 backward
     (mvsb200_build_cost_volume_backward).  Returns (grad_ref [B,H,W,C], [grad_src_s], grad_temp or None)."""
@@ -351,6 +395,7 @@ class PackedConv:
         return self._tc_packed
 
 
+@_on_operand_device
 def conv3d(x, layer, x2=None, skip=None, engine=None, out=None, amax=None):
     """x [B,D,H,W,Cin] (+ x2 [B,D,H,W,Cin2] concatenated on channels) -> [B,Do,Ho,Wo,Cout].
     `out`: caller-owned output buffer; `amax`: zeroed device scalar that receives max|y| (z-march engine)."""
@@ -400,7 +445,7 @@ def conv3d(x, layer, x2=None, skip=None, engine=None, out=None, amax=None):
         L.check(lib.mvsb200_conv3d_zm(ctypes.byref(desc), _ptr(x), _ptr(x2), _ptr(layer.zm_packed(desc)), _ptr(layer.scale),
                                       _ptr(layer.bias), _ptr(skip), _ptr(y), _ptr(absmax(x)),
                                       _ptr(absmax(x2)) if x2 is not None else None, _ptr(amax), _stream()), "mvsb200_conv3d_zm")
-        y._mvs_amax = amax
+        set_absmax(y, amax)
         return y
     if (engine == "zm" and x.device == layer.w.device and x2 is None and C1 % 16 == 0 and layer.skip_mode != L.SKIP_AFTER_RELU
             and layer.k == (3, 3, 3)):
@@ -418,7 +463,7 @@ def conv3d(x, layer, x2=None, skip=None, engine=None, out=None, amax=None):
             half.relu, half.skip_mode = b.relu, L.SKIP_BEFORE_RELU
             L.check(lib.mvsb200_conv3d_zm_slice(ctypes.byref(half), _ptr(x), C1, C1 // 2, None, _ptr(b.zm_packed(half)), _ptr(b.scale),
                                                 None, _ptr(y), _ptr(y), xa, None, _ptr(amax), _stream()), "mvsb200_conv3d_zm_slice")
-            y._mvs_amax = amax
+            set_absmax(y, amax)
             return y
     if engine != "fp32" and x.device == layer.w.device and lib.mvsb200_conv3d_tc_supported(ctypes.byref(desc)):
         prec = L.PRECISION_TF32 if engine == "tc_tf32" else L.PRECISION_3XTF32
@@ -431,6 +476,7 @@ def conv3d(x, layer, x2=None, skip=None, engine=None, out=None, amax=None):
 
 
 # ---- K2 in training (row f2): forward and input gradient on the K2 engines, weight gradient on mvsb200_conv3d_wgrad ----
+@_on_operand_device
 def conv3d_wgrad(a, b, stride):
     """R[ca][cb][3,3,3] = sum_v a[v,ca] * b[stride*v + tap - 1, cb]   (a [B,Da,Ha,Wa,Ca] the low-resolution side, b
     [B,Db,Hb,Wb,Cb] the high-resolution side).  Conv3d: a = grad_out, b = input -> dW [Cout,Cin,3,3,3];
@@ -495,8 +541,12 @@ def conv3d_train(x, weight, bias=None, stride=1, transposed=False):
 # ------------------------------------------------------------------------------------------------
 # K3 / K4
 # ------------------------------------------------------------------------------------------------
-def depth_regress(score, depth, interval=None, conf_mode=L.CONF_NONE, want_entropy=False, want_prob=False):
-    """score [B,D,H,W] -> dict(depth [B,H,W], conf, entropy, prob)."""
+@_on_operand_device
+def depth_regress(score, depth, interval=None, conf_mode=L.CONF_NONE, want_entropy=False, want_prob=False,
+                  out_depth=None, out_conf=None):
+    """score [B,D,H,W] -> dict(depth [B,H,W], conf, entropy, prob).  `out_depth` / `out_conf`: caller-owned [B,H,W]
+    buffers the kernel writes into -- e.g. this rank's slice of a gather buffer (shard.DepthGather), so that the depth
+    map is born where the all-gather sends it from."""
     lib = L.load()
     score = _dev_f32(score, "score")
     B, D, H, W = score.shape
@@ -505,7 +555,12 @@ def depth_regress(score, depth, interval=None, conf_mode=L.CONF_NONE, want_entro
         interval = _dev_f32(interval.contiguous().view(-1), "interval")
     mode = _depth_mode(depth, interval, B, D, H, W)
     new = lambda *s: torch.empty(*s, device=score.device, dtype=torch.float32)
-    out = {"depth": new(B, H, W), "conf": new(B, H, W) if conf_mode else None,
+    for name, t in (("out_depth", out_depth), ("out_conf", out_conf)):
+        if t is not None and (tuple(_dev_f32(t, name).shape) != (B, H, W) or t.device != score.device):
+            raise L.Mvsb200Error("depth_regress: %s has shape %s on %s, expected %s on %s"
+                                 % (name, tuple(t.shape), t.device, (B, H, W), score.device))
+    out = {"depth": out_depth if out_depth is not None else new(B, H, W),
+           "conf": (out_conf if out_conf is not None else new(B, H, W)) if conf_mode else None,
            "entropy": new(B, H, W) if want_entropy else None, "prob": new(B, D, H, W) if want_prob else None}
     L.check(lib.mvsb200_depth_regress(_ptr(score), B, D, H, W, mode, _ptr(depth), _ptr(interval), conf_mode,
                                       _ptr(out["depth"]), _ptr(out["conf"]), _ptr(out["entropy"]), _ptr(out["prob"]),
@@ -513,6 +568,7 @@ def depth_regress(score, depth, interval=None, conf_mode=L.CONF_NONE, want_entro
     return out
 
 
+@_on_operand_device
 def depth_regress_backward(grad_depth, score, depth, interval=None, want_grad_hyp=False):
     """grad_score [B,D,H,W] of depth_regress()["depth"] (K3 backward, mvsb200_depth_regress_backward); with
     `want_grad_hyp` (per-voxel hypotheses [B,D,H,W] only) -> (grad_score, grad_hypotheses)."""
@@ -562,6 +618,7 @@ def regress_depth(score, depth, interval=None, conf_mode=L.CONF_NONE):
     return _DepthRegressFn.apply(score, depth, interval, conf_mode)
 
 
+@_on_operand_device
 def vis_fuse(interms, uncerts):
     """interms list of [B,D,H,W,G]; uncerts list of [B,H,W] -> [B,D,H,W,G]."""
     lib = L.load()
@@ -587,6 +644,7 @@ def uncert_net_params(conv1, conv2, head):
     return (ctypes.c_float * 752)(*flat.tolist())
 
 
+@_on_operand_device
 def vis_uncert_net(entropy, params):
     """entropy [N,H,W] -> log-uncertainty [N,H,W] (UncertNet, VisMVSNet/model_cas.py:77-98, one fused kernel)."""
     entropy = _dev_f32(entropy.contiguous(), "entropy")
@@ -621,6 +679,7 @@ class PackedConv2d:
             self.bias = conv_bias.detach().float().contiguous() if conv_bias is not None else None
 
 
+@_on_operand_device
 def conv2d(x, layer):
     """x [B,H,W,Cin] channels-last -> [B,Ho,Wo,Cout] (K7)."""
     x = _dev_f32(x, "x")
@@ -638,6 +697,7 @@ def conv2d(x, layer):
 # ------------------------------------------------------------------------------------------------
 # K5
 # ------------------------------------------------------------------------------------------------
+@_on_operand_device
 def cvp_depth_delta(ref_depth, ref_in, src_in, ref_ex, src_ex):
     """ref_depth [B,H,W]; ref_in, src_in [B,3,3]; ref_ex, src_ex [B,4,4] -> |delta| [B,H*W] fp64, +inf where invalid
     (the per-pixel solve of calDepthHypo, CVP_MVSNet/models/modules.py:131-214)."""

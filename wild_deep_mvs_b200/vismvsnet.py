@@ -168,7 +168,7 @@ class FeatExt(nn.Module):
             amax = getattr(up, "_mvs_amax", None)                        # (tracked by the z-march engine only)
             up = up[:, :1].contiguous()                                   # plane 0 is the 2-D result, plane 1 has no taps
             if amax is not None:
-                up._mvs_amax = amax
+                ops.set_absmax(up, amax)
             v = ops.conv3d(up, d["post"], x2=enc[-2 - i])                 # conv(cat([up, enc], 1))
             for b in d["blocks"]:
                 v = _run_block2d(b, v)
@@ -288,9 +288,10 @@ class SingleStage(nn.Module):
             self._key = key
         return self._packed
 
-    def run(self, ref, srcs, ref_cam, src_cams, depth_num, depth_start, depth_interval, s_scale):
+    def run(self, ref, srcs, ref_cam, src_cams, depth_num, depth_start, depth_interval, s_scale, out_depth=None):
         """ref [B,H,W,32], srcs list of [B,Hs,Ws,32]; cams [B,2,4,4] / [B,S,2,4,4]; depth_start [B] or [B,H,W];
-        depth_interval [B].  Returns est_depth [B,H,W], prob_map [B,H,W], pair list [(depth, uncert)]."""
+        depth_interval [B].  Returns est_depth [B,H,W], prob_map [B,H,W], pair list [(depth, uncert)].
+        `out_depth` [B,H,W]: caller-owned buffer for est_depth (a gather slice, shard.DepthGather)."""
         if self.training:
             return self._run_train(ref, srcs, ref_cam, src_cams, depth_num, depth_start, depth_interval, s_scale)
         pk = self._pack()
@@ -304,7 +305,7 @@ class SingleStage(nn.Module):
         cost = ops.build_cost_volume(ref, srcs, warp, depth_start, D, L.GEOM_VIS, L.AGG_GROUPCORR,
                                      interval=depth_interval, groups=8, amax=am.take())   # [S,B,D,H,W,8]
         cost_sb = cost.view(S * B, D, H, W, 8)                                      # pairs stacked on the batch axis
-        cost_sb._mvs_amax = cost._mvs_amax                                          # abs-max tracked by K1 (views drop attributes)
+        ops.set_absmax(cost_sb, cost._mvs_amax)                                       # abs-max tracked by K1 (views drop attributes)
         interm = _RegUNet.run(pk["reg"], cost_sb, am)
         del cost, cost_sb
         score = ops.conv3d(interm, pk["pair_head"]).squeeze(-1)                     # [S*B,D,H,W]
@@ -314,12 +315,12 @@ class SingleStage(nn.Module):
         interm_amax = interm._mvs_amax
         interm = interm.view(S, B, D, H, W, 8)
         fused = ops.vis_fuse([interm[s] for s in range(S)], [u[s] for s in range(S)])
-        fused._mvs_amax = interm_amax   # a convex combination of the per-pair volumes: their abs-max bounds it
+        ops.set_absmax(fused, interm_amax)   # a convex combination of the per-pair volumes: their abs-max bounds it
         pair_depth = pair["depth"].view(S, B, H, W)
         pairs = [[pair_depth[s].unsqueeze(1), [u[s].unsqueeze(1)]] for s in range(S)]
         del interm
         fscore = ops.conv3d(_RegUNet.run(pk["fuse"], fused, am), pk["fuse_head"]).squeeze(-1)
-        out = ops.depth_regress(fscore, depth_start, interval=depth_interval, conf_mode=L.CONF_WINDOW)
+        out = ops.depth_regress(fscore, depth_start, interval=depth_interval, conf_mode=L.CONF_WINDOW, out_depth=out_depth)
         return out["depth"], out["conf"], pairs
 
 
@@ -368,11 +369,13 @@ class Model(nn.Module):
 
 
 class _GraphedCascade:
-    def __init__(self, net, feats, ref_cam, src_cams, depth_min, depth_interval, depth_nums, interval_scales, warmup=2):
+    def __init__(self, net, feats, ref_cam, src_cams, depth_min, depth_interval, depth_nums, interval_scales, warmup=2,
+                 out_depth=None):
         self.feats = [[f.clone() for f in fv] for fv in feats]
         self.ref_cam, self.src_cams = ref_cam.clone(), src_cams.clone()
         self.depth_min, self.depth_interval = depth_min.clone(), depth_interval.clone()
-        args = (self.feats, self.ref_cam, self.src_cams, self.depth_min, self.depth_interval, depth_nums, interval_scales)
+        args = (self.feats, self.ref_cam, self.src_cams, self.depth_min, self.depth_interval, depth_nums, interval_scales,
+                out_depth)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):   # first calls pack weights and set kernel attributes: keep them out of the capture
@@ -414,9 +417,11 @@ class Frontend(nn.Module):
         res[:, 1, 3, 1] = depth_interval
         return res
 
-    def depth_from_features(self, feats, ref_cam, src_cams, depth_min, depth_interval, depth_nums, interval_scales):
+    def depth_from_features(self, feats, ref_cam, src_cams, depth_min, depth_interval, depth_nums, interval_scales,
+                            out_depth=None):
         """feats[v][k]: channels-last [B,h_k,w_k,32] of view v (0 = reference) at stage k; ref_cam [B,2,4,4];
-        src_cams [B,S,2,4,4]; depth_min, depth_interval [B].  The cascade of frontend.py:66-98."""
+        src_cams [B,S,2,4,4]; depth_min, depth_interval [B].  The cascade of frontend.py:66-98.  `out_depth`: caller-owned
+        [B,h_3,w_3] buffer the last stage's regression kernel writes the final depth map into."""
         stages = (self.model.stage1, self.model.stage2, self.model.stage3)
         ests, probs, pairs = [], [], []
         start = depth_min.contiguous()
@@ -428,18 +433,20 @@ class Frontend(nn.Module):
                 # the reference reads self.interval_scales here, not the kwarg override (frontend.py:76-78)
                 start = (up - depth_nums[k] * depth_interval.view(-1, 1, 1) * self.interval_scales[k] / 2).contiguous()
             d, p, pr = stage.run(ref, [f[k] for f in feats[1:]], ref_cam, src_cams, depth_nums[k], start,
-                                 (depth_interval * interval_scales[k]).contiguous(), s_scale)
+                                 (depth_interval * interval_scales[k]).contiguous(), s_scale,
+                                 out_depth=out_depth if k == 2 else None)
             ests.append(d)
             probs.append(p)
             pairs.append(pr)
         return ests, probs, pairs
 
-    def graphed(self, feats, ref_cam, src_cams, depth_min, depth_interval, depth_nums, interval_scales):
+    def graphed(self, feats, ref_cam, src_cams, depth_min, depth_interval, depth_nums, interval_scales, out_depth=None):
         """CUDA-graph version of depth_from_features for inputs of these shapes: the ~90 launches of the three stages
         (and the PyTorch glue between them) replay as one graph.  Returns a callable taking the same tensors (copied
         into the captured buffers) and returning (ests, probs, pairs) -- the captured outputs, overwritten by the next
         replay."""
-        return _GraphedCascade(self, feats, ref_cam, src_cams, depth_min, depth_interval, depth_nums, interval_scales)
+        return _GraphedCascade(self, feats, ref_cam, src_cams, depth_min, depth_interval, depth_nums, interval_scales,
+                               out_depth=out_depth)
 
     def forward(self, imgs, K, R, t, depth_min, depth_max, reference_frame=0, **kwargs):
         depth_interval = (depth_max - depth_min) / 128
