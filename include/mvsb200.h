@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MVSB200_ABI_VERSION 4
+#define MVSB200_ABI_VERSION 5
 
 #define MVSB200_OK 0
 #define MVSB200_E_INVALID (-1)  /* bad argument / unsupported shape */
@@ -133,6 +133,13 @@ typedef struct {
     int transposed;     /* 1: ConvTranspose3d(k=3, stride=2, padding=1, output_padding=1) */
     int relu;
     int skip_mode;
+    int static_params;  /* 1: the caller guarantees that the layer's parameters (packed weights, scale, bias) were written
+                         * before the PREVIOUS launch on the stream was issued -- they are not outputs of the preceding
+                         * kernels.  The z-march engine is then launched as a programmatic dependent launch
+                         * (cudaLaunchAttributeProgrammaticStreamSerialization): its prologue (barrier init, TMEM
+                         * allocation, staging of the resident weights) overlaps the tail of the previous kernel and
+                         * only the reads of x / x2 / skip / the abs-max scalars wait for it (griddepcontrol.wait).
+                         * 0: ordinary stream-ordered launch. */
 } mvsb200_conv3d_desc;
 
 /* Output spatial size for a descriptor (PyTorch's rules). */

@@ -17,7 +17,11 @@ lib.mvsb200_debug_zm_profile.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_u
 dev = "cuda:0"
 torch.manual_seed(0)
 LAYERS = [("conv0", 32, 8, 1, False, (1, 192, 128, 160)), ("conv1", 8, 16, 2, False, (1, 192, 128, 160)),
-          ("conv2", 16, 16, 1, False, (1, 96, 64, 80)), ("conv9", 32, 16, 2, True, (1, 48, 32, 40)),
+          ("conv2", 16, 16, 1, False, (1, 96, 64, 80)), ("conv3", 16, 32, 2, False, (1, 96, 64, 80)),
+          ("conv4", 32, 32, 1, False, (1, 48, 32, 40)), ("conv5", 32, 64, 2, False, (1, 48, 32, 40)),
+          ("conv6h", 32, 64, 1, False, (1, 24, 16, 20)), ("conv7", 64, 32, 2, True, (1, 24, 16, 20)),
+          ("conv9", 32, 16, 2, True, (1, 48, 32, 40)),
+          ("tiny", 16, 16, 1, False, (1, 2, 7, 16)),   # one tile, two planes: the fixed cost of a launch (prologue + one pipeline pass)
           ("conv11", 16, 8, 2, True, (1, 96, 64, 80)),
           # Vis-MVSNet Reg blocks: 4 source views on the batch axis, stage 3 / stage 1 volumes
           ("vis8x8s3", 8, 8, 1, False, (4, 8, 256, 320)), ("vis8x8s1", 8, 8, 1, False, (4, 32, 64, 80)),

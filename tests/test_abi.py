@@ -27,14 +27,14 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in _declared():
         assert hasattr(lib, name), name
     assert set(_declared()) == set(_lib.SIGNATURES), "ctypes binding and header disagree"
-    assert _lib.load().mvsb200_abi_version() == _lib.ABI_VERSION == 4
+    assert _lib.load().mvsb200_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_struct_layouts_match_header():
     from wild_deep_mvs_b200 import _lib
     # 10 ints + 2*16 ints + one long long (8-byte aligned)
     assert ctypes.sizeof(_lib.CostVolumeDesc) == (10 + 32) * 4 + 8
-    assert ctypes.sizeof(_lib.Conv3dDesc) == 14 * 4
+    assert ctypes.sizeof(_lib.Conv3dDesc) == 15 * 4   # 14 shape / epilogue ints + static_params
 
 
 def test_argument_validation_without_gpu():

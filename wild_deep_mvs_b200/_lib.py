@@ -15,7 +15,7 @@ DEPTH_VALUES, DEPTH_VOLUME, DEPTH_START, DEPTH_START_MAP = 0, 1, 2, 3
 SKIP_NONE, SKIP_BEFORE_RELU, SKIP_AFTER_RELU = 0, 1, 2
 CONF_NONE, CONF_SUM4, CONF_WINDOW = 0, 1, 2
 PRECISION_3XTF32, PRECISION_TF32 = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class Mvsb200Error(RuntimeError):
@@ -36,7 +36,7 @@ class Conv3dDesc(ctypes.Structure):
                 ("Cin", ctypes.c_int), ("Cin2", ctypes.c_int), ("Cout", ctypes.c_int),
                 ("kd", ctypes.c_int), ("kh", ctypes.c_int), ("kw", ctypes.c_int),
                 ("stride", ctypes.c_int), ("transposed", ctypes.c_int),
-                ("relu", ctypes.c_int), ("skip_mode", ctypes.c_int)]
+                ("relu", ctypes.c_int), ("skip_mode", ctypes.c_int), ("static_params", ctypes.c_int)]
 
 
 _vp = ctypes.c_void_p

@@ -89,6 +89,7 @@ struct ZmParams {
     int tiles_x, tiles_y, nseg, zseg, ntiles, nstages;
     int x_cstride, x_coff;   // x may be a channel slice of a wider tensor: voxel pitch and first channel (floats)
     int profile;
+    int pdl;                 // launched as a programmatic dependent launch: x / x2 / skip / amax reads follow griddepcontrol.wait
 };
 
 // ---- small PTX helpers local to this engine -------------------------------------------------------------------
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
     constexpr int NPY = (MODE == ZM_S2) ? 2 : 1, NPX = NPY;
     constexpr int TEAM_WARPS = 4 * MT, NTEAMS = ZM_EPI_WARPS / TEAM_WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long s_full[MAXUB], s_empty[MAXUB], s_accfull[8], s_accempty[8], s_wbar;
+    __shared__ __align__(8) unsigned long long s_full[MAXUB], s_empty[MAXUB], s_accfull[8], s_accempty[8];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) unsigned long long s_planfull[ZM_NPLAN], s_planempty[ZM_NPLAN];
     __shared__ __align__(16) uint32_t s_plan[ZM_NPLAN][8];   // planner -> MMA issuer, see the planner warp
@@ -282,11 +283,32 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
     if (tid == 0) {
         for (int i = 0; i < NUB; i++) { mbar_init(smem_u32(&s_full[i]), ZM_PROD_GROUP / 32); mbar_init(smem_u32(&s_empty[i]), 1); }
         for (int i = 0; i < NACC; i++) { mbar_init(smem_u32(&s_accfull[i]), 1); mbar_init(smem_u32(&s_accempty[i]), TEAM_WARPS); }
-        mbar_init(smem_u32(&s_wbar), ZM_PROD_WARPS);
         for (int i = 0; i < ZM_NPLAN; i++) { mbar_init(smem_u32(&s_planfull[i]), 1); mbar_init(smem_u32(&s_planempty[i]), 1); }
         fence_mbar_init();
     }
     if (warp == ZM_EPI_WARPS + ZM_PROD_WARPS) tmem_alloc(smem_u32(&s_tmem), 512);
+    // Programmatic dependent launch: let the NEXT kernel of the stream be scheduled as soon as every CTA of this grid is
+    // resident (its CTAs need this SM's shared memory, so they start as this grid's CTAs retire and run their own
+    // prologue while the slower CTAs of this grid finish).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    // staged rows beyond the plane tile are only ever read by discarded GEMM rows; give them a defined value once
+    for (int i = tid; i < NUB * T::UNIT_BYTES / 16; i += ZM_THREADS) reinterpret_cast<uint4 *>(sA)[i] = make_uint4(0, 0, 0, 0);
+    if (warp >= ZM_EPI_WARPS && warp < ZM_EPI_WARPS + ZM_PROD_WARPS) {
+        // resident weights of this CTA: S1 one variant, S2 both x-parity variants, DECONV the variant of the CTA's
+        // output class (the grid is a multiple of 4 wide and the class is the fastest tile index, so every tile of a
+        // CTA has class blockIdx.x % 4).  Layer parameters do not depend on the previous kernel: staged before the wait.
+        const int ptid = tid - ZM_EPI_WARPS * 32;
+        const size_t wblock_halves = T::WBLOCK_BYTES / 2;
+        const __half *wsrc = p.wp + ZM_HEADER_HALVES + (size_t)nb * ((MODE == ZM_S1 ? 1 : 2) * nch * 9) * wblock_halves;
+        if (MODE == ZM_DECONV) wsrc += (size_t)(blockIdx.x & 1) * (nch * 9) * wblock_halves;
+        const uint4 *src = reinterpret_cast<const uint4 *>(wsrc);
+        uint4 *dst = reinterpret_cast<uint4 *>(sW);
+        const int n16 = wblocks * T::WBLOCK_BYTES / 16;
+        for (int i = ptid; i < n16; i += ZM_PROD_WARPS * 32) dst[i] = __ldg(src + i);
+    }
+    // everything below reads what the previous kernel(s) of the stream wrote (activations, their abs-max scalars)
+    if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     // operand scales
     float amax = __ldg(p.x_amax);
     if (p.x2) amax = fmaxf(amax, __ldg(p.x2_amax));
@@ -298,9 +320,6 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
         s_sc[tid] = unscale * ((p.scale && co < p.Cout) ? __ldg(p.scale + co) : 1.f);
         s_bi[tid] = (p.bias && co < p.Cout) ? __ldg(p.bias + co) : 0.f;
     }
-
-    // staged rows beyond the plane tile are only ever read by discarded GEMM rows; give them a defined value once
-    for (int i = tid; i < NUB * T::UNIT_BYTES / 16; i += ZM_THREADS) reinterpret_cast<uint4 *>(sA)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
@@ -453,21 +472,6 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
         // =================================== producer warps ===================================
         const int ptid = tid - ZM_EPI_WARPS * 32;
         const int group = ptid / ZM_PROD_GROUP, gt = ptid % ZM_PROD_GROUP;
-        // resident weights of this CTA: S1 one variant, S2 both x-parity variants, DECONV the variant of the CTA's
-        // output class (the grid is a multiple of 4 wide and the class is the fastest tile index, so every tile of a
-        // CTA has class blockIdx.x % 4)
-        {
-            const size_t wblock_halves = T::WBLOCK_BYTES / 2;
-            const __half *wsrc = p.wp + ZM_HEADER_HALVES + (size_t)nb * ((MODE == ZM_S1 ? 1 : 2) * nch * 9) * wblock_halves;
-            if (MODE == ZM_DECONV) wsrc += (size_t)(blockIdx.x & 1) * (nch * 9) * wblock_halves;
-            const uint4 *src = reinterpret_cast<const uint4 *>(wsrc);
-            uint4 *dst = reinterpret_cast<uint4 *>(sW);
-            const int n16 = wblocks * T::WBLOCK_BYTES / 16;
-            for (int i = ptid; i < n16; i += ZM_PROD_WARPS * 32) dst[i] = __ldg(src + i);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&s_wbar));
-        }
         constexpr int XV = EX * NPX;          // voxels of one staged row run (contiguous in x)
         constexpr int BATCH = 5;              // 16-byte loads in flight per thread
         int un = 0;               // units so far (all groups count all units)
@@ -579,8 +583,6 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
         // flow; only the tcgen05 instructions are predicated on the elected lane, which keeps descriptors in uniform
         // registers instead of a per-instruction leader-election loop.
         {
-            mbar_wait(smem_u32(&s_wbar), 0);
-            tc_fence_after_sync();
             const uint32_t a_hi = (uint32_t)(smem_desc(0, RA * 16, 128) >> 32), b_hi = (uint32_t)(smem_desc(0, NC * 16, 128) >> 32);
             const uint32_t a_lo0 = (uint32_t)smem_desc(smem_u32(sA), RA * 16, 128), b_lo0 = (uint32_t)smem_desc(smem_u32(sW), 0, 128);
             const uint32_t full0 = smem_u32(&s_full[0]), empty0 = smem_u32(&s_empty[0]);
@@ -908,7 +910,22 @@ static int launch_zm(ZmParams p, int sm_count, cudaStream_t st)
     if (int rc = ensure_dynamic_smem(k2_conv3d_zm_kernel<MODE, CT>, smem, "conv3d_zm")) return rc;
     dim3 grid((unsigned)(tiles < ctas ? tiles : ctas), (unsigned)nblocks, 1);
     if (MODE == ZM_DECONV && grid.x % 4) grid.x = (grid.x + 3) / 4 * 4;   // ntiles is a multiple of 4
-    k2_conv3d_zm_kernel<MODE, CT><<<grid, ZM_THREADS, smem, st>>>(p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(ZM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p.pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k2_conv3d_zm_kernel<MODE, CT>, p);
+    if (e != cudaSuccess) {
+        set_error("k2_conv3d_zm_kernel: %s", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return MVSB200_E_CUDA;
+    }
     return check_launch("k2_conv3d_zm_kernel");
 }
 
@@ -1018,6 +1035,7 @@ extern "C" int mvsb200_conv3d_zm_slice(const mvsb200_conv3d_desc *d, const float
     p.tiles_x = p.tiles_y = p.nseg = p.zseg = p.ntiles = p.nstages = 0;
     p.x_cstride = x_channels; p.x_coff = x_first_channel;
     p.profile = g_zm_prof_on;
+    p.pdl = d->static_params ? 1 : 0;
     int sm_count = 0, dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;

@@ -21,6 +21,8 @@ from . import _lib as L
 #   "fp32"    = the CUDA-core kernel (also runs every 1x1x1 / 2-D / Cin % 8 != 0 layer).
 ENGINES = ("zm", "tc", "tc_tf32", "fp32")
 DEFAULT_ENGINE = os.environ.get("MVSB200_K2_ENGINE", "zm")
+# programmatic dependent launch of the z-march engine (MVSB200_PDL=0 switches it off: A/B runs)
+PDL = os.environ.get("MVSB200_PDL", "1") != "0"
 
 
 def _stream():
@@ -344,6 +346,7 @@ class PackedConv:
         self._zm_packed = None
         self._c1_host = None
         self._halves = None
+        self._launches = 0   # z-march launches so far: from the second on, the packed parameters predate the stream's tail
 
     def halves(self):
         """The layer split over its input channels into two layers whose sum is this layer (z-march engine, layers whose
@@ -358,6 +361,7 @@ class PackedConv:
                 part.stride, part.transposed = self.stride, self.transposed
                 part.scale = self.scale
                 part._tc_packed = part._zm_packed = part._c1_host = part._halves = None
+                part._launches = 0
             a.bias, a.relu, a.skip_mode = self.bias, 0, self.skip_mode
             b.bias, b.relu, b.skip_mode = None, self.relu, L.SKIP_BEFORE_RELU
             self._halves = (a, b)
@@ -442,6 +446,10 @@ def conv3d(x, layer, x2=None, skip=None, engine=None, out=None, amax=None):
     if engine == "zm" and x.device == layer.w.device and lib.mvsb200_conv3d_zm_supported(ctypes.byref(desc)):
         if amax is None:
             amax = torch.zeros(1, device=x.device, dtype=torch.float32)
+        # parameters packed by an earlier call are not outputs of the kernels in front of this launch: the engine may
+        # overlap its prologue with them (programmatic dependent launch, see mvsb200.h)
+        desc.static_params = 1 if (PDL and layer._launches > 0) else 0
+        layer._launches += 1
         L.check(lib.mvsb200_conv3d_zm(ctypes.byref(desc), _ptr(x), _ptr(x2), _ptr(layer.zm_packed(desc)), _ptr(layer.scale),
                                       _ptr(layer.bias), _ptr(skip), _ptr(y), _ptr(absmax(x)),
                                       _ptr(absmax(x2)) if x2 is not None else None, _ptr(amax), _stream()), "mvsb200_conv3d_zm")
@@ -457,6 +465,9 @@ def conv3d(x, layer, x2=None, skip=None, engine=None, out=None, amax=None):
             if amax is None:
                 amax = torch.zeros(1, device=x.device, dtype=torch.float32)
             xa = _ptr(absmax(x))
+            half.static_params = 1 if (PDL and a._launches > 0 and b._launches > 0) else 0
+            a._launches += 1
+            b._launches += 1
             half.relu, half.skip_mode = a.relu, (a.skip_mode if skip is not None else L.SKIP_NONE)
             L.check(lib.mvsb200_conv3d_zm_slice(ctypes.byref(half), _ptr(x), C1, 0, None, _ptr(a.zm_packed(half)), _ptr(a.scale),
                                                 _ptr(a.bias), _ptr(skip), _ptr(y), xa, None, None, _stream()), "mvsb200_conv3d_zm_slice")
