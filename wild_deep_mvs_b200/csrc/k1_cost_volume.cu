@@ -199,6 +199,293 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_cost_volume_kernel(const K1P
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1-M, the depth-marching kernel (default for 1, 2 or 4 source views and C = 16 / 32).
+//
+// What bounds this path is the traffic from L1 into the register file (128 B / clk / SM): every (pixel, hypothesis, view)
+// needs four C-wide taps, 512 bytes for C = 32 (profiles/k1_r2_hypothesis_major.md).  Consecutive hypotheses of a pixel move
+// a fraction of a source pixel along the epipolar line, so the kernel above keeps the taps of a view in registers while the
+// 2x2 cell is unchanged -- but it walks the depth axis in chunks of 4 hypotheses with the views outside, and the forced
+// reload at the start of every (chunk, view) is the larger half of its loads.  Here a pixel is owned by L = C/4 lanes, each
+// holding FOUR channels of the 2x2 windows of ALL S views (S x 16 registers), and marches along a long depth segment with
+// the views inside: a window is re-loaded only when its cell really changes.  One hypothesis is accumulated at a time
+// (8 accumulator registers), finished and stored, so nothing else is live.
+// The channel-independent tap geometry of the 4 x S (hypothesis, view) pairs of a mini-chunk is computed once, spread
+// over the L lanes of the pixel -- a lane always serves the same view, whose constants it keeps in registers, with the
+// per-pixel part of the projection hoisted out of the depth loop -- and handed to the other lanes through shared memory
+// as packed-pair weights (two LDS.128 + one LDS.32 per (hypothesis, view) instead of five shuffles and four moves).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int K1M_THREADS = 128;
+constexpr int K1M_HC = 4;        // hypotheses per mini-chunk (geometry is shared per mini-chunk)
+constexpr int K1M_TAPF = 12;     // floats per packed tap record: {w00,w00,w01,w01, w10,w10,w11,w11, cell, -, -, -}
+
+struct K1MView {                 // per source view, staged in shared memory once per block
+    const float *base;           // first pixel of the view's map for batch item b
+    unsigned row_bytes;
+    int Hs, Ws;
+    float nx, rnx, ny, rny;
+    float wp[16];
+};
+
+template <int C, int GEOM, int AGG, int S>
+__global__ void __launch_bounds__(K1M_THREADS, 4) k1m_cost_volume_kernel(const K1Params p, const int seg)
+{
+    constexpr int L = C / 4;                // lanes per pixel, each owning 4 channels (one 16-byte vector per tap)
+    constexpr int PXW = 32 / L;             // x-adjacent pixels per warp
+    constexpr int R = L / S;                // hypotheses whose geometry one round of the L lanes covers
+    constexpr int ROUNDS = (K1M_HC + R - 1) / R;
+    constexpr int TH = K1M_THREADS / 32;
+    constexpr int PIXF = K1M_HC * S * K1M_TAPF + 4;   // + 16 bytes: the records of the pixels of a warp fall into different banks
+    static_assert(L % S == 0 && R >= 1 && (K1M_HC % R == 0 || R > K1M_HC), "views must divide the lanes of a pixel");
+    __shared__ K1MView s_view[S];
+    __shared__ __align__(16) float s_taps[TH][PXW][PIXF];
+
+    const int b = blockIdx.z;
+    const long long HW = (long long)p.H * p.W;
+    if (threadIdx.x < S) {
+        const int s = threadIdx.x;
+        K1MView &v = s_view[s];
+        v.Hs = p.src_h[s]; v.Ws = p.src_w[s];
+        v.base = p.src[s] + (long long)b * v.Hs * v.Ws * C;
+        v.row_bytes = (unsigned)(v.Ws * C) * 4u;
+        v.nx = p.nx[s]; v.rnx = p.rnx[s]; v.ny = p.ny[s]; v.rny = p.rny[s];
+#pragma unroll
+        for (int i = 0; i < 16; i++) v.wp[i] = p.warp[((long long)b * S + s) * 16 + i];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int sub = lane % L, pxi = lane / L;
+    const int sv = sub % S, h_off = sub / S;         // this lane's geometry duty: view sv, hypothesis h_off of every round
+    const int tiles_x = (p.W + PXW - 1) / PXW;
+    const int x_raw = (int)(blockIdx.x % tiles_x) * PXW + pxi;
+    const int y_raw = (int)(blockIdx.x / tiles_x) * TH + wrp;
+    const bool active = x_raw < p.W && y_raw < p.H;          // inactive lanes shadow a border pixel and store nothing
+    const int x = min(x_raw, p.W - 1), y = min(y_raw, p.H - 1);
+    const long long pix = (long long)y * p.W + x;
+    const int d_begin = (int)blockIdx.y * seg, d_end = min(p.D, d_begin + seg);
+
+    // ---- this lane's view: constants in registers, the per-pixel part of the projection hoisted ----
+    const K1MView &mv = s_view[sv];
+    const int Hs = mv.Hs, Ws = mv.Ws;
+    const float Wm1f = (float)(Ws - 1), Hm1f = (float)(Hs - 1);
+    const float nx = mv.nx, rnx = mv.rnx, ny = mv.ny, rny = mv.rny;
+    const float fx = (GEOM == MVSB200_GEOM_MVS) ? (float)x : (float)x + 0.5f, fy = (GEOM == MVSB200_GEOM_MVS) ? (float)y : (float)y + 0.5f;
+    const float ax = mv.wp[0] * fx + mv.wp[1] * fy + mv.wp[2];
+    const float ay = mv.wp[3] * fx + mv.wp[4] * fy + mv.wp[5];
+    const float az = mv.wp[6] * fx + mv.wp[7] * fy + mv.wp[8];
+    const float bx = mv.wp[9], by = mv.wp[10], bz = mv.wp[11];
+    const float np_ = (GEOM == MVSB200_GEOM_VIS) ? mv.wp[12] * fx + mv.wp[13] * fy + mv.wp[14] : 0.f;
+
+    const float interval = (p.depth_mode >= MVSB200_DEPTH_START) ? __ldg(p.interval + b) : 0.f;
+    const float temp = (AGG == MVSB200_AGG_SOFTMIN) ? __ldg(p.temp) : 0.f;
+    const float V = (float)(S + 1);
+    const float rV = 1.f / V, rV2 = 1.f / (V * V);
+    const float4 r4 = ldg4(p.ref + ((long long)b * HW + pix) * C + sub * 4);
+    const float2 r0 = make_float2(r4.x, r4.y), r1 = make_float2(r4.z, r4.w);
+    float vmax = 0.f;   // max |stored value| of this thread (abs-max tracking for the z-march conv engine)
+
+    // the 2x2 windows of the S views (this lane's 4 channels) and the cells they hold
+    float4 ta[S], tb[S], tc[S], td[S];
+    int cur[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) cur[s] = -2;
+
+    float *rec = &s_taps[wrp][pxi][0];
+    for (int k0 = d_begin; k0 < d_end; k0 += K1M_HC) {
+        __syncwarp();   // the previous mini-chunk's records have been read
+        // ---- geometry of the mini-chunk's (hypothesis, view) pairs, one per lane and round ----
+#pragma unroll
+        for (int rd = 0; rd < ROUNDS; rd++) {
+            const int k = rd * R + h_off;
+            if (R > K1M_HC && k >= K1M_HC) break;        // more lanes than (hypothesis, view) pairs: the rest sit the round out
+            const int d = min(k0 + k, p.D - 1);
+            const float dv = hypothesis(p.depth_mode, p.depth, interval, b, d, p.D, HW, pix);
+            float gx, gy;
+            if (GEOM == MVSB200_GEOM_MVS) {
+                const float qx = ax * dv + bx, qy = ay * dv + by, qz = az * dv + bz;
+                const float rz = rcp_nr(qz);
+                float px = div_by(qx, qz, rz), py = div_by(qy, qz, rz);
+                if (qz <= 0.f) px = -10.f, py = -10.f;
+                gx = clampf(div_by(px, nx, rnx) - 1.f, -10.f, 10.f);
+                gy = clampf(div_by(py, ny, rny) - 1.f, -10.f, 10.f);
+            } else {
+                const float dd = dv + 1e-9f;
+                const float f = div_by(np_, dd, rcp_nr(dd));
+                const float qx = ax - bx * f, qy = ay - by * f, qz = az - bz * f;
+                const float zc = fmaxf(qz, 1e-9f), rz = rcp_nr(zc);
+                float u = div_by(qx, zc, rz), w = div_by(qy, zc, rz);
+                if (!(qz > 0.f)) u = -10.f, w = -10.f;
+                gx = clampf(div_by(u, nx, rnx) * 2.f - 1.f, -1.1f, 1.1f);
+                gy = clampf(div_by(w, ny, rny) * 2.f - 1.f, -1.1f, 1.1f);
+            }
+            // grid_sample(bilinear, zeros, align_corners=True).  A sample whose 2x2 cell lies inside the map (the test is
+            // false for NaN coordinates) needs none of make_taps' border handling: its weights and cell directly.
+            PackedTaps t;
+            {
+                const float ix = ((gx + 1.f) / 2.f) * Wm1f, iy = ((gy + 1.f) / 2.f) * Hm1f;
+                if (ix >= 0.f && ix < Wm1f && iy >= 0.f && iy < Hm1f) {
+                    const float fx0 = floorf(ix), fy0 = floorf(iy);
+                    const float x1 = fx0 + 1.f, y1 = fy0 + 1.f;
+                    t.w00 = (x1 - ix) * (y1 - iy);
+                    t.w01 = (ix - fx0) * (y1 - iy);
+                    t.w10 = (x1 - ix) * (iy - fy0);
+                    t.w11 = (ix - fx0) * (iy - fy0);
+                    t.cell = (int)fy0 * Ws + (int)fx0;
+                } else {
+                    if (!(gx == gx) || !(gy == gy)) gx = gy = -10.f;   // NaN coordinates (degenerate cameras) sample nothing
+                    t = make_taps(gx, gy, Hs, Ws);
+                }
+            }
+            float *e = rec + (k * S + sv) * K1M_TAPF;
+            *reinterpret_cast<float4 *>(e) = make_float4(t.w00, t.w00, t.w01, t.w01);
+            *reinterpret_cast<float4 *>(e + 4) = make_float4(t.w10, t.w10, t.w11, t.w11);
+            e[8] = __int_as_float(t.cell);
+        }
+        __syncwarp();
+
+#pragma unroll
+        for (int k = 0; k < K1M_HC; k++) {
+            const int d = k0 + k;
+            if (d >= d_end) break;                       // warp-uniform
+            float2 m1a, m1b, m2a, m2b;
+            float sum_exp = 0.f;
+            if (AGG == MVSB200_AGG_VARIANCE || AGG == MVSB200_AGG_VARIANCE_MEAN) {
+                m1a = r0; m1b = r1;
+                m2a = __fmul2_rn(r0, r0); m2b = __fmul2_rn(r1, r1);
+            } else {
+                m1a = m1b = m2a = m2b = make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const float *e = rec + (k * S + s) * K1M_TAPF;
+                const float4 wn = *reinterpret_cast<const float4 *>(e);       // {w00, w00, w01, w01}
+                const float4 ws = *reinterpret_cast<const float4 *>(e + 4);   // {w10, w10, w11, w11}
+                const int cell = __float_as_int(e[8]);
+                if (cell != cur[s]) {
+                    const char *q0 = reinterpret_cast<const char *>(s_view[s].base + sub * 4) + (unsigned long long)(unsigned)cell * (C * 4);
+                    const char *q1 = q0 + s_view[s].row_bytes;
+                    ta[s] = ldg4(reinterpret_cast<const float *>(q0));
+                    tc[s] = ldg4(reinterpret_cast<const float *>(q1));
+                    tb[s] = ldg4(reinterpret_cast<const float *>(q0) + C);
+                    td[s] = ldg4(reinterpret_cast<const float *>(q1) + C);
+                    cur[s] = cell;
+                }
+                // accumulation order nw, ne, sw, se (ATen grid_sampler_2d)
+                const float2 p00 = make_float2(wn.x, wn.y), p01 = make_float2(wn.z, wn.w), p10 = make_float2(ws.x, ws.y), p11 = make_float2(ws.z, ws.w);
+                float2 wa = __fmul2_rn(make_float2(ta[s].x, ta[s].y), p00), wb = __fmul2_rn(make_float2(ta[s].z, ta[s].w), p00);
+                wa = __ffma2_rn(make_float2(tb[s].x, tb[s].y), p01, wa); wb = __ffma2_rn(make_float2(tb[s].z, tb[s].w), p01, wb);
+                wa = __ffma2_rn(make_float2(tc[s].x, tc[s].y), p10, wa); wb = __ffma2_rn(make_float2(tc[s].z, tc[s].w), p10, wb);
+                wa = __ffma2_rn(make_float2(td[s].x, td[s].y), p11, wa); wb = __ffma2_rn(make_float2(td[s].z, td[s].w), p11, wb);
+                if (AGG == MVSB200_AGG_VARIANCE || AGG == MVSB200_AGG_VARIANCE_MEAN) {
+                    m1a = __fadd2_rn(m1a, wa); m1b = __fadd2_rn(m1b, wb);
+                    m2a = __ffma2_rn(wa, wa, m2a); m2b = __ffma2_rn(wb, wb, m2b);
+                } else if (AGG == MVSB200_AGG_SOFTMIN) {
+                    const float2 m1 = make_float2(-1.f, -1.f);
+                    float2 da = __ffma2_rn(r0, m1, wa), db = __ffma2_rn(r1, m1, wb);   // w - r (the product is exact)
+                    da = __fmul2_rn(da, da); db = __fmul2_rn(db, db);
+                    float ssd = (da.x + da.y) + (db.x + db.y);
+#pragma unroll
+                    for (int m = L / 2; m >= 1; m >>= 1) ssd += __shfl_xor_sync(0xffffffffu, ssd, m);
+                    const float ex = expf(-temp * ssd);
+                    sum_exp += ex;
+                    const float2 ee = make_float2(ex, ex);
+                    m1a = __ffma2_rn(da, ee, m1a); m1b = __ffma2_rn(db, ee, m1b);
+                } else {  // GROUPCORR: a lane's 4 channels are one group; one output volume per source view
+                    float g = r0.x * wa.x;
+                    g += r0.y * wa.y;
+                    g += r1.x * wb.x;
+                    g += r1.y * wb.y;
+                    if (active) {
+                        vmax = fmaxf(vmax, fabsf(g));
+                        __stcs(p.out + s * p.out_view_stride + (((long long)b * p.D + d) * HW + pix) * L + sub, g);
+                    }
+                }
+            }
+            if (AGG != MVSB200_AGG_GROUPCORR && active) {
+                float2 oa, ob;
+                if (AGG == MVSB200_AGG_VARIANCE) {           // M2/V - M1^2/V^2 (models/MVSNet/model.py:134)
+                    const float2 nv2 = make_float2(-rV2, -rV2), v1 = make_float2(rV, rV);
+                    oa = __ffma2_rn(m2a, v1, __fmul2_rn(__fmul2_rn(m1a, m1a), nv2));
+                    ob = __ffma2_rn(m2b, v1, __fmul2_rn(__fmul2_rn(m1b, m1b), nv2));
+                } else if (AGG == MVSB200_AGG_VARIANCE_MEAN) {   // M2/V - (M1/V)^2 (CVP_MVSNet/models/net.py:152)
+                    const float2 v1 = make_float2(rV, rV), neg = make_float2(-1.f, -1.f);
+                    const float2 ma = __fmul2_rn(m1a, v1), mb = __fmul2_rn(m1b, v1);
+                    oa = __ffma2_rn(m2a, v1, __fmul2_rn(__fmul2_rn(ma, ma), neg));
+                    ob = __ffma2_rn(m2b, v1, __fmul2_rn(__fmul2_rn(mb, mb), neg));
+                } else {
+                    const float rden = 1.f / (sum_exp + 1e-6f);
+                    oa = __fmul2_rn(m1a, make_float2(rden, rden));
+                    ob = __fmul2_rn(m1b, make_float2(rden, rden));
+                }
+                vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(oa.x), fabsf(oa.y))), fmaxf(fabsf(ob.x), fabsf(ob.y)));
+                st4_stream(p.out + (((long long)b * p.D + d) * HW + pix) * C + sub * 4, make_float4(oa.x, oa.y, ob.x, ob.y));
+            }
+        }
+    }
+    if (p.out_amax) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, m));
+        if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned int *>(p.out_amax), __float_as_uint(vmax));
+    }
+}
+
+// Host: pixel tiles of (128 / C) x 4; the depth axis is cut into as few segments as still give the grid ~8 waves of blocks
+// (a segment starts with one forced window load per view, so longer is better).
+static bool k1m_supported(const mvsb200_cost_volume_desc *d)
+{
+    return (d->C == 16 || d->C == 32) && (d->S == 1 || d->S == 2 || d->S == 4);
+}
+static int k1m_grid(const mvsb200_cost_volume_desc *d, dim3 &grid, int &seg, const char *what)
+{
+    const int pxw = 32 / (d->C / 4), th = K1M_THREADS / 32;
+    int sms = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const long long tiles = (long long)((d->W + pxw - 1) / pxw) * ((d->H + th - 1) / th);
+    MVSB200_REQUIRE(tiles < (1ll << 31), "%s: image too large", what);
+    const int chunks = (d->D + K1M_HC - 1) / K1M_HC;
+    long long nseg = (32ll * sms + tiles * d->B - 1) / (tiles * d->B);
+    if (nseg > chunks) nseg = chunks;
+    if (nseg < 1) nseg = 1;
+    seg = (int)((chunks + nseg - 1) / nseg) * K1M_HC;
+    nseg = (d->D + seg - 1) / seg;
+    MVSB200_REQUIRE(d->B <= 65535 && nseg <= 65535, "%s: B or D too large", what);
+    grid = dim3((unsigned)tiles, (unsigned)nseg, (unsigned)d->B);
+    return MVSB200_OK;
+}
+
+template <int C, int GEOM, int S>
+static int launch_m_agg(const K1Params &p, int agg, dim3 grid, int seg, cudaStream_t st)
+{
+    switch (agg) {
+    case MVSB200_AGG_VARIANCE: k1m_cost_volume_kernel<C, GEOM, MVSB200_AGG_VARIANCE, S><<<grid, K1M_THREADS, 0, st>>>(p, seg); break;
+    case MVSB200_AGG_VARIANCE_MEAN: k1m_cost_volume_kernel<C, GEOM, MVSB200_AGG_VARIANCE_MEAN, S><<<grid, K1M_THREADS, 0, st>>>(p, seg); break;
+    case MVSB200_AGG_SOFTMIN: k1m_cost_volume_kernel<C, GEOM, MVSB200_AGG_SOFTMIN, S><<<grid, K1M_THREADS, 0, st>>>(p, seg); break;
+    case MVSB200_AGG_GROUPCORR: k1m_cost_volume_kernel<C, GEOM, MVSB200_AGG_GROUPCORR, S><<<grid, K1M_THREADS, 0, st>>>(p, seg); break;
+    default: set_error("build_cost_volume: unknown aggregation %d", agg); return MVSB200_E_INVALID;
+    }
+    return check_launch("k1m_cost_volume_kernel");
+}
+template <int C, int GEOM>
+static int launch_m_views(const K1Params &p, int S, int agg, dim3 grid, int seg, cudaStream_t st)
+{
+    if (S == 1) return launch_m_agg<C, GEOM, 1>(p, agg, grid, seg, st);
+    if (S == 2) return launch_m_agg<C, GEOM, 2>(p, agg, grid, seg, st);
+    return launch_m_agg<C, GEOM, 4>(p, agg, grid, seg, st);
+}
+template <int C>
+static int launch_m_geom(const K1Params &p, int geom, int agg, dim3 grid, int seg, cudaStream_t st)
+{
+    if (geom == MVSB200_GEOM_MVS) return launch_m_views<C, MVSB200_GEOM_MVS>(p, p.S, agg, grid, seg, st);
+    if (geom == MVSB200_GEOM_VIS) return launch_m_views<C, MVSB200_GEOM_VIS>(p, p.S, agg, grid, seg, st);
+    set_error("build_cost_volume: unknown geometry %d", geom);
+    return MVSB200_E_INVALID;
+}
+
 template <int C, int GEOM>
 static int launch_agg(const K1Params &p, int agg, dim3 grid, cudaStream_t st)
 {
@@ -246,7 +533,15 @@ extern "C" int mvsb200_build_cost_volume(const mvsb200_cost_volume_desc *d, cons
     p.warp = warp; p.depth = depth; p.interval = interval; p.temp = temp; p.out = out; p.out_amax = out_amax;
     p.out_view_stride = d->out_view_stride;
     p.B = d->B; p.S = d->S; p.D = d->D; p.H = d->H; p.W = d->W; p.depth_mode = d->depth_mode;
+    cudaStream_t st = (cudaStream_t)stream;
     dim3 grid;
+    static const bool use_v1 = [] { const char *e = getenv("MVSB200_K1"); return e && e[0] == 'v' && e[1] == '1'; }();   // A/B runs
+    if (!use_v1 && k1m_supported(d)) {   // depth-marching kernel
+        int seg = 0;
+        if (int rc = k1m_grid(d, grid, seg, "build_cost_volume")) return rc;
+        p.chunks = 0;
+        return d->C == 16 ? launch_m_geom<16>(p, d->geom, d->agg, grid, seg, st) : launch_m_geom<32>(p, d->geom, d->agg, grid, seg, st);
+    }
     if (int rc = k1_grid(p, d, grid, "build_cost_volume")) return rc;
 #ifdef MVSB200_K1_EXPERIMENTS
     {
@@ -254,7 +549,6 @@ extern "C" int mvsb200_build_cost_volume(const mvsb200_cost_volume_desc *d, cons
         p.dbg = e ? atoi(e) : 0;
     }
 #endif
-    cudaStream_t st = (cudaStream_t)stream;
     switch (d->C) {
     case 8: return launch_geom<8>(p, d->geom, d->agg, grid, st);
     case 16: return launch_geom<16>(p, d->geom, d->agg, grid, st);

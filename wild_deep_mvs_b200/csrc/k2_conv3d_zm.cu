@@ -28,6 +28,7 @@
 // the instruction count drops 3x (an N = 48 MMA costs ~80 cycles of issue/operand latency for 24 cycles of math).
 // The MMA is split only where the slot ring wraps and, in the first window of a plane, between the planes that
 // accumulate and the plane that starts (overwrite).
+#include <cuda.h>        // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -39,7 +40,9 @@ using namespace umma;
 
 constexpr int ZM_S1 = 0, ZM_S2 = 1, ZM_DECONV = 2;
 constexpr int ZM_EPI_WARPS = 8, ZM_PROD_WARPS = 9;   // 19 warps with the MMA and planner warps: at most 5 per scheduler, 96 registers each
-constexpr int ZM_THREADS = (ZM_EPI_WARPS + ZM_PROD_WARPS + 2) * 32;   // 608: + MMA issuer warp + planner warp
+constexpr int ZM_THREADS = (ZM_EPI_WARPS + ZM_PROD_WARPS + 3) * 32;   // 640: + MMA issuer warp + planner warp + TMA loader warp
+constexpr int ZM_WARP_MMA = ZM_EPI_WARPS + ZM_PROD_WARPS, ZM_WARP_PLAN = ZM_WARP_MMA + 1, ZM_WARP_LOAD = ZM_WARP_MMA + 2;
+constexpr int ZM_MAXRAW = 8;                                           // raw (fp32, TMA-written) unit buffers in the ring
 constexpr int ZM_NPLAN = 4;                                            // plans the planner may run ahead of the issuer
 constexpr int ZM_PROD_GROUP = 96;                                      // producer threads working on one unit
 constexpr int ZM_NGROUPS = ZM_PROD_WARPS * 32 / ZM_PROD_GROUP;         // units being filled concurrently
@@ -87,6 +90,9 @@ struct ZmParams {
     int Cin1, Cin2, Cout;
     int relu, skip_mode;
     int tiles_x, tiles_y, nseg, zseg, ntiles, nstages;
+    int g1, g2;              // chunks (of 8 channels) per producer unit for x and for x2 (one TMA box each)
+    int nraw, raw_bytes;     // ring of raw fp32 unit buffers the TMA loader fills
+    int unit_bytes;          // bytes of one converted unit buffer = max(g1, g2) * NPX stage buffers
     int x_cstride, x_coff;   // x may be a channel slice of a wider tensor: voxel pitch and first channel (floats)
     int profile;
     int pdl;                 // launched as a programmatic dependent launch: x / x2 / skip / amax reads follow griddepcontrol.wait
@@ -244,19 +250,36 @@ template <int MODE, int CT> __device__ __forceinline__ ZmTile zm_decode(const Zm
 // Pipeline stages of one input plane, in issue order:  for py: for chunk c: for px  (py, px: parity sub-grids of S2).
 // The producers fill them in UNITS of G chunks x NPX sub-grids = one contiguous run of G*32 bytes per voxel (the
 // whole 128-byte voxel record when Cin >= 32), so that a warp-level 16-byte load covers whole cache lines.
-__device__ __forceinline__ int zm_unit_chunks(int c, int nch1, int nch, int gmax)
+__device__ __forceinline__ int zm_unit_chunks(int c, int nch1, int g1, int g2)
 {
-    const int rem = (c < nch1 ? nch1 : nch) - c;   // chunks left in the tensor this chunk belongs to
-    int g = 1;
-    while (g * 2 <= gmax && g * 2 <= rem) g *= 2;
-    return g;
+    return c < nch1 ? g1 : g2;   // constant per tensor: one TMA box shape per tensor map
+}
+
+// ---- TMA (cp.async.bulk.tensor) --------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// One 5-D box {channels, x, y, z, b} of the fp32 volume -> dense shared memory [y][x][channels]; elements outside the
+// tensor (the conv's zero padding: x, y = -1 / W, H) arrive as zeros; completion is signalled on `bar` (transaction bytes).
+__device__ __forceinline__ void tma_load_5d(uint32_t dst_smem, const CUtensorMap *tm, uint32_t bar, int c, int x, int y, int z, int b)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c), "r"(x), "r"(y), "r"(z), "r"(b)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
 
 #define ZM_T0() (prof ? clock64() : 0ll)
 #define ZM_ACC(var, t0) do { if (prof) var += clock64() - (t0); } while (0)
 
 template <int MODE, int CT>
-__global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmParams p)
+__global__ void __launch_bounds__(ZM_THREADS, 1)
+k2_conv3d_zm_kernel(const ZmParams p, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_x2)
 {
     const bool prof = p.profile && blockIdx.x == 0 && blockIdx.y == 0;
     using T = ZmCfg<MODE, CT>;
@@ -266,6 +289,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
     constexpr int TEAM_WARPS = 4 * MT, NTEAMS = ZM_EPI_WARPS / TEAM_WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_full[MAXUB], s_empty[MAXUB], s_accfull[8], s_accempty[8];
+    __shared__ __align__(8) unsigned long long s_rawfull[ZM_MAXRAW], s_rawempty[ZM_MAXRAW];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) unsigned long long s_planfull[ZM_NPLAN], s_planempty[ZM_NPLAN];
     __shared__ __align__(16) uint32_t s_plan[ZM_NPLAN][8];   // planner -> MMA issuer, see the planner warp
@@ -278,22 +302,29 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
     const int wblocks = T::NPXL * nch * 9;
     unsigned char *sW = smem_raw;
     unsigned char *sA = sW + (size_t)wblocks * T::WBLOCK_BYTES;
-    float4 *sXall = reinterpret_cast<float4 *>(sA + (size_t)NUB * T::UNIT_BYTES);
+    float4 *sXall = reinterpret_cast<float4 *>(sA + (size_t)NUB * p.unit_bytes);
+    unsigned char *sRaw = reinterpret_cast<unsigned char *>(sXall) + (size_t)T::NTEAMS * T::XBUF * T::X_BYTES;
+    sRaw += (128u - (smem_u32(sRaw) & 127u)) & 127u;   // TMA destinations are 128-byte aligned (the plan reserves the slack)
 
     if (tid == 0) {
         for (int i = 0; i < NUB; i++) { mbar_init(smem_u32(&s_full[i]), ZM_PROD_GROUP / 32); mbar_init(smem_u32(&s_empty[i]), 1); }
         for (int i = 0; i < NACC; i++) { mbar_init(smem_u32(&s_accfull[i]), 1); mbar_init(smem_u32(&s_accempty[i]), TEAM_WARPS); }
+        for (int i = 0; i < p.nraw; i++) { mbar_init(smem_u32(&s_rawfull[i]), 1); mbar_init(smem_u32(&s_rawempty[i]), ZM_PROD_GROUP / 32); }
         for (int i = 0; i < ZM_NPLAN; i++) { mbar_init(smem_u32(&s_planfull[i]), 1); mbar_init(smem_u32(&s_planempty[i]), 1); }
         fence_mbar_init();
     }
-    if (warp == ZM_EPI_WARPS + ZM_PROD_WARPS) tmem_alloc(smem_u32(&s_tmem), 512);
+    if (warp == ZM_WARP_MMA) tmem_alloc(smem_u32(&s_tmem), 512);
+    if (warp == ZM_WARP_LOAD && lane == 0) {
+        tma_prefetch_desc(&tm_x);
+        if (p.x2) tma_prefetch_desc(&tm_x2);
+    }
     // Programmatic dependent launch: let the NEXT kernel of the stream be scheduled as soon as every CTA of this grid is
     // resident (its CTAs need this SM's shared memory, so they start as this grid's CTAs retire and run their own
     // prologue while the slower CTAs of this grid finish).
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // staged rows beyond the plane tile are only ever read by discarded GEMM rows; give them a defined value once
-    for (int i = tid; i < NUB * T::UNIT_BYTES / 16; i += ZM_THREADS) reinterpret_cast<uint4 *>(sA)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < NUB * p.unit_bytes / 16; i += ZM_THREADS) reinterpret_cast<uint4 *>(sA)[i] = make_uint4(0, 0, 0, 0);
     if (warp >= ZM_EPI_WARPS && warp < ZM_EPI_WARPS + ZM_PROD_WARPS) {
         // resident weights of this CTA: S1 one variant, S2 both x-parity variants, DECONV the variant of the CTA's
         // output class (the grid is a multiple of 4 wide and the class is the fastest tile index, so every tile of a
@@ -469,15 +500,22 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
             g_zm_prof[16] += clock64() - pe_tot; g_zm_prof[17] += pe_wait; g_zm_prof[18] += pe_bar; g_zm_prof[19] += pe_n;
         }
     } else if (warp < ZM_EPI_WARPS + ZM_PROD_WARPS) {
-        // =================================== producer warps ===================================
+        // =================================== converter warps ===================================
+        // The TMA loader warp streams raw fp32 units (one 5-D box each: G chunks x the haloed plane tile, zero padding
+        // filled in by the TMA unit) into the raw ring; a group of 96 threads turns a raw unit into the scaled fp16 h / l
+        // pieces in the canonical K-major layout the MMAs read.  The converters never touch global memory: their loads
+        // are conflict-free LDS.128 at a fixed stride, so a unit costs ~25 instructions per 16-byte piece and no
+        // memory latency -- the bytes in flight are set by the depth of the raw ring, not by the thread count.
         const int ptid = tid - ZM_EPI_WARPS * 32;
         const int group = ptid / ZM_PROD_GROUP, gt = ptid % ZM_PROD_GROUP;
         constexpr int XV = EX * NPX;          // voxels of one staged row run (contiguous in x)
-        constexpr int BATCH = 5;              // 16-byte loads in flight per thread
+        constexpr int NVOX = T::EY * XV;
+        constexpr int BATCH = 4;              // 16-byte pieces converted per loop trip (loads first, then the arithmetic)
         int un = 0;               // units so far (all groups count all units)
         int ub = 0;               // ring position of the current unit's buffer
         uint32_t uphase = 1;      // parity to wait for on its empty barrier (first pass: free)
         long long pp_tot = ZM_T0(), pp_wait = 0, pp_n = 0;
+        const uint32_t raw0 = smem_u32(sRaw);
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             const ZmTile t = zm_decode<MODE, CT>(p, tile);
             const int np = zm_nplanes<MODE>(t.nq);
@@ -486,50 +524,48 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                 if ((unsigned)gz >= (unsigned)p.D) continue;   // an all-zero plane contributes nothing: no stage at all
                 for (int py = 0; py < NPY; py++) {
                     for (int c0 = 0; c0 < nch;) {
-                        const int G = zm_unit_chunks(c0, nch1, nch, 4 / NPX);
+                        const int G = zm_unit_chunks(c0, nch1, p.g1, p.g2);
                         const int my_ub = ub;
                         const uint32_t my_phase = uphase;
                         if (++ub == NUB) { ub = 0; uphase ^= 1u; }
                         c0 += G;
-                        if ((un++ % ZM_NGROUPS) != group) continue;
-                        const float *src;
-                        int cs, cstride;
-                        const int cb = c0 - G;   // first chunk of this unit
-                        if (cb < nch1) { src = p.x; cs = cb * 8 + p.x_coff; cstride = p.x_cstride; }
-                        else { src = p.x2; cs = (cb - nch1) * 8; cstride = p.Cin2; }
+                        const int u = un++;
+                        if ((u % ZM_NGROUPS) != group) continue;
+                        const int rs = u % p.nraw;
+                        const uint32_t rphase = (uint32_t)(u / p.nraw) & 1u;
                         const int lgp = (G == 4) ? 3 : (G == 2 ? 2 : 1);     // log2(16-byte pieces per voxel)
-                        const int nvox = T::EY * XV;
                         // A thread's pieces are idx = gt + k * ZM_PROD_GROUP; the group size is a multiple of the pieces
                         // per voxel, so the piece within the voxel -- and with it the chunk, the 8-byte half and (S1,
-                        // DECONV) the stage buffer -- is the same for every k: everything but the voxel is hoisted.
+                        // DECONV) the stage buffer -- is the same for every k; the raw unit is dense [voxel][piece],
+                        // so piece idx sits at byte idx * 16.
                         const int piece = gt & ((1 << lgp) - 1);
                         const int vstep = ZM_PROD_GROUP >> lgp;
-                        const float *plane = src + ((long long)t.b * p.D + gz) * p.H * p.W * cstride + cs + piece * 4;
                         uint32_t dst_px[NPX];                                  // shared address of row 0 in the stage(s) of this piece
 #pragma unroll
                         for (int px = 0; px < NPX; px++)
-                            dst_px[px] = smem_u32(sA) + my_ub * T::UNIT_BYTES + ((piece >> 1) * NPX + px) * T::STAGE_BYTES + (piece & 1) * 8;
-                        const int ybase = (MODE == ZM_S1) ? t.y0 - 1 : (MODE == ZM_S2 ? 2 * t.y0 - 1 + py : t.y0);
-                        const int xbase = (MODE == ZM_S1) ? t.x0 - 1 : (MODE == ZM_S2 ? 2 * t.x0 - 1 : t.x0);
-                        const unsigned rowpitch = (unsigned)p.W * cstride;
-                        // batch of BATCH 16-byte pieces per thread: global -> registers
-                        auto load_batch = [&](int v0, float4 (&v)[BATCH]) {
+                            dst_px[px] = smem_u32(sA) + my_ub * p.unit_bytes + ((piece >> 1) * NPX + px) * T::STAGE_BYTES + (piece & 1) * 8;
+                        {
+                            const long long tq = ZM_T0();
+                            mbar_wait_relaxed(smem_u32(&s_rawfull[rs]), rphase);      // the TMA box has landed
+                            mbar_wait_relaxed(smem_u32(&s_empty[my_ub]), my_phase);   // the MMAs that read this unit buffer are done
+                            ZM_ACC(pp_wait, tq);
+                            pp_n++;
+                        }
+                        const uint32_t src0 = raw0 + rs * p.raw_bytes + gt * 16;
+                        for (int v0 = gt >> lgp, k0 = 0; v0 < NVOX; v0 += BATCH * vstep, k0 += BATCH) {
+                            float4 v[BATCH];
 #pragma unroll
                             for (int k = 0; k < BATCH; k++) {
-                                const int vx = v0 + k * vstep;
-                                const int lxv = vx % XV, ly = vx / XV;
-                                const int gy = ybase + ((MODE == ZM_S2) ? 2 * ly : ly), gx = xbase + lxv;
                                 v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (vx < nvox && (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W)
-                                    v[k] = ldg4(plane + ((unsigned)gy * rowpitch + (unsigned)gx * cstride));
+                                if (v0 + k * vstep < NVOX)
+                                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                                 : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w)
+                                                 : "r"(src0 + (k0 + k) * (ZM_PROD_GROUP * 16)));
                             }
-                        };
-                        // registers -> scaled fp16 h / l pieces -> the stage buffers of the unit
-                        auto store_batch = [&](int v0, const float4 (&v)[BATCH]) {
 #pragma unroll
                             for (int k = 0; k < BATCH; k++) {
                                 const int vx = v0 + k * vstep;
-                                if (vx >= nvox) break;
+                                if (vx >= NVOX) break;
                                 const int lxv = vx % XV, ly = vx / XV;
                                 const int px = (NPX == 2) ? (lxv & 1) : 0, lx = (NPX == 2) ? (lxv >> 1) : lxv;
                                 const float f0 = v[k].x * sx, f1 = v[k].y * sx, f2 = v[k].z * sx, f3 = v[k].w * sx;
@@ -542,37 +578,52 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                                 asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + RA * 16), "r"(*reinterpret_cast<const uint32_t *>(&l01)),
                                              "r"(*reinterpret_cast<const uint32_t *>(&l23)) : "memory");
                             }
-                        };
-                        // two register batches in flight: the loads of batch b+1 are issued before batch b is converted
-                        const int STEP = BATCH * vstep;
-                        const int v00 = gt >> lgp;
-                        float4 va[BATCH], vb[BATCH];
-                        load_batch(v00, va);
-                        if (v00 + STEP < nvox) load_batch(v00 + STEP, vb);
-                        // the unit's buffer must have been released by the MMAs that read it
-                        {
-                            const long long tq = ZM_T0();
-                            mbar_wait_relaxed(smem_u32(&s_empty[my_ub]), my_phase);
-                            ZM_ACC(pp_wait, tq);
-                            pp_n++;
-                        }
-                        for (int v0 = v00; v0 < nvox; v0 += 2 * STEP) {
-                            store_batch(v0, va);
-                            if (v0 + 2 * STEP < nvox) load_batch(v0 + 2 * STEP, va);
-                            if (v0 + STEP < nvox) {
-                                store_batch(v0 + STEP, vb);
-                                if (v0 + 3 * STEP < nvox) load_batch(v0 + 3 * STEP, vb);
-                            }
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&s_full[my_ub]));
+                        if (lane == 0) {
+                            mbar_arrive(smem_u32(&s_rawempty[rs]));   // raw slot read: the loader may refill it
+                            mbar_arrive(smem_u32(&s_full[my_ub]));    // converted unit ready for the MMAs
+                        }
                     }
                 }
             }
         }
         if (prof && ptid == 0) { g_zm_prof[8] += clock64() - pp_tot; g_zm_prof[9] += pp_wait; g_zm_prof[10] += pp_n; }
-    } else if (warp == ZM_EPI_WARPS + ZM_PROD_WARPS) {
+    } else if (warp == ZM_WARP_LOAD) {
+        // =================================== TMA loader ===================================
+        // One thread walks the units in pipeline order and keeps the raw ring full: wait until the converters have
+        // drained a slot, post the transaction size on its "full" barrier and issue the box load.
+        if (lane == 0) {
+            constexpr int XV = EX * NPX;
+            const uint32_t raw0 = smem_u32(sRaw);
+            int u = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                const ZmTile t = zm_decode<MODE, CT>(p, tile);
+                const int np = zm_nplanes<MODE>(t.nq);
+                const int xbase = (MODE == ZM_S1) ? t.x0 - 1 : (MODE == ZM_S2 ? 2 * t.x0 - 1 : t.x0);
+                for (int pl = 0; pl < np; pl++) {
+                    const int gz = zm_zin<MODE>(t.zb, pl);
+                    if ((unsigned)gz >= (unsigned)p.D) continue;
+                    for (int py = 0; py < NPY; py++) {
+                        const int ybase = (MODE == ZM_S1) ? t.y0 - 1 : (MODE == ZM_S2 ? 2 * t.y0 - 1 + py : t.y0);
+                        for (int c0 = 0; c0 < nch;) {
+                            const int G = zm_unit_chunks(c0, nch1, p.g1, p.g2);
+                            const int rs = u % p.nraw;
+                            mbar_wait_relaxed(smem_u32(&s_rawempty[rs]), ((uint32_t)(u / p.nraw) & 1u) ^ 1u);   // first pass: free
+                            const uint32_t bar = smem_u32(&s_rawfull[rs]);
+                            mbar_arrive_expect_tx(bar, (uint32_t)(G * 32 * T::EY * XV));
+                            if (c0 < nch1) tma_load_5d(raw0 + rs * p.raw_bytes, &tm_x, bar, c0 * 8, xbase, ybase, gz, t.b);
+                            else tma_load_5d(raw0 + rs * p.raw_bytes, &tm_x2, bar, (c0 - nch1) * 8, xbase, ybase, gz, t.b);
+                            c0 += G;
+                            u++;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == ZM_WARP_MMA) {
         // =================================== MMA issuer ===================================
         // ONE thread issues every MMA of the CTA and the queue between it and the tensor core is shallow, so whatever
         // this warp does besides issuing idles the tensor core.  It therefore does nothing else: which accumulator slots
@@ -623,7 +674,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                         for (int py = 0; py < NPY; py++) {
                             const int vy = (MODE == ZM_S2) ? py : vy_cls;
                             for (int c0 = 0; c0 < nch;) {
-                                const int G = zm_unit_chunks(c0, nch1, nch, 4 / NPX);
+                                const int G = zm_unit_chunks(c0, nch1, p.g1, p.g2);
                                 tq = ZM_T0();
                                 mbar_wait(full0 + ub * 8, uphase);
                                 ZM_ACC(pm_full, tq);
@@ -631,7 +682,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
                                 tc_fence_after_sync();
                                 tq = ZM_T0();
                                 if (elect_one_sync()) {
-                                    uint32_t a_lo = a_lo0 + ub * (T::UNIT_BYTES / 16);
+                                    uint32_t a_lo = a_lo0 + ub * (p.unit_bytes / 16);
                                     for (int cc = 0; cc < G; cc++) {
 #pragma unroll
                                         for (int px = 0; px < NPX; px++, a_lo += T::STAGE_BYTES / 16) {
@@ -689,7 +740,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp == ZM_WARP_PLAN) {
         // =================================== planner warp ===================================
         // Runs ahead of the MMA issuer (ring of ZM_NPLAN plans).  Per input plane: the output planes q = qf + i,
         // i in [i0, i1), it feeds sit in consecutive accumulator ring positions; cut them into runs of adjacent TMEM
@@ -754,7 +805,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k2_conv3d_zm_kernel(const ZmPar
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == ZM_EPI_WARPS + ZM_PROD_WARPS) tmem_dealloc(tmem, 512);
+    if (warp == ZM_WARP_MMA) tmem_dealloc(tmem, 512);
 }
 
 // ---- weight packing ----------------------------------------------------------------------------------------------
@@ -837,27 +888,103 @@ static int zm_mode(const mvsb200_conv3d_desc *d) { return d->transposed ? ZM_DEC
 static int zm_ct(const mvsb200_conv3d_desc *d) { return d->Cout == 8 ? 8 : 16; }
 static int zm_nvar(int mode) { return mode == ZM_S1 ? 1 : 2; }
 
-template <int MODE, int CT> static size_t zm_smem_bytes(int nch, int nst)
+// ---- shared-memory plan ---------------------------------------------------------------------------------------------
+// resident weights | NUB converted unit buffers | x-shift exchange buffers | NRAW raw (TMA) unit buffers
+struct ZmDims {
+    int npx, npxl, ey, xv, stage_bytes, wblock_bytes, x_bytes_total;
+};
+template <int MODE, int CT> static ZmDims zm_dims_of()
 {
     using T = ZmCfg<MODE, CT>;
-    return (size_t)T::NPXL * nch * 9 * T::WBLOCK_BYTES + (size_t)nst * T::UNIT_BYTES + (size_t)T::NTEAMS * T::XBUF * T::X_BYTES;
+    ZmDims d;
+    d.npx = (MODE == ZM_S2) ? 2 : 1;
+    d.npxl = T::NPXL;
+    d.ey = T::EY;
+    d.xv = T::EX * d.npx;
+    d.stage_bytes = T::STAGE_BYTES;
+    d.wblock_bytes = T::WBLOCK_BYTES;
+    d.x_bytes_total = T::NTEAMS * T::XBUF * T::X_BYTES;
+    return d;
+}
+static ZmDims zm_dims(int mode, int ct)
+{
+    if (mode == ZM_S1) return ct == 8 ? zm_dims_of<ZM_S1, 8>() : zm_dims_of<ZM_S1, 16>();
+    if (mode == ZM_S2) return ct == 8 ? zm_dims_of<ZM_S2, 8>() : zm_dims_of<ZM_S2, 16>();
+    return ct == 8 ? zm_dims_of<ZM_DECONV, 8>() : zm_dims_of<ZM_DECONV, 16>();
 }
 
-// number of unit buffers that fit next to the resident weights (0: the layer does not fit this engine)
-template <int MODE, int CT> static int zm_stages(int nch)
+struct ZmPlan {
+    int g1, g2, nub, nraw, raw_bytes, unit_bytes;
+    size_t smem;   // dynamic shared memory; 0: the layer does not fit this engine
+};
+// Chunks per unit are a power of two that divides the tensor's chunk count (one TMA box shape per tensor), as large as
+// the shared memory left by the resident weights allows; then the raw ring -- the bytes in flight from HBM -- gets
+// what is left (up to ZM_MAXRAW slots), the converted ring one more buffer if there is room.
+static ZmPlan zm_plan(int mode, int ct, int nch1, int nch2)
 {
-    // At least as many buffers as producer groups: a group waits on the "empty" barrier of a buffer by phase parity,
-    // which is only unambiguous if it can never be two completions behind (true for nst >= ZM_NGROUPS).
-    for (int nst = 6; nst >= ZM_NGROUPS; nst--)
-        if (zm_smem_bytes<MODE, CT>(nch, nst) + 2048 <= 227 * 1024) return nst;
-    return 0;
+    const ZmDims d = zm_dims(mode, ct);
+    ZmPlan pl = {};
+    const size_t limit = 227 * 1024 - 2560;   // static shared memory (barriers, plans, scale / bias) + alignment slack
+    const size_t fixed = (size_t)d.npxl * (nch1 + nch2) * 9 * d.wblock_bytes + d.x_bytes_total;
+    auto pow2_div = [](int n, int gmax) { int g = 1; while (g * 2 <= gmax && n % (g * 2) == 0) g *= 2; return g; };
+    for (int gmax = 4 / d.npx; gmax >= 1; gmax /= 2) {
+        const int g1 = pow2_div(nch1, gmax), g2 = nch2 ? pow2_div(nch2, gmax) : 0, gm = g1 > g2 ? g1 : g2;
+        const size_t unit = (size_t)gm * d.npx * d.stage_bytes;
+        const size_t raw = ((size_t)gm * 32 * d.ey * d.xv + 127) / 128 * 128;
+        // at least as many buffers as converter groups in either ring: a group waits on an "empty" barrier by phase
+        // parity, which is only unambiguous if it can never be two completions behind
+        if (fixed + ZM_NGROUPS * (unit + raw) > limit) continue;
+        int nub = ZM_NGROUPS, nraw = ZM_NGROUPS;
+        auto fits = [&](int a, int b) { return fixed + a * unit + b * raw <= limit; };
+        while (nraw < 6 && fits(nub, nraw + 1)) nraw++;
+        if (nub < 4 && fits(nub + 1, nraw)) nub++;
+        while (nraw < ZM_MAXRAW && fits(nub, nraw + 1)) nraw++;
+        pl.g1 = g1; pl.g2 = g2; pl.nub = nub; pl.nraw = nraw;
+        pl.raw_bytes = (int)raw; pl.unit_bytes = (int)unit;
+        pl.smem = fixed + nub * unit + nraw * raw + 128;   // + slack to align the raw ring to 128 bytes
+        return pl;
+    }
+    return pl;
 }
 
-static int zm_stages_for(int mode, int ct, int nch)
+// ---- tensor maps ------------------------------------------------------------------------------------------------------
+typedef CUresult (*ZmEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static ZmEncodeTiled zm_encode_fn()
 {
-    if (mode == ZM_S1) return ct == 8 ? zm_stages<ZM_S1, 8>(nch) : zm_stages<ZM_S1, 16>(nch);
-    if (mode == ZM_S2) return ct == 8 ? zm_stages<ZM_S2, 8>(nch) : zm_stages<ZM_S2, 16>(nch);
-    return ct == 8 ? zm_stages<ZM_DECONV, 8>(nch) : zm_stages<ZM_DECONV, 16>(nch);
+    static ZmEncodeTiled fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return reinterpret_cast<ZmEncodeTiled>(f);
+    }();
+    return fn;
+}
+// fp32 volume [B, D, H, W, cstride] (channels [coff, coff + C) of every voxel) as a rank-5 tensor {C, W, H, D, B};
+// box = {g * 8 channels, xv voxels, ey rows (every ystep-th row), 1, 1}; out-of-range elements read as zero.
+static int zm_make_tmap(CUtensorMap *tm, const float *x, int coff, int C, int cstride, int B, int D, int H, int W, int g, int xv, int ey,
+                        int ystep, const char *what)
+{
+    ZmEncodeTiled enc = zm_encode_fn();
+    if (!enc) {
+        set_error("%s: cuTensorMapEncodeTiled is not available from this driver", what);
+        return MVSB200_E_CUDA;
+    }
+    const cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+    const cuuint64_t vox = (cuuint64_t)cstride * 4;
+    const cuuint64_t gstr[4] = {vox, vox * W, vox * W * H, vox * W * H * D};
+    const cuuint32_t box[5] = {(cuuint32_t)(g * 8), (cuuint32_t)xv, (cuuint32_t)(ey * ystep), 1, 1};
+    const cuuint32_t estr[5] = {1, 1, (cuuint32_t)ystep, 1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(x + coff), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("%s: cuTensorMapEncodeTiled failed (%d) for a [%d,%d,%d,%d,%d/%d] volume, box %dx%dx%d", what, (int)r, B, D, H, W, C, cstride,
+                  g * 8, xv, ey);
+        return MVSB200_E_INVALID;
+    }
+    return MVSB200_OK;
 }
 
 static bool zm_shape_ok(const mvsb200_conv3d_desc *d)
@@ -866,16 +993,25 @@ static bool zm_shape_ok(const mvsb200_conv3d_desc *d)
     if (!(d->kd == 3 && d->kh == 3 && d->kw == 3 && d->Cin % 8 == 0 && d->Cin2 % 8 == 0 && cin >= 8)) return false;
     if (!(d->Cout == 8 || (d->Cout % 16 == 0 && d->Cout <= 256))) return false;
     if (!((d->stride == 1 && !d->transposed) || d->stride == 2)) return false;
-    return zm_stages_for(zm_mode(d), zm_ct(d), cin / 8) > 0;
+    return zm_plan(zm_mode(d), zm_ct(d), d->Cin / 8, d->Cin2 / 8).smem > 0;
 }
 
 template <int MODE, int CT>
 static int launch_zm(ZmParams p, int sm_count, cudaStream_t st)
 {
     using T = ZmCfg<MODE, CT>;
-    const int nch = (p.Cin1 + p.Cin2) / 8;
-    p.nstages = zm_stages<MODE, CT>(nch);
-    const size_t smem = zm_smem_bytes<MODE, CT>(nch, p.nstages);
+    const ZmPlan plan = zm_plan(MODE, CT, p.Cin1 / 8, p.Cin2 / 8);
+    p.nstages = plan.nub;
+    p.g1 = plan.g1; p.g2 = plan.g2 ? plan.g2 : 1;
+    p.nraw = plan.nraw; p.raw_bytes = plan.raw_bytes; p.unit_bytes = plan.unit_bytes;
+    const size_t smem = plan.smem;
+    const ZmDims dm = zm_dims(MODE, CT);
+    CUtensorMap tm_x, tm_x2;
+    const int ystep = (MODE == ZM_S2) ? 2 : 1;
+    if (int rc = zm_make_tmap(&tm_x, p.x, p.x_coff, p.Cin1, p.x_cstride, p.B, p.D, p.H, p.W, plan.g1, dm.xv, dm.ey, ystep, "conv3d_zm")) return rc;
+    tm_x2 = tm_x;
+    if (p.x2)
+        if (int rc = zm_make_tmap(&tm_x2, p.x2, 0, p.Cin2, p.Cin2, p.B, p.D, p.H, p.W, plan.g2, dm.xv, dm.ey, ystep, "conv3d_zm")) return rc;
     const int nzt = (MODE == ZM_DECONV) ? p.D : p.Do, ny = (MODE == ZM_DECONV) ? p.H : p.Ho, nx = (MODE == ZM_DECONV) ? p.W : p.Wo;
     p.tiles_y = (ny + T::TY - 1) / T::TY;
     p.tiles_x = (nx + T::TX - 1) / T::TX;
@@ -920,7 +1056,7 @@ static int launch_zm(ZmParams p, int sm_count, cudaStream_t st)
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = p.pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k2_conv3d_zm_kernel<MODE, CT>, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k2_conv3d_zm_kernel<MODE, CT>, p, tm_x, tm_x2);
     if (e != cudaSuccess) {
         set_error("k2_conv3d_zm_kernel: %s", cudaGetErrorString(e));
         (void)cudaGetLastError();
@@ -1033,6 +1169,7 @@ extern "C" int mvsb200_conv3d_zm_slice(const mvsb200_conv3d_desc *d, const float
     p.Cin1 = d->Cin; p.Cin2 = d->Cin2; p.Cout = d->Cout;
     p.relu = d->relu; p.skip_mode = d->skip_mode;
     p.tiles_x = p.tiles_y = p.nseg = p.zseg = p.ntiles = p.nstages = 0;
+    p.g1 = p.g2 = p.nraw = p.raw_bytes = p.unit_bytes = 0;
     p.x_cstride = x_channels; p.x_coff = x_first_channel;
     p.profile = g_zm_prof_on;
     p.pdl = d->static_params ? 1 : 0;
