@@ -89,7 +89,7 @@ struct ZmParams {
     int B, D, H, W, Do, Ho, Wo;
     int Cin1, Cin2, Cout;
     int relu, skip_mode;
-    int tiles_x, tiles_y, nseg, zseg, ntiles, nstages;
+    int tiles_x, tiles_y, per, total, nstages;   // work decomposition: see ZmWalk
     int g1, g2;              // chunks (of 8 channels) per producer unit for x and for x2 (one TMA box each)
     int nraw, raw_bytes;     // ring of raw fp32 unit buffers the TMA loader fills
     int unit_bytes;          // bytes of one converted unit buffer = max(g1, g2) * NPX stage buffers
@@ -226,24 +226,43 @@ struct ZmTile {
     int b, zb, nq, y0, x0, cls;
 };
 
-template <int MODE, int CT> __device__ __forceinline__ ZmTile zm_decode(const ZmParams &p, int tile)
+// Work decomposition.  The (tile column, z) index space of a layer -- columns = (x tile, y tile, batch item), z counted in
+// output planes (S1, S2) or input planes (DECONV) -- is flattened column-major and cut into EQUAL contiguous runs, one per
+// CTA (per output-parity class for DECONV: class = blockIdx.x % 4, so the class and with it the resident weight variant is
+// constant per CTA).  A run is walked as one z-march per column it touches (each with its own halo planes).  Every CTA
+// gets the same number of planes whatever the ratio of columns to SMs (a volume of 50 columns on 148 SMs used to run 100
+// CTAs x 48 planes; it now runs 148 x 33).  All warp roles of a CTA walk the same sequence.
+struct ZmWalk {
+    int flat, hi, cls;
+};
+template <int MODE> __device__ __forceinline__ ZmWalk zm_walk_begin(const ZmParams &p)
+{
+    ZmWalk w;
+    int c = blockIdx.x;
+    w.cls = 0;
+    if (MODE == ZM_DECONV) { w.cls = c & 3; c >>= 2; }
+    w.flat = c * p.per;
+    w.hi = min(w.flat + p.per, p.total);
+    return w;
+}
+template <int MODE, int CT> __device__ __forceinline__ bool zm_walk_next(const ZmParams &p, ZmWalk &w, ZmTile &t)
 {
     using T = ZmCfg<MODE, CT>;
-    ZmTile t;
-    t.cls = 0;
-    if (MODE == ZM_DECONV) { t.cls = tile & 3; tile >>= 2; }
-    const int tx = tile % p.tiles_x; tile /= p.tiles_x;
-    const int ty = tile % p.tiles_y; tile /= p.tiles_y;
-    const int sg = tile % p.nseg;
-    t.b = tile / p.nseg;
+    if (w.flat >= w.hi) return false;
+    const int ztot = (MODE == ZM_DECONV) ? p.D : p.Do;
+    int col = w.flat / ztot;
+    const int z = w.flat - col * ztot;
+    const int n = min(ztot - z, w.hi - w.flat);
+    w.flat += n;
+    const int tx = col % p.tiles_x; col /= p.tiles_x;
+    const int ty = col % p.tiles_y;
+    t.b = col / p.tiles_y;
     t.x0 = tx * T::TX;
     t.y0 = ty * T::TY;
-    // segments are counted in output planes (S1, S2) or input planes (DECONV)
-    const int ztot = (MODE == ZM_DECONV) ? p.D : p.Do;
-    t.zb = sg * p.zseg;
-    const int n = min(p.zseg, ztot - t.zb);
+    t.zb = z;
     t.nq = (MODE == ZM_DECONV) ? 2 * n : n;
-    return t;
+    t.cls = w.cls;
+    return true;
 }
 
 
@@ -371,8 +390,8 @@ k2_conv3d_zm_kernel(const ZmParams p, const __grid_constant__ CUtensorMap tm_x, 
         float vmax = 0.f;
         int qg = 0;
         long long pe_tot = ZM_T0(), pe_wait = 0, pe_bar = 0, pe_n = 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            const ZmTile t = zm_decode<MODE, CT>(p, tile);
+        ZmTile t;
+        for (ZmWalk walk = zm_walk_begin<MODE>(p); zm_walk_next<MODE, CT>(p, walk, t);) {
             const int ry = (t.cls >> 1) & 1, rx = t.cls & 1;
             int oy = t.y0 + oy_l, ox = t.x0 + ox_l;
             bool ok_yx = oy_l < T::TY && ox_l < T::TX;
@@ -516,8 +535,8 @@ k2_conv3d_zm_kernel(const ZmParams p, const __grid_constant__ CUtensorMap tm_x, 
         uint32_t uphase = 1;      // parity to wait for on its empty barrier (first pass: free)
         long long pp_tot = ZM_T0(), pp_wait = 0, pp_n = 0;
         const uint32_t raw0 = smem_u32(sRaw);
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            const ZmTile t = zm_decode<MODE, CT>(p, tile);
+        ZmTile t;
+        for (ZmWalk walk = zm_walk_begin<MODE>(p); zm_walk_next<MODE, CT>(p, walk, t);) {
             const int np = zm_nplanes<MODE>(t.nq);
             for (int pl = 0; pl < np; pl++) {
                 const int gz = zm_zin<MODE>(t.zb, pl);
@@ -598,8 +617,8 @@ k2_conv3d_zm_kernel(const ZmParams p, const __grid_constant__ CUtensorMap tm_x, 
             constexpr int XV = EX * NPX;
             const uint32_t raw0 = smem_u32(sRaw);
             int u = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                const ZmTile t = zm_decode<MODE, CT>(p, tile);
+            ZmTile t;
+            for (ZmWalk walk = zm_walk_begin<MODE>(p); zm_walk_next<MODE, CT>(p, walk, t);) {
                 const int np = zm_nplanes<MODE>(t.nq);
                 const int xbase = (MODE == ZM_S1) ? t.x0 - 1 : (MODE == ZM_S2 ? 2 * t.x0 - 1 : t.x0);
                 for (int pl = 0; pl < np; pl++) {
@@ -644,8 +663,8 @@ k2_conv3d_zm_kernel(const ZmParams p, const __grid_constant__ CUtensorMap tm_x, 
             int pi = 0;              // plan ring position
             uint32_t pphase = 0;
             long long pm_tot = ZM_T0(), pm_full = 0, pm_acc = 0, pm_issue = 0, pm_n = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                const ZmTile t = zm_decode<MODE, CT>(p, tile);
+            ZmTile t;
+            for (ZmWalk walk = zm_walk_begin<MODE>(p); zm_walk_next<MODE, CT>(p, walk, t);) {
                 const int np = zm_nplanes<MODE>(t.nq);
                 const int vy_cls = (t.cls >> 1) & 1;
                 for (int pl = 0; pl < np; pl++) {
@@ -752,8 +771,8 @@ k2_conv3d_zm_kernel(const ZmParams p, const __grid_constant__ CUtensorMap tm_x, 
         uint32_t started = 0;    // bit per accumulator slot: the plane in it has received its first MMA
         int pi = 0;
         uint32_t pphase = 1;     // first pass over the plan ring: free
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            const ZmTile t = zm_decode<MODE, CT>(p, tile);
+        ZmTile t;
+        for (ZmWalk walk = zm_walk_begin<MODE>(p); zm_walk_next<MODE, CT>(p, walk, t);) {
             const int np = zm_nplanes<MODE>(t.nq);
             for (int pl = 0; pl < np; pl++) {
                 const int gz = zm_zin<MODE>(t.zb, pl);
@@ -1017,35 +1036,24 @@ static int launch_zm(ZmParams p, int sm_count, cudaStream_t st)
     p.tiles_x = (nx + T::TX - 1) / T::TX;
     const int nblocks = (p.Cout + CT - 1) / CT;
     const int classes = (MODE == ZM_DECONV) ? 4 : 1;
-    const long long base = (long long)p.tiles_x * p.tiles_y * p.B * classes;
     int ctas = sm_count / nblocks;
-    if (ctas < 1) ctas = 1;
-    if (MODE == ZM_DECONV) ctas = ctas / 4 * 4 > 0 ? ctas / 4 * 4 : 4;   // tile % 4 (the class) must be constant per CTA
-    // segment length: trade the z halo of a segment against filling all CTAs for a whole number of rounds
-    const int halo = (MODE == ZM_S1) ? 2 : 1;
-    double best = -1.0;
-    int best_nseg = 1;
-    for (int nseg = 1; nseg <= nzt; nseg++) {
-        const int zseg = (nzt + nseg - 1) / nseg;
-        if ((long long)(nseg - 1) * zseg >= nzt) continue;
-        const long long tiles = base * nseg;
-        const long long rounds = (tiles + ctas - 1) / ctas;
-        const double eff = (double)tiles / (double)(rounds * ctas) * (double)zseg / (double)(zseg + halo) *
-                           (1.0 - 0.02 * (double)rounds / (double)(rounds + 8));
-        if (eff > best) { best = eff; best_nseg = nseg; }
-        if (tiles > 64ll * ctas) break;
-    }
-    p.nseg = best_nseg;
-    p.zseg = (nzt + best_nseg - 1) / best_nseg;
-    const long long tiles = base * p.nseg;
-    if (tiles >= (1ll << 30)) {
+    if (ctas < classes) ctas = classes;
+    ctas = ctas / classes * classes;                    // CTAs per class x classes (blockIdx.x % 4 is the class)
+    const long long total = (long long)p.tiles_x * p.tiles_y * p.B * nzt;   // planes of one class
+    if (total * classes >= (1ll << 30)) {
         set_error("conv3d_zm: volume too large");
         return MVSB200_E_INVALID;
     }
-    p.ntiles = (int)tiles;
+    // equal runs of planes per CTA; a run shorter than 4 planes would spend most of its time on the z halo and the pipeline
+    // fill of its segment, so small volumes use fewer CTAs instead
+    long long per = (total + ctas / classes - 1) / (ctas / classes);
+    const long long per_min = nzt < 4 ? nzt : 4;
+    if (per < per_min) per = per_min;
+    p.per = (int)per;
+    p.total = (int)total;
+    const long long used = (total + per - 1) / per * classes;
     if (int rc = ensure_dynamic_smem(k2_conv3d_zm_kernel<MODE, CT>, smem, "conv3d_zm")) return rc;
-    dim3 grid((unsigned)(tiles < ctas ? tiles : ctas), (unsigned)nblocks, 1);
-    if (MODE == ZM_DECONV && grid.x % 4) grid.x = (grid.x + 3) / 4 * 4;   // ntiles is a multiple of 4
+    dim3 grid((unsigned)used, (unsigned)nblocks, 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(ZM_THREADS);
@@ -1168,7 +1176,7 @@ extern "C" int mvsb200_conv3d_zm_slice(const mvsb200_conv3d_desc *d, const float
     p.B = d->B; p.D = d->D; p.H = d->H; p.W = d->W;
     p.Cin1 = d->Cin; p.Cin2 = d->Cin2; p.Cout = d->Cout;
     p.relu = d->relu; p.skip_mode = d->skip_mode;
-    p.tiles_x = p.tiles_y = p.nseg = p.zseg = p.ntiles = p.nstages = 0;
+    p.tiles_x = p.tiles_y = p.per = p.total = p.nstages = 0;
     p.g1 = p.g2 = p.nraw = p.raw_bytes = p.unit_bytes = 0;
     p.x_cstride = x_channels; p.x_coff = x_first_channel;
     p.profile = g_zm_prof_on;
