@@ -98,7 +98,9 @@ typedef struct {
  * (SOFTMIN only, models/MVSNet/model.py:94-95).
  * out: [B,D,H,W,C] (VARIANCE*, SOFTMIN) or S volumes [B,D,H,W,groups] (GROUPCORR).
  * out_amax: optional device scalar, atomically max-ed with max|out| (zero it before the launch); the z-march conv
- * engine takes it as x_amax so the volume is not read a second time. */
+ * engine takes it as x_amax so the volume is not read a second time.
+ * Alignment: ref, every src[s] and out (and, for the backward entry point, grad_out / grad_ref / grad_src[s]) must be
+ * 32-byte aligned -- the kernels move a pixel's channels with 256-bit accesses; violated -> MVSB200_E_INVALID. */
 MVSB200_API int mvsb200_build_cost_volume(const mvsb200_cost_volume_desc *desc, const float *ref, const float *const *src,
                               const float *warp, const float *depth, const float *interval, const float *temp,
                               float *out, float *out_amax, mvsb200_stream_t stream);

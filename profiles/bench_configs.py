@@ -19,6 +19,23 @@ from wild_deep_mvs_b200.mvsnet import MVSNet  # noqa: E402
 from wild_deep_mvs_b200.vismvsnet import Frontend as Vis  # noqa: E402
 
 DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# layer-wise compulsory fp32 traffic of the hot path of each config (bytes), the roofline denominator
+ALGORITHMIC_BYTES = {"cfg1": 495.6e6, "cfg2": 1963.6e6, "cfg3 ": 2969.6e6, "cfg3'": 5823.0e6, "cfg4": 20160e6}
+
+
+def hbm_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def add_roofline(r):
+    """hot-path fraction of the measured HBM roofline: algorithmic bytes / hot-path time / measured copy bandwidth."""
+    for key, nbytes in ALGORITHMIC_BYTES.items():
+        if r["config"].startswith(key):
+            r["algorithmic_MB"] = nbytes / 1e6
+            r["hot_path_frac_of_hbm_roofline"] = round(nbytes / (r["hot_path_ms"] * 1e-3) / 1e9 / hbm_gbs(), 4)
+    return r
 
 
 def timed(fn, reps=5, warmup=2):
@@ -52,7 +69,7 @@ def run(name, net, s, vox, feat_fn, **kw):
     r = {"config": name, "voxels": vox, "forward_ms": round(ms_fwd, 3), "features_ms": round(ms_feat, 3),
          "hot_path_ms": round(ms_hot, 3), "hot_path_Mvox_per_s": round(vox / ms_hot / 1e3, 1),
          "depth_maps_per_s": round(1e3 / ms_fwd, 1), "depth_shape": list(out["depth"].shape)}
-    print(json.dumps(r), flush=True)
+    print(json.dumps(add_roofline(r)), flush=True)
     return r
 
 
@@ -71,7 +88,7 @@ def vis_graphed(name, net, s, vox, nums, scales):
         ms = timed(lambda: g(), reps=20, warmup=3)
     r = {"config": name + " -- hot path as one CUDA graph", "voxels": vox, "hot_path_ms": round(ms, 3),
          "hot_path_Mvox_per_s": round(vox / ms / 1e3, 1)}
-    print(json.dumps(r), flush=True)
+    print(json.dumps(add_roofline(r)), flush=True)
     return r
 
 

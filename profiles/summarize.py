@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
 
-OURS = ("k1_", "k2_", "k3_", "k4_", "geom_", "mvs_relative", "vis_homography", "pack_")
+OURS = ("k1_", "k1m_", "k2_", "k3_", "k4_", "geom_", "mvs_relative", "vis_homography", "pack_")
 
 METRICS = [
     ("gpu__time_duration.sum", "time"),
@@ -93,9 +93,15 @@ def full(tag):
     hdr, units = rows[0], rows[1]
     traffic_path = os.path.join(PROF, "traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
-    # the capture holds the kernels of ONE cfg2 step in launch order: name them by layer for bench.py
-    step_layers = ["k1_cost_volume", "conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv9",
-                   "conv11", "prob", "k3_regress"]
+    # the capture holds the kernels of ONE cfg2 step in launch order: name them by layer for bench.py.  A layer is identified
+    # by its position AND the kernel it must be (conv6 runs as two launches over the halves of its input channels: their
+    # traffic is summed); if the sequence does not match, no per-layer attribution is written rather than a wrong one.
+    step_layers = [("k1_cost_volume", "k1m_cost_volume_kernel"), ("conv0", "k2_conv3d_zm_kernel<0, 8>"), ("conv1", "k2_conv3d_zm_kernel<1, 16>"),
+                   ("conv2", "k2_conv3d_zm_kernel<0, 16>"), ("conv3", "k2_conv3d_zm_kernel<1, 16>"), ("conv4", "k2_conv3d_zm_kernel<0, 16>"),
+                   ("conv5", "k2_conv3d_zm_kernel<1, 16>"), ("conv6", "k2_conv3d_zm_kernel<0, 16>"), ("conv6", "k2_conv3d_zm_kernel<0, 16>"),
+                   ("conv7", "k2_conv3d_zm_kernel<2, 16>"), ("conv9", "k2_conv3d_zm_kernel<2, 16>"), ("conv11", "k2_conv3d_zm_kernel<2, 8>"),
+                   ("prob", "k2_conv3d_c1_kernel"), ("k3_regress", "k3_depth_regress")]
+    mismatch = False
     layers, nth = {}, 0
     with open(os.path.join(PROF, "ncu_%s.md" % tag), "w") as f:
         f.write("# ncu --set full `%s` (--clock-control none, one pass of cfg2 under the profiler; not a bench value)\n\n" % tag)
@@ -118,10 +124,20 @@ def full(tag):
                 key = name + "#" + r[hdr.index("ID")]
                 traffic[key] = rd + wr
                 if nth < len(step_layers):
-                    layers[step_layers[nth]] = {"kernel": name, "dram_bytes": rd + wr, "tag": tag}
+                    lname, kprefix = step_layers[nth]
+                    if not name.startswith(kprefix):
+                        mismatch = True
+                    elif lname in layers:
+                        layers[lname]["dram_bytes"] += rd + wr
+                        layers[lname]["launches"] += 1
+                    else:
+                        layers[lname] = {"kernel": name, "dram_bytes": rd + wr, "launches": 1, "tag": tag,
+                                         "grid": r[hdr.index("launch__grid_size")] if "launch__grid_size" in hdr else None}
             nth += 1
             f.write("\n")
-    if len(layers) >= 2:
+    if mismatch:
+        print("launch sequence does not match one cfg2 step: traffic.json `layers` left unchanged")
+    elif len(layers) >= 2:
         traffic["layers"] = layers
     json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
     print("wrote profiles/ncu_%s.md, profiles/traffic.json" % tag)

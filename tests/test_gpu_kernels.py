@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import oracle as orc
-from conftest import rel_linf
+from conftest import assert_mismatches_on_boundary, expected_index_boundary_distance, rel_linf
 
 pytestmark = pytest.mark.gpu
 
@@ -293,7 +293,11 @@ def test_k3_all_modes_against_oracle(D):
     assert rel_linf(got["depth"][0].cpu().numpy(), want["depth"]) < 1e-5
     assert rel_linf(got["prob"][0].cpu().numpy(), want["prob"]) < 1e-5
     assert rel_linf(got["entropy"][0].cpu().numpy(), want["entropy"]) < 1e-4
-    assert (np.abs(got["conf"][0].cpu().numpy() - want["conf"]) > 1e-4).mean() < 0.01
+    # the confidence sums the 4 bins around floor(expected index): index work -- it may differ from the oracle ONLY where the
+    # expected index sits on an integer (1e-5 of the index range), and such pixels are rare
+    dist = expected_index_boundary_distance(want["prob"])
+    n_bad = assert_mismatches_on_boundary(got["conf"][0].cpu().numpy(), want["conf"], dist, 1e-4, 1e-5 * D, "K3 CONF_SUM4")
+    assert n_bad <= max(1, int(0.01 * H * W)), n_bad
     # per-pixel hypotheses
     dpp = (dv[:, None, None] + rng.random((D, H, W))).astype(np.float32)
     got = ops.depth_regress(cu(score[None]), cu(dpp[None]))
@@ -303,7 +307,8 @@ def test_k3_all_modes_against_oracle(D):
     got = ops.depth_regress(cu(score[None]), cu(start[None]), interval=cu(np.array([2.5])), conf_mode=L.CONF_WINDOW)
     want = orc.softmax_regress(score, 2, start, 2.5, conf_mode=2)
     assert rel_linf(got["depth"][0].cpu().numpy(), want["depth"]) < 1e-5
-    assert (np.abs(got["conf"][0].cpu().numpy() - want["conf"]) > 1e-4).mean() < 0.01
+    n_bad = assert_mismatches_on_boundary(got["conf"][0].cpu().numpy(), want["conf"], dist, 1e-4, 1e-5 * D, "K3 CONF_WINDOW")
+    assert n_bad <= max(1, int(0.01 * H * W)), n_bad
     got = ops.depth_regress(cu(score[None]), cu(np.array([425.0])), interval=cu(np.array([2.5])))
     assert rel_linf(got["depth"][0].cpu().numpy(), orc.softmax_regress(score, 2, np.array([425.0]), 2.5)["depth"]) < 1e-5
 

@@ -16,6 +16,7 @@
 //   soft-min      out = sum_s e_s d_s / (sum_s e_s + 1e-6), d_s = (r - w_s)^2, e_s = exp(-temp sum_c d_s)
 //   group corr.   out_s[g] = sum_{c in g} r_c w_s,c    dL/dw_s,c = G_s[g] r_c;  dL/dr_c = sum_s,d G_s[g] w_s,c
 #include "k1_common.cuh"
+#include <cstdint>
 
 namespace mvsb200 {
 
@@ -309,6 +310,12 @@ extern "C" int mvsb200_build_cost_volume_backward(const mvsb200_cost_volume_desc
 {
     const char *what = "build_cost_volume_backward";
     MVSB200_REQUIRE(d && ref && src && warp && depth && grad_out && grad_ref && grad_src, "%s: null pointer", what);
+    // 256-bit loads of the maps and of grad_out, 128-bit vector reductions into the gradient maps
+    MVSB200_REQUIRE(((reinterpret_cast<uintptr_t>(ref) | reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(grad_ref)) & 31) == 0,
+                    "%s: ref, grad_out and grad_ref must be 32-byte aligned", what);
+    for (int s = 0; s < d->S && s < MVSB200_MAX_SRC; s++)
+        MVSB200_REQUIRE(src[s] && grad_src[s] && ((reinterpret_cast<uintptr_t>(src[s]) | reinterpret_cast<uintptr_t>(grad_src[s])) & 31) == 0,
+                        "%s: src[%d] and grad_src[%d] must be non-null and 32-byte aligned", what, s, s);
     MVSB200_REQUIRE(d->B > 0 && d->D > 0 && d->H > 0 && d->W > 0, "%s: bad shape B=%d D=%d H=%d W=%d", what, d->B, d->D, d->H, d->W);
     MVSB200_REQUIRE(d->S >= 1 && d->S <= MVSB200_MAX_SRC, "%s: S=%d not in [1,%d]", what, d->S, MVSB200_MAX_SRC);
     MVSB200_REQUIRE(d->C == 8 || d->C == 16 || d->C == 32, "%s: C=%d (supported: 8, 16, 32)", what, d->C);

@@ -17,6 +17,7 @@
 //   VIS geometry  models/VisMVSNet/homography.py:77-121 (pixel centres +0.5, normalise by size, clamp +-1.1)
 //   grid_sample(bilinear, zeros, align_corners=True): per-tap zero padding.
 #include "k1_common.cuh"
+#include <cstdint>
 #include <cstdlib>
 
 namespace mvsb200 {
@@ -518,6 +519,11 @@ extern "C" int mvsb200_build_cost_volume(const mvsb200_cost_volume_desc *d, cons
                                          mvsb200_stream_t stream)
 {
     MVSB200_REQUIRE(d && ref && src && warp && depth && out, "build_cost_volume: null pointer");
+    // feature maps and the volume are moved with 256-bit (pixel-major kernel) / 128-bit (depth-marching kernel) accesses
+    MVSB200_REQUIRE(((reinterpret_cast<uintptr_t>(ref) | reinterpret_cast<uintptr_t>(out)) & 31) == 0,
+                    "build_cost_volume: ref and out must be 32-byte aligned");
+    for (int s = 0; s < d->S && s < MVSB200_MAX_SRC; s++)
+        MVSB200_REQUIRE(src[s] && (reinterpret_cast<uintptr_t>(src[s]) & 31) == 0, "build_cost_volume: src[%d] must be non-null and 32-byte aligned", s);
     MVSB200_REQUIRE(d->B > 0 && d->D > 0 && d->H > 0 && d->W > 0, "build_cost_volume: bad shape B=%d D=%d H=%d W=%d",
                     d->B, d->D, d->H, d->W);
     MVSB200_REQUIRE(d->S >= 1 && d->S <= MVSB200_MAX_SRC, "build_cost_volume: S=%d not in [1,%d]", d->S, MVSB200_MAX_SRC);

@@ -529,7 +529,7 @@ k2_conv3d_zm_kernel(const ZmParams p, const __grid_constant__ CUtensorMap tm_x, 
         const int group = ptid / ZM_PROD_GROUP, gt = ptid % ZM_PROD_GROUP;
         constexpr int XV = EX * NPX;          // voxels of one staged row run (contiguous in x)
         constexpr int NVOX = T::EY * XV;
-        constexpr int BATCH = 4;              // 16-byte pieces converted per loop trip (loads first, then the arithmetic)
+        constexpr int BATCH = 8;              // 16-byte pieces converted per loop trip (loads first, then the arithmetic)
         int un = 0;               // units so far (all groups count all units)
         int ub = 0;               // ring position of the current unit's buffer
         uint32_t uphase = 1;      // parity to wait for on its empty barrier (first pass: free)

@@ -152,14 +152,20 @@ def read_pfm(path):
         channels = {"PF": 3, "Pf": 1}.get(magic)
         if channels is None:
             raise Exception("Not a PFM file.")
-        dims = f.readline().decode("utf-8")          # digits, one whitespace character, digits, one whitespace character
-        body = dims[:-1]
+        # the reference's header rule is re.match(r'^(\d+)\s(\d+)\s$', line) (data/MVSDataset.py:152-187): digits, ONE whitespace
+        # character, digits, ONE whitespace character -- where `$` also matches just before a trailing newline, so
+        # "640 480\r\n" and "640 480 \n" are accepted as well as "640 480\n"
+        dims = f.readline().decode("utf-8")
+        body = dims[:-1] if dims.endswith("\n") and len(dims) >= 2 and dims[-2].isspace() else dims
         i = 0
         while i < len(body) and body[i].isdigit():
             i += 1
-        if not (0 < i < len(body) - 1 and body[i].isspace() and body[i + 1:].isdigit() and dims[-1:].isspace()):
+        j = i + 1
+        while j < len(body) and body[j].isdigit():
+            j += 1
+        if not (0 < i < len(body) and body[i].isspace() and j > i + 1 and j == len(body) - 1 and body[j].isspace()):
             raise Exception("Malformed PFM header.")
-        parts = (body[:i], body[i + 1:])
+        parts = (body[:i], body[i + 1:j])
         w, h = int(parts[0]), int(parts[1])
         scale = float(f.readline().rstrip())
         data = np.frombuffer(f.read(), dtype=("<" if scale < 0 else ">") + "f4")
