@@ -309,10 +309,10 @@ def own_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    clocks = ClockSampler(local, enabled=(rank == 0))   # NVML init takes ~0.1 s: BEFORE the barrier, or rank 0 enters the timed
+    for _ in range(args.warmup):                        # region late and every other rank bills the wait to its first all-gather
         step()
     barrier()
-    clocks = ClockSampler(local, enabled=(rank == 0))
     # ONE event pair around the K steps, launched back to back.  No L2 flush between steps: a step streams 1.4 GB of
     # intermediates (503 MB cost volume, 389 MB activations, ...) through the 126 MB L2, so nothing a step reads first
     # (13 MB of feature maps, last touched 1.4 GB of traffic earlier) is still resident -- the "inputs larger than L2"

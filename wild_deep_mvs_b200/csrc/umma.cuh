@@ -1,5 +1,7 @@
-// Thin inline-PTX wrappers for the Blackwell (sm_100a) tensor-core path: tcgen05.mma (kind::tf32) with shared
-// memory operands and TMEM accumulators, TMEM allocation / loads, mbarriers and the proxy fences between them.
+// Thin inline-PTX wrappers for the Blackwell (sm_100a) tensor-core path: tcgen05.mma with shared-memory operands and TMEM
+// accumulators (kind::tf32 here, used by the tile engine k2_conv3d_tc.cu; the z-march engine k2_conv3d_zm.cu issues
+// kind::f16 with its own mma_f16 / idesc_f16 on the same descriptors), TMEM allocation / loads, mbarriers and the proxy
+// fences between them.
 //
 // Shared-memory operand layout used throughout libmvsb200 (SWIZZLE_NONE, K-major "interleave" canonical form):
 // a matrix of R rows x 8 tf32 (one MMA K step = 32 bytes) is stored as two K-chunk planes of R x 16 bytes,

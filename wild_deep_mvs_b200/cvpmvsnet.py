@@ -10,9 +10,12 @@ Per pyramid level (coarsest first):
       (homo_warping / proj_cost, modules.py:74-128,229-293)
   K2  the shared CostRegNet (net.py:50-85) on the tcgen05 tensor cores, BN/ReLU/skip fused
   K3  softmax + (per-pixel) depth regression, and the 4-bin confidence on the last level (net.py:161-162,203-219)
-FeaturePyramid (2-D CNN), the bicubic x2 depth up-sampling (net.py:169-170) and the fp64 epipolar interval search
-`calDepthHypo` (modules.py:131-226) stay in PyTorch on the device ("next" rows f1 / f4 of SURVEY.md 8-f).
-Inference only.
+  K5  the fp64 per-pixel epipolar solve of `calDepthHypo` (modules.py:131-226; mvsb200_cvp_depth_delta) -- only the median of
+      its result (a device sort) is a PyTorch op
+FeaturePyramid (2-D CNN, all same-sized views as one batch) and the bicubic x2 depth up-sampling (net.py:169-170) stay in
+PyTorch on the device ("next" row f1 of SURVEY.md 8-f).
+Eval mode runs the kernels above; training mode (row f2) uses the K1 / K3 forward + backward kernels behind autograd
+Functions with the regulariser as PyTorch modules (network._forward_train; tests/test_gpu_backward.py).
 """
 import os
 

@@ -6,14 +6,16 @@ reference_frame=0, **kwargs)` signature, returned dict and state_dict key names 
 written by the reference's train.py loads unchanged (models/MVSNet/model.py:86-218).
 
 What runs where:
-  * FeatureNet (2-D CNN, models/MVSNet/model.py:21-41): PyTorch/cuDNN, channels_last  ("next" row f1)
+  * FeatureNet (2-D CNN, models/MVSNet/model.py:21-41) -> K7 (mvsb200_conv2d) in eval mode, PyTorch modules in training
   * build_cost_volume  -> K1 (mvsb200_build_cost_volume), fused warp + aggregation
-  * cost_regularization -> K2 (mvsb200_conv3d), BN/ReLU/skip fused
+  * cost_regularization -> K2 (mvsb200_conv3d*), BN/ReLU/skip fused
   * softmax / depth regression / confidence -> K3 (mvsb200_depth_regress)
-Training mode (row f2 of SURVEY.md 8, started): the warp + aggregation and the regression head run on the library forward AND
+Training mode (row f2 of SURVEY.md 8): the warp + aggregation and the regression head run on the library forward AND
 backward (K1 / K3 backward kernels behind torch.autograd.Function, ops.cost_volume / ops.regress_depth); the 3-D
-regulariser and the 2-D FeatureNet run as the PyTorch modules that own the parameters (batch-statistics BatchNorm,
-cuDNN dgrad / wgrad) -- a K2 backward is the part of f2 not built yet.
+regulariser runs as the PyTorch modules that own the parameters (batch-statistics BatchNorm) -- on cuDNN by default, on
+the K2 engines forward + input gradient with mvsb200_conv3d_wgrad for the weight gradient when MVSB200_TRAIN_K2=lib.
+Multi-GPU (row e): `graphed(..., gather=shard.DepthGather)` makes K3 write the depth map into the rank's slice of the
+preallocated gather buffer and captures the in-place all-gather into the step's CUDA graph.
 """
 import os
 

@@ -9,8 +9,11 @@ Per stage (SingleStage.forward, models/VisMVSNet/model_cas.py:303-420, mode='sof
   K2  Reg U-Net + RegPair head on the S pair volumes stacked along the batch axis (shared weights)
   K3  pair soft-argmin + entropy;  UncertNet (three tiny 2-D convs, also K2);
   K4  visibility-weighted fusion;  K2 RegFuse U-Net + head;  K3 soft-argmin with the +-2 window confidence.
-FeatExt (2-D U-Net) and the bilinear up-sampling of the previous stage's depth stay in PyTorch ("next" rows).
-Inference only.
+FeatExt (2-D U-Net) and the bilinear up-sampling of the previous stage's depth stay in PyTorch ("next" rows; FeatExt has
+an opt-in library path, MVSB200_VIS_FEATEXT=lib).
+Eval mode runs the kernels above; training mode (`net.train()`, row f2) builds the per-pair group-correlation volumes with
+the K1 forward / backward kernels (ops.cost_volume) and runs everything downstream as the reference's own PyTorch modules,
+so every output carries the reference's gradient (SingleStage._run_train; tests/test_gpu_backward.py).
 """
 import os
 
