@@ -39,4 +39,24 @@ for name, cin, cout, stride, tr, dims in CASES:
             b.synchronize()
             ts.append(a.elapsed_time(b) / reps * 1e3)
         res.append(sorted(ts)[2])
-    print("%-40s single launch %.1f us, 16 back to back %.1f us each" % (name, res[0], res[1]))
+    # GPU-side cost without the host: 16 launches captured in one CUDA graph
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.conv3d(x, layer, engine="zm", out=y)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(16):
+            ops.conv3d(x, layer, engine="zm", out=y)
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b) / 16 * 1e3)
+    print("%-40s single launch %.1f us, 16 back to back %.1f us each, 16 in one CUDA graph %.1f us each" % (name, res[0], res[1], sorted(ts)[2]))

@@ -89,7 +89,7 @@ struct ZmParams {
     int B, D, H, W, Do, Ho, Wo;
     int Cin1, Cin2, Cout;
     int relu, skip_mode;
-    int tiles_x, tiles_y, per, total, nstages;   // work decomposition: see ZmWalk
+    int tiles_x, tiles_y, per, total, nseg, nstages;   // work decomposition: see ZmWalk
     int g1, g2;              // chunks (of 8 channels) per producer unit for x and for x2 (one TMA box each)
     int nraw, raw_bytes;     // ring of raw fp32 unit buffers the TMA loader fills
     int unit_bytes;          // bytes of one converted unit buffer = max(g1, g2) * NPX stage buffers
@@ -226,12 +226,17 @@ struct ZmTile {
     int b, zb, nq, y0, x0, cls;
 };
 
-// Work decomposition.  The (tile column, z) index space of a layer -- columns = (x tile, y tile, batch item), z counted in
-// output planes (S1, S2) or input planes (DECONV) -- is flattened column-major and cut into EQUAL contiguous runs, one per
-// CTA (per output-parity class for DECONV: class = blockIdx.x % 4, so the class and with it the resident weight variant is
-// constant per CTA).  A run is walked as one z-march per column it touches (each with its own halo planes).  Every CTA
-// gets the same number of planes whatever the ratio of columns to SMs (a volume of 50 columns on 148 SMs used to run 100
-// CTAs x 48 planes; it now runs 148 x 33).  All warp roles of a CTA walk the same sequence.
+// Work decomposition over the (tile column, z) index space of a layer -- columns = (x tile, y tile, batch item), z counted in
+// output planes (S1, S2) or input planes (DECONV); per output-parity class for DECONV (class = blockIdx.x % 4, so the class
+// and with it the resident weight variant is constant per CTA).  Two schemes, chosen per launch by the host:
+//   * lockstep (nseg > 0): z is cut into nseg equal segments and the CTAs take the (segment, column) tiles round-robin,
+//     neighbouring columns of the SAME segment at the same time -- the in-plane halo rows a tile shares with its
+//     neighbours are then in L2 when the neighbour asks for them (a volume that does not fit L2 is read once);
+//   * flat (nseg == 0): the index space is flattened column-major and cut into EQUAL contiguous runs, one per CTA, walked
+//     as one z-march per column touched.  Every CTA gets the same number of planes whatever the ratio of columns to
+//     SMs (50 columns on 148 SMs: 148 CTAs x 33 planes instead of 100 x 48) -- for volumes whose lockstep tiling leaves
+//     SMs idle, which are the ones small enough for L2 to absorb the halo re-reads.
+// All warp roles of a CTA walk the same sequence.
 struct ZmWalk {
     int flat, hi, cls;
 };
@@ -241,8 +246,13 @@ template <int MODE> __device__ __forceinline__ ZmWalk zm_walk_begin(const ZmPara
     int c = blockIdx.x;
     w.cls = 0;
     if (MODE == ZM_DECONV) { w.cls = c & 3; c >>= 2; }
-    w.flat = c * p.per;
-    w.hi = min(w.flat + p.per, p.total);
+    if (p.nseg > 0) {          // lockstep: tiles c, c + G, c + 2G, ... of the (segment, column) grid
+        w.flat = c;
+        w.hi = p.total;        // = segments x columns
+    } else {                   // flat: the contiguous run [c * per, (c + 1) * per) of the (column, z) index space
+        w.flat = c * p.per;
+        w.hi = min(w.flat + p.per, p.total);
+    }
     return w;
 }
 template <int MODE, int CT> __device__ __forceinline__ bool zm_walk_next(const ZmParams &p, ZmWalk &w, ZmTile &t)
@@ -250,10 +260,20 @@ template <int MODE, int CT> __device__ __forceinline__ bool zm_walk_next(const Z
     using T = ZmCfg<MODE, CT>;
     if (w.flat >= w.hi) return false;
     const int ztot = (MODE == ZM_DECONV) ? p.D : p.Do;
-    int col = w.flat / ztot;
-    const int z = w.flat - col * ztot;
-    const int n = min(ztot - z, w.hi - w.flat);
-    w.flat += n;
+    int col, z, n;
+    if (p.nseg > 0) {
+        const int ncol = p.total / p.nseg;
+        const int sg = w.flat / ncol;
+        col = w.flat - sg * ncol;
+        z = sg * p.per;
+        n = min(p.per, ztot - z);
+        w.flat += (MODE == ZM_DECONV) ? (int)(gridDim.x >> 2) : (int)gridDim.x;
+    } else {
+        col = w.flat / ztot;
+        z = w.flat - col * ztot;
+        n = min(ztot - z, w.hi - w.flat);
+        w.flat += n;
+    }
     const int tx = col % p.tiles_x; col /= p.tiles_x;
     const int ty = col % p.tiles_y;
     t.b = col / p.tiles_y;
@@ -1044,14 +1064,42 @@ static int launch_zm(ZmParams p, int sm_count, cudaStream_t st)
         set_error("conv3d_zm: volume too large");
         return MVSB200_E_INVALID;
     }
-    // equal runs of planes per CTA; a run shorter than 4 planes would spend most of its time on the z halo and the pipeline
-    // fill of its segment, so small volumes use fewer CTAs instead
-    long long per = (total + ctas / classes - 1) / (ctas / classes);
-    const long long per_min = nzt < 4 ? nzt : 4;
-    if (per < per_min) per = per_min;
-    p.per = (int)per;
-    p.total = (int)total;
-    const long long used = (total + per - 1) / per * classes;
+    // lockstep candidate: segment count that best trades the z halo against filling all CTAs for whole rounds
+    const long long ncol = (long long)p.tiles_x * p.tiles_y * p.B;
+    const int cpc = ctas / classes;                    // CTAs per class
+    const int halo = (MODE == ZM_S1) ? 2 : 1;
+    double best = -1.0;
+    int best_nseg = 1;
+    for (int nseg = 1; nseg <= nzt; nseg++) {
+        const int zseg = (nzt + nseg - 1) / nseg;
+        if ((long long)(nseg - 1) * zseg >= nzt) continue;
+        const long long tiles = ncol * nseg;
+        const long long rounds = (tiles + cpc - 1) / cpc;
+        const double eff = (double)tiles / (double)(rounds * cpc) * (double)zseg / (double)(zseg + halo) *
+                           (1.0 - 0.02 * (double)rounds / (double)(rounds + 8));
+        if (eff > best) { best = eff; best_nseg = nseg; }
+        if (tiles > 64ll * cpc) break;
+    }
+    long long used;
+    // lockstep only pays for inputs that do not fit L2 (B200: 126 MB; halo re-reads of a smaller volume are L2 hits under
+    // either scheme) and only if its tiling keeps the CTAs busy
+    const double in_bytes = (double)p.B * p.D * p.H * p.W * (p.Cin1 + p.Cin2) * 4.0;
+    if (best >= 0.88 && in_bytes >= 64e6) {
+        p.nseg = best_nseg;
+        p.per = (nzt + best_nseg - 1) / best_nseg;
+        p.total = (int)(ncol * best_nseg);
+        used = (p.total < cpc ? p.total : cpc) * (long long)classes;
+    } else {
+        // flat: equal runs of planes per CTA; a run shorter than 4 planes would spend most of its time on the z halo and the
+        // pipeline fill of its segment, so small volumes use fewer CTAs instead
+        long long per = (total + cpc - 1) / cpc;
+        const long long per_min = nzt < 4 ? nzt : 4;
+        if (per < per_min) per = per_min;
+        p.nseg = 0;
+        p.per = (int)per;
+        p.total = (int)total;
+        used = (total + per - 1) / per * classes;
+    }
     if (int rc = ensure_dynamic_smem(k2_conv3d_zm_kernel<MODE, CT>, smem, "conv3d_zm")) return rc;
     dim3 grid((unsigned)used, (unsigned)nblocks, 1);
     cudaLaunchConfig_t cfg = {};
@@ -1176,7 +1224,7 @@ extern "C" int mvsb200_conv3d_zm_slice(const mvsb200_conv3d_desc *d, const float
     p.B = d->B; p.D = d->D; p.H = d->H; p.W = d->W;
     p.Cin1 = d->Cin; p.Cin2 = d->Cin2; p.Cout = d->Cout;
     p.relu = d->relu; p.skip_mode = d->skip_mode;
-    p.tiles_x = p.tiles_y = p.per = p.total = p.nstages = 0;
+    p.tiles_x = p.tiles_y = p.per = p.total = p.nseg = p.nstages = 0;
     p.g1 = p.g2 = p.nraw = p.raw_bytes = p.unit_bytes = 0;
     p.x_cstride = x_channels; p.x_coff = x_first_channel;
     p.profile = g_zm_prof_on;
