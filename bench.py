@@ -248,7 +248,9 @@ def workload_config(n):
                         "features->depth+confidence (K1 warp+variance, K2 3-D U-Net, K3 softmax/regress)",
             "views": CFG["views"], "feature_hw": [CFG["h"], CFG["w"]], "D": CFG["D"], "voxels_per_map": voxels(),
             "maps_per_step": n, "k2_engine": K2_ENGINE_NOTE.get(os.environ.get("MVSB200_K2_ENGINE", "zm"), "?"),
-            "parallelism": "view-sharded replicas x%d + 1 in-place all-gather of depth maps per step (inside the step's CUDA graph)" % n,
+            "parallelism": "view-sharded replicas x%d + 1 in-place all-gather of depth maps per step (inside the step's CUDA graph; "
+                           "backend: %s)" % (n, "mvsb200_allgather_depth on the library's own NCCL communicator"
+                                             if os.environ.get("MVSB200_GATHER", "lib") == "lib" else "torch.distributed all_gather_into_tensor"),
             "l2": "inputs larger than L2: every step streams ~1.4 GB of intermediates (503 MB cost volume, 389 MB activations) "
                   "through the 126 MB L2 before the next step re-reads its 13 MB of feature maps; K steps back to back between one "
                   "pair of CUDA events, L2 flushed once before the first (per-kernel `kernels` timings: flushed before each)"}
@@ -463,7 +465,11 @@ def own_arm(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-        th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+
+        def teardown():
+            shard.DepthGather.destroy_communicators()
+            dist.destroy_process_group()
+        th = threading.Thread(target=teardown, daemon=True)
         th.start()
         th.join(20.0)
         sys.stderr.flush()

@@ -293,6 +293,23 @@ MVSB200_API int mvsb200_geometric_filter(const float *depth, int H, int W, const
                                          unsigned char *mask_depth, unsigned char *mask_disp, unsigned char *geo_mask,
                                          unsigned char *votes, mvsb200_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Multi-GPU: independent reference views per rank, ONE all-gather of the per-view depth maps -- the
+ * collective the reference issues with `dist.all_gather(all_depthmaps, depth_est)` (models/trainer.py:246-247) on views
+ * sharded as `reference_frame = rank` (:101) / DistributedSampler (depthmap_eval.py:95).
+ * NCCL is bound at run time (dlopen("libnccl.so.2")); the library has no link-time dependency on it.
+ *   mvsb200_gather_unique_id   rank 0: fills a 128-byte HOST buffer (ncclUniqueId); hand it to every rank by any means
+ *   mvsb200_gather_init        every rank, current device: creates the communicator (*comm, opaque)
+ *   mvsb200_allgather_depth    IN PLACE over all_maps [world * count_per_rank] floats (device): rank r owns the slice
+ *                              [r * count_per_rank, (r + 1) * count_per_rank) -- pass that slice as `depth` to
+ *                              mvsb200_depth_regress so the map is born where it is sent from; stream-ordered, no
+ *                              allocation, legal inside a CUDA-graph capture (destroy captured graphs before the communicator)
+ *   mvsb200_gather_destroy */
+MVSB200_API int mvsb200_gather_unique_id(void *id128);
+MVSB200_API int mvsb200_gather_init(const void *id128, int world, int rank, void **comm);
+MVSB200_API int mvsb200_allgather_depth(void *comm, float *all_maps, long long count_per_rank, int rank, mvsb200_stream_t stream);
+MVSB200_API int mvsb200_gather_destroy(void *comm);
+
 #ifdef __cplusplus
 }
 #endif

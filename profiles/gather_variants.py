@@ -113,7 +113,7 @@ import gc
 gc.collect()
 torch.cuda.synchronize()
 dist.barrier()
-th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+th = threading.Thread(target=lambda: (shard.DepthGather.destroy_communicators(), dist.destroy_process_group()), daemon=True)
 th.start()
 th.join(20.0)
 os._exit(0)

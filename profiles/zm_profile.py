@@ -25,7 +25,8 @@ LAYERS = [("conv0", 32, 8, 1, False, (1, 192, 128, 160)), ("conv1", 8, 16, 2, Fa
           ("conv11", 16, 8, 2, True, (1, 96, 64, 80)),
           # Vis-MVSNet Reg blocks: 4 source views on the batch axis, stage 3 / stage 1 volumes
           ("vis8x8s3", 8, 8, 1, False, (4, 8, 256, 320)), ("vis8x8s1", 8, 8, 1, False, (4, 32, 64, 80)),
-          ("vis8x16s3", 8, 16, 2, False, (4, 8, 256, 320)), ("visup-s3", 16, 8, 2, True, (4, 4, 128, 160))]
+          ("vis8x16s3", 8, 16, 2, False, (4, 8, 256, 320)), ("visup-s3", 16, 8, 2, True, (4, 4, 128, 160)),
+          ("vis16x8s3", 16, 8, 1, False, (4, 8, 256, 320))]
 if len(sys.argv) > 1:
     LAYERS = [l for l in LAYERS if any(a in l[0] for a in sys.argv[1:])]
 for name, cin, cout, stride, tr, dims in LAYERS:

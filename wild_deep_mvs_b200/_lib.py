@@ -75,6 +75,10 @@ SIGNATURES = {
     "mvsb200_geometric_filter": (_i, [_vp, _i, _i, ctypes.POINTER(_vp), ctypes.POINTER(_i), ctypes.POINTER(_i), _i, _vp, _vp, _vp,
                                       ctypes.c_float, ctypes.c_float, ctypes.c_float, _i, _vp, _vp, _vp, _vp, _vp]),
     "mvsb200_vis_fuse": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "mvsb200_gather_unique_id": (_i, [_vp]),
+    "mvsb200_gather_init": (_i, [_vp, _i, _i, ctypes.POINTER(_vp)]),
+    "mvsb200_allgather_depth": (_i, [_vp, _vp, ctypes.c_longlong, _i, _vp]),
+    "mvsb200_gather_destroy": (_i, [_vp]),
 }
 
 _lib = None

@@ -62,7 +62,7 @@ def build(force=False, verbose=False):
         failed |= pr.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "--shared", "-o", SO] + objs)
+    subprocess.check_call([nvcc, "--shared", "-o", SO] + objs + ["-ldl"])
     return SO
 
 
