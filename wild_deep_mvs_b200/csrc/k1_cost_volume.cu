@@ -215,11 +215,13 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_cost_volume_kernel(const K1P
 // The channel-independent tap geometry of the 4 x S (hypothesis, view) pairs of a mini-chunk is computed once, spread
 // over the L lanes of the pixel -- a lane always serves the same view, whose constants it keeps in registers, with the
 // per-pixel part of the projection hoisted out of the depth loop -- and handed to the other lanes through shared memory
-// as packed-pair weights (two LDS.128 + one LDS.32 per (hypothesis, view) instead of five shuffles and four moves).
+// (one LDS.128 + one LDS.32 per (hypothesis, view): 5 wavefronts of the LSU pipe, this kernel's busiest unit after the
+// change; broadcast 128-bit shared loads cost 4 wavefronts each, so packed-pair duplicates are made with moves instead).
+// The pixels that share a warp are stacked ACROSS the epipolar direction so that they change cells together, and the
+// window re-load is a real warp-uniform branch (the compiler otherwise if-converts it into ~30 always-issued instructions).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int K1M_THREADS = 128;
 constexpr int K1M_HC = 4;        // hypotheses per mini-chunk (geometry is shared per mini-chunk)
-constexpr int K1M_TAPF = 12;     // floats per packed tap record: {w00,w00,w01,w01, w10,w10,w11,w11, cell, -, -, -}
 
 struct K1MView {                 // per source view, staged in shared memory once per block
     const float *base;           // first pixel of the view's map for batch item b
@@ -233,14 +235,18 @@ template <int C, int GEOM, int AGG, int S>
 __global__ void __launch_bounds__(K1M_THREADS, 4) k1m_cost_volume_kernel(const K1Params p, const int seg)
 {
     constexpr int L = C / 4;                // lanes per pixel, each owning 4 channels (one 16-byte vector per tap)
-    constexpr int PXW = 32 / L;             // x-adjacent pixels per warp
+    constexpr int PXW = 32 / L;             // adjacent pixels per warp (along x or along y, see `stack_y`)
     constexpr int R = L / S;                // hypotheses whose geometry one round of the L lanes covers
     constexpr int ROUNDS = (K1M_HC + R - 1) / R;
     constexpr int TH = K1M_THREADS / 32;
-    constexpr int PIXF = K1M_HC * S * K1M_TAPF + 4;   // + 16 bytes: the records of the pixels of a warp fall into different banks
+    constexpr int NREC = K1M_HC * S;        // (hypothesis, view) tap records of a pixel per mini-chunk
     static_assert(L % S == 0 && R >= 1 && (K1M_HC % R == 0 || R > K1M_HC), "views must divide the lanes of a pixel");
     __shared__ K1MView s_view[S];
-    __shared__ __align__(16) float s_taps[TH][PXW][PIXF];
+    // tap records {w00, w01, w10, w11} + cell.  A broadcast LDS.128 costs the LSU pipe four wavefronts however few distinct
+    // addresses it has (one per quarter warp) and that pipe, shared with the tap loads, is this kernel's busiest unit: the
+    // record is therefore ONE 16-byte vector + one 4-byte word (5 wavefronts), the packed-pair weights are made with moves
+    __shared__ __align__(16) float4 s_w[TH][PXW][NREC + 1];   // + 1: the pixels of a warp start in different banks
+    __shared__ int s_cell[TH][PXW][NREC + 1];
 
     const int b = blockIdx.z;
     const long long HW = (long long)p.H * p.W;
@@ -259,9 +265,28 @@ __global__ void __launch_bounds__(K1M_THREADS, 4) k1m_cost_volume_kernel(const K
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const int sub = lane % L, pxi = lane / L;
     const int sv = sub % S, h_off = sub / S;         // this lane's geometry duty: view sv, hypothesis h_off of every round
-    const int tiles_x = (p.W + PXW - 1) / PXW;
-    const int x_raw = (int)(blockIdx.x % tiles_x) * PXW + pxi;
-    const int y_raw = (int)(blockIdx.x / tiles_x) * TH + wrp;
+    // Which PXW pixels share a warp?  A warp re-loads a window whenever ANY of its pixels changes cell, so its pixels should
+    // change cells TOGETHER: neighbours ACROSS the epipolar direction see (almost) the same sub-pixel motion per hypothesis,
+    // neighbours ALONG it cross cell borders at different hypotheses.  d(u,v)/d(depth) of a projected point is parallel to
+    // (ax bz - az bx, ay bz - az by) whatever the depth; it is evaluated at the image centre, summed over the views (one
+    // decision per launch, the same in every block): mostly horizontal motion -> the pixels of a warp are stacked along y.
+    float ex = 0.f, ey = 0.f;
+    {
+        const float cx = (float)(p.W / 2) + (GEOM == MVSB200_GEOM_VIS ? 0.5f : 0.f), cy = (float)(p.H / 2) + (GEOM == MVSB200_GEOM_VIS ? 0.5f : 0.f);
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const float *wp = s_view[s].wp;
+            const float cax = wp[0] * cx + wp[1] * cy + wp[2], cay = wp[3] * cx + wp[4] * cy + wp[5], caz = wp[6] * cx + wp[7] * cy + wp[8];
+            ex += fabsf(cax * wp[11] - caz * wp[9]);
+            ey += fabsf(cay * wp[11] - caz * wp[10]);
+        }
+    }
+    const bool stack_y = ex >= ey;
+    const int tw = stack_y ? TH : PXW, th = stack_y ? PXW : TH;      // tile = tw x th pixels
+    const int tiles_x = (p.W + tw - 1) / tw;
+    if ((long long)blockIdx.x >= (long long)tiles_x * ((p.H + th - 1) / th)) return;   // the grid covers the larger of the two tilings
+    const int x_raw = (int)(blockIdx.x % tiles_x) * tw + (stack_y ? wrp : pxi);
+    const int y_raw = (int)(blockIdx.x / tiles_x) * th + (stack_y ? pxi : wrp);
     const bool active = x_raw < p.W && y_raw < p.H;          // inactive lanes shadow a border pixel and store nothing
     const int x = min(x_raw, p.W - 1), y = min(y_raw, p.H - 1);
     const long long pix = (long long)y * p.W + x;
@@ -293,7 +318,8 @@ __global__ void __launch_bounds__(K1M_THREADS, 4) k1m_cost_volume_kernel(const K
 #pragma unroll
     for (int s = 0; s < S; s++) cur[s] = -2;
 
-    float *rec = &s_taps[wrp][pxi][0];
+    float4 *rec_w = s_w[wrp][pxi];
+    int *rec_c = s_cell[wrp][pxi];
     for (int k0 = d_begin; k0 < d_end; k0 += K1M_HC) {
         __syncwarp();   // the previous mini-chunk's records have been read
         // ---- geometry of the mini-chunk's (hypothesis, view) pairs, one per lane and round ----
@@ -339,10 +365,8 @@ __global__ void __launch_bounds__(K1M_THREADS, 4) k1m_cost_volume_kernel(const K
                     t = make_taps(gx, gy, Hs, Ws);
                 }
             }
-            float *e = rec + (k * S + sv) * K1M_TAPF;
-            *reinterpret_cast<float4 *>(e) = make_float4(t.w00, t.w00, t.w01, t.w01);
-            *reinterpret_cast<float4 *>(e + 4) = make_float4(t.w10, t.w10, t.w11, t.w11);
-            e[8] = __int_as_float(t.cell);
+            rec_w[k * S + sv] = make_float4(t.w00, t.w01, t.w10, t.w11);
+            rec_c[k * S + sv] = t.cell;
         }
         __syncwarp();
 
@@ -360,11 +384,11 @@ __global__ void __launch_bounds__(K1M_THREADS, 4) k1m_cost_volume_kernel(const K
             }
 #pragma unroll
             for (int s = 0; s < S; s++) {
-                const float *e = rec + (k * S + s) * K1M_TAPF;
-                const float4 wn = *reinterpret_cast<const float4 *>(e);       // {w00, w00, w01, w01}
-                const float4 ws = *reinterpret_cast<const float4 *>(e + 4);   // {w10, w10, w11, w11}
-                const int cell = __float_as_int(e[8]);
-                if (cell != cur[s]) {
+                const float4 wt = rec_w[k * S + s];             // {w00, w01, w10, w11}
+                const int cell = rec_c[k * S + s];
+                // a real, warp-uniform branch (the compiler would otherwise if-convert the block and issue its ~30 predicated
+                // instructions for every (hypothesis, view) whether or not any lane re-loads)
+                if (__any_sync(0xffffffffu, cell != cur[s]) && cell != cur[s]) {
                     const char *q0 = reinterpret_cast<const char *>(s_view[s].base + sub * 4) + (unsigned long long)(unsigned)cell * (C * 4);
                     const char *q1 = q0 + s_view[s].row_bytes;
                     ta[s] = ldg4(reinterpret_cast<const float *>(q0));
@@ -374,7 +398,7 @@ __global__ void __launch_bounds__(K1M_THREADS, 4) k1m_cost_volume_kernel(const K
                     cur[s] = cell;
                 }
                 // accumulation order nw, ne, sw, se (ATen grid_sampler_2d)
-                const float2 p00 = make_float2(wn.x, wn.y), p01 = make_float2(wn.z, wn.w), p10 = make_float2(ws.x, ws.y), p11 = make_float2(ws.z, ws.w);
+                const float2 p00 = make_float2(wt.x, wt.x), p01 = make_float2(wt.y, wt.y), p10 = make_float2(wt.z, wt.z), p11 = make_float2(wt.w, wt.w);
                 float2 wa = __fmul2_rn(make_float2(ta[s].x, ta[s].y), p00), wb = __fmul2_rn(make_float2(ta[s].z, ta[s].w), p00);
                 wa = __ffma2_rn(make_float2(tb[s].x, tb[s].y), p01, wa); wb = __ffma2_rn(make_float2(tb[s].z, tb[s].w), p01, wb);
                 wa = __ffma2_rn(make_float2(tc[s].x, tc[s].y), p10, wa); wb = __ffma2_rn(make_float2(tc[s].z, tc[s].w), p10, wb);
@@ -446,7 +470,10 @@ static int k1m_grid(const mvsb200_cost_volume_desc *d, dim3 &grid, int &seg, con
         int dev = 0;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const long long tiles = (long long)((d->W + pxw - 1) / pxw) * ((d->H + th - 1) / th);
+    // the kernel tiles the image pxw x th or th x pxw (see `stack_y`): enough blocks for either
+    const long long tiles_a = (long long)((d->W + pxw - 1) / pxw) * ((d->H + th - 1) / th);
+    const long long tiles_b = (long long)((d->W + th - 1) / th) * ((d->H + pxw - 1) / pxw);
+    const long long tiles = tiles_a > tiles_b ? tiles_a : tiles_b;
     MVSB200_REQUIRE(tiles < (1ll << 31), "%s: image too large", what);
     const int chunks = (d->D + K1M_HC - 1) / K1M_HC;
     long long nseg = (32ll * sms + tiles * d->B - 1) / (tiles * d->B);
