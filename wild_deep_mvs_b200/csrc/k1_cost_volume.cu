@@ -221,7 +221,40 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_cost_volume_kernel(const K1P
 // window re-load is a real warp-uniform branch (the compiler otherwise if-converts it into ~30 always-issued instructions).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int K1M_THREADS = 128;
+#ifndef K1M_MIN_BLOCKS
+#define K1M_MIN_BLOCKS 4
+#endif
+// Window re-loads one hypothesis ahead of the arithmetic (see the kernel): measured on B200 (profiles/k1_ab.py) -- group
+// correlation 0.112 -> 0.103 ms, variance-mean with per-pixel hypotheses 0.487 -> 0.462 ms, but cfg2's variance 0.262 -> 0.269 ms
+// (its arithmetic block is the longest and already covers the load latency): on for the first two, off otherwise.
+#ifndef K1M_AHEAD
+#define K1M_AHEAD(AGG) ((AGG) == MVSB200_AGG_GROUPCORR || (AGG) == MVSB200_AGG_VARIANCE_MEAN)
+#endif
+// ptxas if-converts a short conditional block into predicated instructions that are issued whether or not any lane needs
+// them; a block that ends in a (never taken) backward branch on a launch parameter the compiler knows nothing about stays a
+// branch: `if (warp-uniform condition) K1M_REAL_BRANCH_BEGIN { ... } K1M_REAL_BRANCH_END(positive_kernel_argument);`
+#define K1M_REAL_BRANCH_BEGIN do
+#define K1M_REAL_BRANCH_END(positive) while ((positive) < 0)
 constexpr int K1M_HC = 4;        // hypotheses per mini-chunk (geometry is shared per mini-chunk)
+
+// shared-memory record accesses by 32-bit shared address (+ compile-time offset folded into the instruction)
+__device__ __forceinline__ float4 lds128(unsigned a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds32(unsigned a)
+{
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(unsigned a, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(unsigned a, int v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 
 struct K1MView {                 // per source view, staged in shared memory once per block
     const float *base;           // first pixel of the view's map for batch item b
@@ -232,7 +265,7 @@ struct K1MView {                 // per source view, staged in shared memory onc
 };
 
 template <int C, int GEOM, int AGG, int S>
-__global__ void __launch_bounds__(K1M_THREADS, 4) k1m_cost_volume_kernel(const K1Params p, const int seg)
+__global__ void __launch_bounds__(K1M_THREADS, K1M_MIN_BLOCKS) k1m_cost_volume_kernel(const K1Params p, const int seg)
 {
     constexpr int L = C / 4;                // lanes per pixel, each owning 4 channels (one 16-byte vector per tap)
     constexpr int PXW = 32 / L;             // adjacent pixels per warp (along x or along y, see `stack_y`)
@@ -245,8 +278,12 @@ __global__ void __launch_bounds__(K1M_THREADS, 4) k1m_cost_volume_kernel(const K
     // tap records {w00, w01, w10, w11} + cell.  A broadcast LDS.128 costs the LSU pipe four wavefronts however few distinct
     // addresses it has (one per quarter warp) and that pipe, shared with the tap loads, is this kernel's busiest unit: the
     // record is therefore ONE 16-byte vector + one 4-byte word (5 wavefronts), the packed-pair weights are made with moves
-    __shared__ __align__(16) float4 s_w[TH][PXW][NREC + 1];   // + 1: the pixels of a warp start in different banks
-    __shared__ int s_cell[TH][PXW][NREC + 1];
+    // per pixel: NREC weight vectors, then NREC cells, padded to an odd number of 16-byte vectors (conflict-free across the pixels of a warp) -- ONE shared
+    // base address per lane (kept in a register) + immediate offsets
+    constexpr int REC_VECS = ((NREC * 20 + 15) / 16) | 1;   // odd number of 16-byte vectors: no bank conflicts between pixels
+    constexpr int REC_BYTES = REC_VECS * 16;
+    constexpr int REC_CELL = NREC * 16;     // byte offset of the cells inside a pixel's record block
+    __shared__ __align__(16) unsigned char s_rec[TH][PXW][REC_BYTES];
 
     const int b = blockIdx.z;
     const long long HW = (long long)p.H * p.W;
@@ -318,8 +355,31 @@ __global__ void __launch_bounds__(K1M_THREADS, 4) k1m_cost_volume_kernel(const K
 #pragma unroll
     for (int s = 0; s < S; s++) cur[s] = -2;
 
-    float4 *rec_w = s_w[wrp][pxi];
-    int *rec_c = s_cell[wrp][pxi];
+    // block-uniform view bases (batch item b) and row pitches in 16-byte vectors: launch parameters -> uniform registers
+    const float4 *vbase[S];
+    unsigned vrow[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        vbase[s] = reinterpret_cast<const float4 *>(p.src[s] + (long long)b * p.src_h[s] * p.src_w[s] * C);
+        vrow[s] = (unsigned)p.src_w[s] * L;
+    }
+    // this lane's 16-byte vector of the volume, advanced one plane per hypothesis
+    float4 *outp = reinterpret_cast<float4 *>(p.out + (((long long)b * p.D + d_begin) * HW + pix) * C + sub * 4);
+    const long long plane_vecs = HW * L;
+
+    unsigned rec = (unsigned)__cvta_generic_to_shared(&s_rec[wrp][pxi][0]);
+    unsigned rec_st = rec + (h_off * S + sv) * 16, rec_st_cell = rec + REC_CELL + (h_off * S + sv) * 4;   // the records this lane writes
+    asm volatile("" : "+r"(rec), "+r"(rec_st), "+r"(rec_st_cell));   // pinned: the compiler otherwise re-derives the addresses before every access
+    // the four depth modes of common.cuh hypothesis() as ONE expression: value(d) = dbase[d * dstride] + interval * d
+    // (a mode without an interval adds 0 * d, one with a start value reads the same word for every d)
+    const float *dbase;
+    long long dstride = 0;
+    switch (p.depth_mode) {
+    case MVSB200_DEPTH_VALUES: dbase = p.depth + (long long)b * p.D; dstride = 1; break;
+    case MVSB200_DEPTH_VOLUME: dbase = p.depth + (long long)b * p.D * HW + pix; dstride = HW; break;
+    case MVSB200_DEPTH_START: dbase = p.depth + b; break;
+    default: dbase = p.depth + (long long)b * HW + pix; break;
+    }
     for (int k0 = d_begin; k0 < d_end; k0 += K1M_HC) {
         __syncwarp();   // the previous mini-chunk's records have been read
         // ---- geometry of the mini-chunk's (hypothesis, view) pairs, one per lane and round ----
@@ -328,7 +388,7 @@ __global__ void __launch_bounds__(K1M_THREADS, 4) k1m_cost_volume_kernel(const K
             const int k = rd * R + h_off;
             if (R > K1M_HC && k >= K1M_HC) break;        // more lanes than (hypothesis, view) pairs: the rest sit the round out
             const int d = min(k0 + k, p.D - 1);
-            const float dv = hypothesis(p.depth_mode, p.depth, interval, b, d, p.D, HW, pix);
+            const float dv = __ldg(dbase + (long long)d * dstride) + interval * (float)d;   // common.cuh hypothesis(), branch-free
             float gx, gy;
             if (GEOM == MVSB200_GEOM_MVS) {
                 const float qx = ax * dv + bx, qy = ay * dv + by, qz = az * dv + bz;
@@ -365,11 +425,36 @@ __global__ void __launch_bounds__(K1M_THREADS, 4) k1m_cost_volume_kernel(const K
                     t = make_taps(gx, gy, Hs, Ws);
                 }
             }
-            rec_w[k * S + sv] = make_float4(t.w00, t.w01, t.w10, t.w11);
-            rec_c[k * S + sv] = t.cell;
+            sts128(rec_st + rd * (R * S * 16), make_float4(t.w00, t.w01, t.w10, t.w11));
+            sts32(rec_st_cell + rd * (R * S * 4), t.cell);
         }
         __syncwarp();
 
+        // Window re-loads of hypothesis k (all S views): a real, warp-uniform branch per view (the compiler would otherwise
+        // if-convert the block and issue its predicated instructions for every (hypothesis, view) whether or not any lane
+        // re-loads).  They run one hypothesis AHEAD of the arithmetic -- after the taps of hypothesis k-1 have been consumed,
+        // before its epilogue and store -- so the loads are in flight while other instructions issue, and the arithmetic of
+        // the S views below is one straight-line block (8 independent FMA chains) that the branches do not cut.
+#define K1M_RELOAD_VIEW(s, cell)                                                                                 \
+        if (__any_sync(0xffffffffu, (cell) != cur[s])) K1M_REAL_BRANCH_BEGIN {                                   \
+            if ((cell) != cur[s]) {                                                                              \
+                /* block-uniform view base (uniform registers) + this lane's 16-byte vector index */             \
+                const float4 *q0 = vbase[s] + ((unsigned)(cell) * L + sub);                                      \
+                const float4 *q1 = q0 + vrow[s];                                                                 \
+                ta[s] = __ldg(q0);                                                                               \
+                tb[s] = __ldg(q0 + L);                                                                           \
+                tc[s] = __ldg(q1);                                                                               \
+                td[s] = __ldg(q1 + L);                                                                           \
+                cur[s] = (cell);                                                                                 \
+            }                                                                                                    \
+        } K1M_REAL_BRANCH_END(seg);
+#define K1M_RELOAD(k)                                                                                            \
+        {                                                                                                        \
+            int cells[S];                                                                                        \
+            _Pragma("unroll") for (int s = 0; s < S; s++) cells[s] = lds32(rec + REC_CELL + ((k) * S + s) * 4);   \
+            _Pragma("unroll") for (int s = 0; s < S; s++) { K1M_RELOAD_VIEW(s, cells[s]) }                       \
+        }
+        if (K1M_AHEAD(AGG)) K1M_RELOAD(0)
 #pragma unroll
         for (int k = 0; k < K1M_HC; k++) {
             const int d = k0 + k;
@@ -382,21 +467,15 @@ __global__ void __launch_bounds__(K1M_THREADS, 4) k1m_cost_volume_kernel(const K
             } else {
                 m1a = m1b = m2a = m2b = make_float2(0.f, 0.f);
             }
+            int cells[S];                                // all S cell loads in flight before the first vote waits on one
+            if (!K1M_AHEAD(AGG)) {
+#pragma unroll
+                for (int s = 0; s < S; s++) cells[s] = lds32(rec + REC_CELL + (k * S + s) * 4);
+            }
 #pragma unroll
             for (int s = 0; s < S; s++) {
-                const float4 wt = rec_w[k * S + s];             // {w00, w01, w10, w11}
-                const int cell = rec_c[k * S + s];
-                // a real, warp-uniform branch (the compiler would otherwise if-convert the block and issue its ~30 predicated
-                // instructions for every (hypothesis, view) whether or not any lane re-loads)
-                if (__any_sync(0xffffffffu, cell != cur[s]) && cell != cur[s]) {
-                    const char *q0 = reinterpret_cast<const char *>(s_view[s].base + sub * 4) + (unsigned long long)(unsigned)cell * (C * 4);
-                    const char *q1 = q0 + s_view[s].row_bytes;
-                    ta[s] = ldg4(reinterpret_cast<const float *>(q0));
-                    tc[s] = ldg4(reinterpret_cast<const float *>(q1));
-                    tb[s] = ldg4(reinterpret_cast<const float *>(q0) + C);
-                    td[s] = ldg4(reinterpret_cast<const float *>(q1) + C);
-                    cur[s] = cell;
-                }
+                const float4 wt = lds128(rec + (k * S + s) * 16);             // {w00, w01, w10, w11}
+                if (!K1M_AHEAD(AGG)) { K1M_RELOAD_VIEW(s, cells[s]) }
                 // accumulation order nw, ne, sw, se (ATen grid_sampler_2d)
                 const float2 p00 = make_float2(wt.x, wt.x), p01 = make_float2(wt.y, wt.y), p10 = make_float2(wt.z, wt.z), p11 = make_float2(wt.w, wt.w);
                 float2 wa = __fmul2_rn(make_float2(ta[s].x, ta[s].y), p00), wb = __fmul2_rn(make_float2(ta[s].z, ta[s].w), p00);
@@ -428,6 +507,7 @@ __global__ void __launch_bounds__(K1M_THREADS, 4) k1m_cost_volume_kernel(const K
                     }
                 }
             }
+            if (K1M_AHEAD(AGG) && k + 1 < K1M_HC && d + 1 < d_end) K1M_RELOAD(k + 1)
             if (AGG != MVSB200_AGG_GROUPCORR && active) {
                 float2 oa, ob;
                 if (AGG == MVSB200_AGG_VARIANCE) {           // M2/V - M1^2/V^2 (models/MVSNet/model.py:134)
@@ -445,9 +525,12 @@ __global__ void __launch_bounds__(K1M_THREADS, 4) k1m_cost_volume_kernel(const K
                     ob = __fmul2_rn(m1b, make_float2(rden, rden));
                 }
                 vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(oa.x), fabsf(oa.y))), fmaxf(fabsf(ob.x), fabsf(ob.y)));
-                st4_stream(p.out + (((long long)b * p.D + d) * HW + pix) * C + sub * 4, make_float4(oa.x, oa.y, ob.x, ob.y));
+                __stcs(outp, make_float4(oa.x, oa.y, ob.x, ob.y));
             }
+            outp += plane_vecs;
         }
+#undef K1M_RELOAD
+#undef K1M_RELOAD_VIEW
     }
     if (p.out_amax) {
 #pragma unroll
