@@ -1,4 +1,6 @@
-"""One eager pass of the Vis-MVSNet hot path at cfg3 size (for `ncu --metrics gpu__time_duration.sum` launch lists)."""
+"""One eager pass of the Vis-MVSNet hot path at cfg3 size (for `ncu --metrics gpu__time_duration.sum` launch lists).
+
+    python profiles/vis_once.py [batch of reference views, default 1] [eval: depth_nums [64,32,16] instead of [32,16,8]]"""
 import os
 import sys
 
@@ -13,8 +15,9 @@ torch.manual_seed(0)
 net = Vis()
 synth.randomize_norm_stats(net, seed=2)
 net = net.to(DEV).eval()
-s = {k: v.to(DEV) for k, v in synth.make_sample(1, 5, 512, 640, seed=0).items()}
-nums, scales = [32, 16, 8], [4, 2, 1]
+NB = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+s = {k: v.to(DEV) for k, v in synth.make_sample(NB, 5, 512, 640, seed=0).items()}
+nums, scales = ([64, 32, 16], [2, 1, 0.5]) if "eval" in sys.argv[2:] else ([32, 16, 8], [4, 2, 1])
 with torch.no_grad():
     interval = ((s["depth_max"] - s["depth_min"]) / 128)
     ref_cam = net.fill_cam_array(s["K"][:, 0], s["R"][:, 0], s["t"][:, 0], s["depth_min"][:, 0], interval[:, 0])
