@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MVSB200_ABI_VERSION 5
+#define MVSB200_ABI_VERSION 6
 
 #define MVSB200_OK 0
 #define MVSB200_E_INVALID (-1)  /* bad argument / unsupported shape */
@@ -292,6 +292,23 @@ MVSB200_API int mvsb200_geometric_filter(const float *depth, int H, int W, const
                                          float depth_threshold, float max_reproj_error, float min_tri_angle, int num_consistent,
                                          unsigned char *mask_depth, unsigned char *mask_disp, unsigned char *geo_mask,
                                          unsigned char *votes, mvsb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K9: the consumer of the all-gathered depth maps, row f3 of SURVEY.md 8 -- the geometric half of
+ * masked_photometricloss (models/trainer.py:240-278) with get_flow_from_depthmap (:209-219),
+ * flows_from_single_depthmap (utils/utils_3D.py:190-211) and normalize (:243-268): per pixel of this rank's depth map
+ * and source view, re-project with the 4x4 projection matrices, sample the GATHERED depth map of that view
+ * (grid_sample bilinear / zeros / align_corners=False) and keep the pixel where the relative depth difference is below
+ * geom_clamping and the sample falls inside the image.
+ * ref_depth [B,H,W]; gathered [B,N,H,W] (the all-gather's output; view `ref` is skipped); proj [B,N,4,4];
+ * inv_ref [B,4,4] = proj[:, ref]^-1; imgs [B,N,C,H,W] or NULL.  Sources are ordered as the reference's src_idx (all
+ * views but `ref`, ascending).  Outputs over [B,N-1,H,W]: mask (bytes 0/1, required); optional inside (bytes),
+ * grid [..,2] (the normalised sampling grid), depth_src, warped_depth, warped [B,N-1,C,H,W] (the images sampled with the
+ * same grid: what the SSIM term compares with the reference image). */
+MVSB200_API int mvsb200_gathered_masks(int B, int N, int C, int H, int W, int ref, const float *ref_depth, const float *gathered,
+                                       const float *proj, const float *inv_ref, const float *imgs, float geom_clamping,
+                                       unsigned char *mask, unsigned char *inside, float *grid, float *depth_src,
+                                       float *warped_depth, float *warped, mvsb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Multi-GPU: independent reference views per rank, ONE all-gather of the per-view depth maps -- the

@@ -76,3 +76,50 @@ def geometric_filter(depth, src_depths, K, R, t, depth_threshold=0.01, max_repro
     k = num_consistent - 1
     cnt = lambda ms: (np.sum(ms, axis=0) >= k).reshape(h, w)
     return {"mask_depth": cnt(dep_masks), "mask_disp": cnt(disp_masks), "geo_mask": cnt(geo_masks), "seams": seams}
+
+
+def gathered_masks(ref_depth, gathered, proj_mat, ref_idx, geom_clamping=0.05, imgs=None):
+    """The geometric half of `masked_photometricloss` (models/trainer.py:240-278 of the reference) in numpy fp32:
+    `flows_from_single_depthmap` (utils/utils_3D.py:190-211: points3D = add_hom(add_hom(grid) * depth) @ inv(P_ref)^T,
+    reprojected = points3D @ P_src^T, flow = xy / clamp(z, 1e-6)), `normalize` (:243-268: 2 f / (size - 1) - 1),
+    `get_flow_from_depthmap` (trainer.py:209-219: z <= 0 -> -10, clamp +-10), the inside mask (:258), the bilinear /
+    zeros / align_corners=False samples of the gathered depth maps and images (:261-262) and the re-projection mask
+    (:264-267).  ref_depth [b,h,w], gathered [b,N,h,w], proj_mat [b,N,4,4], imgs [b,N,c,h,w] or None.
+    Returns dict(masks, inside [b,N-1,h,w] bool; flows [b,N-1,h,w,2]; depth_src, warped_depth, reproj_diff [b,N-1,h,w];
+    warped [b,N-1,c,h,w] or None).  Pinned by tests/golden/gathered_masks.npz (the unmodified reference function)."""
+    ref_depth = np.asarray(ref_depth, f32)
+    gathered = np.asarray(gathered, f32)
+    proj_mat = np.asarray(proj_mat, f32)
+    b, N, h, w = gathered.shape
+    src_idx = [i for i in range(N) if i != ref_idx]
+    ys, xs = np.meshgrid(np.arange(h, dtype=f32), np.arange(w, dtype=f32), indexing="ij")
+    S = N - 1
+    flows = np.zeros((b, S, h, w, 2), f32)
+    depth_src = np.zeros((b, S, h, w), f32)
+    warped_depth = np.zeros((b, S, h, w), f32)
+    warped = None if imgs is None else np.zeros((b, S, imgs.shape[2], h, w), f32)
+    for bi in range(b):
+        inv = np.linalg.inv(proj_mat[bi, ref_idx].astype(np.float64)).astype(f32)
+        d = ref_depth[bi]
+        hom = np.stack([xs * d, ys * d, d, np.ones_like(d)], -1).astype(f32)           # [h,w,4]
+        X = (hom @ inv.T).astype(f32)
+        for j, s in enumerate(src_idx):
+            q = (X @ proj_mat[bi, s].T).astype(f32)
+            z = q[..., 2]
+            zc = np.maximum(z, f32(1e-6))
+            gx = (f32(2) * (q[..., 0] / zc) / f32(w - 1) - f32(1)).astype(f32)
+            gy = (f32(2) * (q[..., 1] / zc) / f32(h - 1) - f32(1)).astype(f32)
+            behind = z <= 0
+            gx = np.clip(np.where(behind, f32(-10), gx), f32(-10), f32(10)).astype(f32)
+            gy = np.clip(np.where(behind, f32(-10), gy), f32(-10), f32(10)).astype(f32)
+            flows[bi, j, ..., 0], flows[bi, j, ..., 1] = gx, gy
+            depth_src[bi, j] = z
+            warped_depth[bi, j] = _grid_sample_bilinear_zeros(gathered[bi, s], gx, gy)
+            if imgs is not None:
+                for c in range(imgs.shape[2]):
+                    warped[bi, j, c] = _grid_sample_bilinear_zeros(np.asarray(imgs[bi, s, c], f32), gx, gy)
+    inside = (flows < 1).all(-1) & (flows > -1).all(-1)
+    reproj_diff = (np.abs(depth_src - warped_depth) / np.maximum(warped_depth, f32(1e-8))).astype(f32)
+    masks = inside & (reproj_diff < f32(geom_clamping))
+    return {"masks": masks, "inside": inside, "flows": flows, "depth_src": depth_src, "warped_depth": warped_depth,
+            "reproj_diff": reproj_diff, "warped": warped}

@@ -27,7 +27,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in _declared():
         assert hasattr(lib, name), name
     assert set(_declared()) == set(_lib.SIGNATURES), "ctypes binding and header disagree"
-    assert _lib.load().mvsb200_abi_version() == _lib.ABI_VERSION == 5
+    assert _lib.load().mvsb200_abi_version() == _lib.ABI_VERSION == 6
 
 
 def test_struct_layouts_match_header():

@@ -95,3 +95,85 @@ def test_errors_are_loud():
         geometric_filter(d, [], eye[:1], eye[:1], torch.zeros(1, 3, device=DEV))
     with pytest.raises(L.Mvsb200Error):
         geometric_filter(d, [d], eye, eye, torch.zeros(3, 3, device=DEV))   # 1 + N cameras expected
+
+
+# ---- K9: the consumer of the all-gathered depth maps (masked_photometricloss, models/trainer.py:240-278) ----------------
+from oracle.filter import gathered_masks as oracle_gathered  # noqa: E402
+from wild_deep_mvs_b200.filtering import gathered_masks  # noqa: E402
+
+
+def check_gathered(out, orc, geom_clamping, eps=1e-4):
+    """Masks are boolean work: the kernel may differ from the oracle only where the pixel sits ON a boundary -- the grid
+    within eps of +-1 (inside test) or the relative depth difference within eps (relative) of geom_clamping."""
+    got = out["masks"].cpu().numpy()
+    assert got.shape == orc["masks"].shape
+    g = orc["flows"].astype(np.float64)
+    edge = np.min(np.abs(np.abs(g) - 1.0), axis=-1)
+    thr = np.abs(orc["reproj_diff"].astype(np.float64) - geom_clamping) / geom_clamping
+    margin = np.minimum(edge, thr)
+    bad = got != orc["masks"]
+    off = bad & ~(margin < eps)
+    assert not off.any(), "%d of %d differing pixels are not on a boundary" % (int(off.sum()), int(bad.sum()))
+    assert bad.mean() < 1e-3, bad.mean()
+    print("gathered masks: %d of %d pixels differ, all within %.0e of a boundary" % (int(bad.sum()), bad.size, eps))
+    assert np.abs(out["flows"].cpu().numpy() - orc["flows"]).max() < 2e-5
+    assert np.abs(out["depth_src"].cpu().numpy() - orc["depth_src"]).max() < 1e-5 * np.abs(orc["depth_src"]).max()
+    ok = np.isfinite(orc["warped_depth"])
+    # a sample next to a depth discontinuity (the scenes have 650-unit steps) amplifies the last bits of the grid coordinate
+    assert np.abs(out["warped_depth"].cpu().numpy() - orc["warped_depth"])[ok].max() < 2e-4 * np.abs(orc["warped_depth"][ok]).max()
+    if orc["warped"] is not None:
+        assert np.abs(out["warped"].cpu().numpy() - orc["warped"]).max() < 5e-5
+    assert (out["inside"].cpu().numpy() != orc["inside"]).mean() < 1e-3
+
+
+def test_gathered_masks_against_the_reference(golden):
+    g = golden("gathered_masks")
+    out = gathered_masks(cu(g["ref_depth"]), cu(g["gathered"]), cu(g["proj"]), int(g["ref_idx"]), float(g["geom_clamping"]),
+                         imgs=cu(g["imgs"]), want=("inside", "flows", "depth_src", "warped_depth", "warped"))
+    orc = oracle_gathered(g["ref_depth"], g["gathered"], g["proj"], int(g["ref_idx"]), float(g["geom_clamping"]), g["imgs"])
+    assert (orc["masks"] != g["masks"]).sum() == 0          # the oracle IS the reference on this scene (also a CPU test)
+    check_gathered(out, orc, float(g["geom_clamping"]))
+    # what the unmodified reference recorded: the warped source images under its masks
+    got = np.clip((out["warped"] * out["masks"][:, :, None]).cpu().numpy(), 0, 1)
+    differ = (out["masks"].cpu().numpy() != g["masks"])[:, :, None]
+    assert np.abs(got - g["warped_masked"])[~np.broadcast_to(differ, got.shape)].max() < 5e-5
+
+
+@pytest.mark.parametrize("ref_idx", [0, 2, 4])
+def test_gathered_masks_against_oracle_random_scene(ref_idx):
+    rng = np.random.default_rng(11 + ref_idx)
+    b, N, h, w = 2, 5, 96, 136
+    proj = np.zeros((b, N, 4, 4), np.float32)
+    gathered = np.zeros((b, N, h, w), np.float32)
+    for bi in range(b):
+        for v in range(N):
+            K = np.array([[700.0, 0, w / 2.0], [0, 690.0, h / 2.0], [0, 0, 1]])
+            a = 0.015 * v * (1 if v % 2 else -1)
+            R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+            t = np.array([[-12.0 * v * (1 if v % 2 else -0.7)], [2.0 * v], [0.5 * v]])
+            P = np.eye(4)
+            P[:3, :3], P[:3, 3:] = K @ R, K @ t
+            proj[bi, v] = P
+            ys, xs = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+            gathered[bi, v] = 650 + 0.4 * xs - 0.3 * ys + 30 * np.sin(xs / 9.0 + v) + rng.standard_normal((h, w)) * 6
+    gathered[:, :, :6] = 0.0        # a band of zero depth (the clamp of the divisor) ...
+    gathered[0, 1, 40:50, 60:80] = -5.0   # ... and a block behind the camera
+    ref_depth = gathered[:, ref_idx].copy()
+    imgs = rng.random((b, N, 3, h, w)).astype(np.float32)
+    out = gathered_masks(cu(ref_depth), cu(gathered), cu(proj), ref_idx, 0.05, imgs=cu(imgs),
+                         want=("inside", "flows", "depth_src", "warped_depth", "warped"))
+    orc = oracle_gathered(ref_depth, gathered, proj, ref_idx, 0.05, imgs)
+    assert 0.05 < orc["masks"].mean() < 0.95
+    check_gathered(out, orc, 0.05)
+
+
+def test_gathered_masks_rejects_bad_arguments():
+    from wild_deep_mvs_b200._lib import Mvsb200Error
+    d = torch.ones(1, 3, 8, 8, device=DEV)
+    P = torch.eye(4, device=DEV).repeat(1, 3, 1, 1)
+    with pytest.raises(Mvsb200Error):
+        gathered_masks(d[:, 0], d, P, 3)                       # reference index out of range
+    with pytest.raises(Mvsb200Error):
+        gathered_masks(d[:, 0], d, P[:, :2], 0)                # projections of another view count
+    with pytest.raises(Mvsb200Error):
+        gathered_masks(d[:, 0], d, P, 0, want=("warped",))     # warped images without images

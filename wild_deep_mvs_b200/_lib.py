@@ -15,7 +15,7 @@ DEPTH_VALUES, DEPTH_VOLUME, DEPTH_START, DEPTH_START_MAP = 0, 1, 2, 3
 SKIP_NONE, SKIP_BEFORE_RELU, SKIP_AFTER_RELU = 0, 1, 2
 CONF_NONE, CONF_SUM4, CONF_WINDOW = 0, 1, 2
 PRECISION_3XTF32, PRECISION_TF32 = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class Mvsb200Error(RuntimeError):
@@ -74,6 +74,7 @@ SIGNATURES = {
     "mvsb200_conv2d": (_i, [_i] * 8 + [_vp] * 6),
     "mvsb200_geometric_filter": (_i, [_vp, _i, _i, ctypes.POINTER(_vp), ctypes.POINTER(_i), ctypes.POINTER(_i), _i, _vp, _vp, _vp,
                                       ctypes.c_float, ctypes.c_float, ctypes.c_float, _i, _vp, _vp, _vp, _vp, _vp]),
+    "mvsb200_gathered_masks": (_i, [_i] * 6 + [_vp] * 5 + [ctypes.c_float] + [_vp] * 7),
     "mvsb200_vis_fuse": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "mvsb200_gather_unique_id": (_i, [_vp]),
     "mvsb200_gather_init": (_i, [_vp, _i, _i, ctypes.POINTER(_vp)]),

@@ -41,3 +41,54 @@ def geometric_filter(depth, src_depths, K, R, t, depth_threshold=0.01, max_repro
     if want_votes:
         out["votes"] = votes
     return out
+
+
+def gathered_masks(ref_depth, gathered, proj_mat, ref_idx, geom_clamping=0.05, imgs=None, want=()):
+    """The consumer of the all-gathered depth maps (K9, mvsb200_gathered_masks): the geometric half of the reference's
+    `masked_photometricloss` (models/trainer.py:240-278) -- `get_flow_from_depthmap` (:209-219) + the re-projection mask.
+
+    ref_depth [b,h,w]: the depth map this rank computed with view `ref_idx` as its reference; gathered [b,N,h,w]: the
+    output of the path's ONE all-gather (`shard.DepthGather.all_gather()` reshaped, or `torch.stack(all_depthmaps, 1)` in
+    the reference's terms); proj_mat [b,N,4,4] (`build_proj_matrices`); `geom_clamping` = the reference's
+    `--geom_clamping` (train.py:278); imgs [b,N,c,h,w] optional.  Sources are all views but `ref_idx`, ascending.
+    Returns dict(masks bool [b,N-1,h,w]) plus what `want` names of: "inside" (bool), "flows" ([b,N-1,h,w,2], the clamped
+    normalised grid), "depth_src", "warped_depth" ([b,N-1,h,w]), "warped" ([b,N-1,c,h,w], needs imgs).
+    The inverse of the reference view's projection is a 4x4 `torch.inverse` on the device, as in the reference."""
+    lib = L.load()
+    ref_depth = _dev_f32(ref_depth.contiguous(), "ref_depth")
+    gathered = _dev_f32(gathered.contiguous(), "gathered")
+    proj_mat = _dev_f32(proj_mat.contiguous(), "proj_mat")
+    b, n, h, w = gathered.shape
+    if tuple(ref_depth.shape) != (b, h, w) or tuple(proj_mat.shape) != (b, n, 4, 4):
+        raise L.Mvsb200Error("gathered_masks: ref_depth %s / proj_mat %s do not match gathered %s"
+                             % (tuple(ref_depth.shape), tuple(proj_mat.shape), tuple(gathered.shape)))
+    if not 0 <= int(ref_idx) < n:
+        raise L.Mvsb200Error("gathered_masks: reference view %d not in [0,%d)" % (ref_idx, n))
+    unknown = set(want) - {"inside", "flows", "depth_src", "warped_depth", "warped"}
+    if unknown:
+        raise L.Mvsb200Error("gathered_masks: unknown outputs %s" % sorted(unknown))
+    c = 0
+    if imgs is not None:
+        imgs = _dev_f32(imgs.contiguous(), "imgs")
+        c = imgs.shape[2]
+        if tuple(imgs.shape) != (b, n, c, h, w):
+            raise L.Mvsb200Error("gathered_masks: imgs %s do not match gathered %s" % (tuple(imgs.shape), tuple(gathered.shape)))
+    if "warped" in want and imgs is None:
+        raise L.Mvsb200Error("gathered_masks: 'warped' needs imgs")
+    inv_ref = torch.inverse(proj_mat[:, ref_idx]).contiguous()
+    dev = gathered.device
+    new = lambda *shape, dt=torch.float32: torch.empty(shape, device=dev, dtype=dt)
+    mask = new(b, n - 1, h, w, dt=torch.uint8)
+    inside = new(b, n - 1, h, w, dt=torch.uint8) if "inside" in want else None
+    flows = new(b, n - 1, h, w, 2) if "flows" in want else None
+    depth_src = new(b, n - 1, h, w) if "depth_src" in want else None
+    warped_depth = new(b, n - 1, h, w) if "warped_depth" in want else None
+    warped = new(b, n - 1, c, h, w) if "warped" in want else None
+    L.check(lib.mvsb200_gathered_masks(b, n, c, h, w, int(ref_idx), _ptr(ref_depth), _ptr(gathered), _ptr(proj_mat), _ptr(inv_ref),
+                                       _ptr(imgs), ctypes.c_float(geom_clamping), _ptr(mask), _ptr(inside), _ptr(flows),
+                                       _ptr(depth_src), _ptr(warped_depth), _ptr(warped), _stream()), "mvsb200_gathered_masks")
+    out = {"masks": mask.bool()}
+    for name, t in (("inside", inside), ("flows", flows), ("depth_src", depth_src), ("warped_depth", warped_depth), ("warped", warped)):
+        if t is not None:
+            out[name] = t.bool() if t.dtype == torch.uint8 else t
+    return out
