@@ -92,6 +92,27 @@ def vis_graphed(name, net, s, vox, nums, scales):
     return r
 
 
+def mvs_graphed(name, net, s, vox):
+    """Hot path of MVSNet / MVSNet-s replayed as one CUDA graph (features resident), as bench.py measures cfg2."""
+    from wild_deep_mvs_b200.mvsnet import build_proj_matrices
+    net = net.to(DEV).eval()
+    with torch.no_grad():
+        feats = [ops.to_nhwc(f) for f in net.extract_features(list(torch.unbind(s["imgs"], 1)))]
+        K = s["K"].clone()
+        K[:, :, :2] /= 4
+        projs = list(torch.unbind(build_proj_matrices(K, s["R"], s["t"]), 1))
+        D = net.num_depth
+        depth = s["depth_min"][:, :1] + (s["depth_max"][:, :1] - s["depth_min"][:, :1]) / (D - 1) * torch.arange(D, device=DEV).view(1, -1)
+        g = net.graphed(feats, projs, depth)
+        eager = net.depth_from_features(feats, projs, depth)
+        assert torch.equal(g()[0], eager[0])
+        ms = timed(lambda: g(), reps=50, warmup=5)
+    r = {"config": name + " -- hot path as one CUDA graph", "voxels": vox, "hot_path_ms": round(ms, 3),
+         "hot_path_Mvox_per_s": round(vox / ms / 1e3, 1)}
+    print(json.dumps(add_roofline(r)), flush=True)
+    return r
+
+
 def main():
     torch.manual_seed(0)
     res = []
@@ -103,6 +124,7 @@ def main():
         synth.randomize_norm_stats(net, seed=1)
         net.num_depth = D
         res.append(run(name, net, sample(views, 512, 640), D * 128 * 160, feat_mvs))
+        res.append(mvs_graphed(name, net, sample(views, 512, 640), D * 128 * 160))
     # cfg3: Vis-MVSNet, 1+4 views, 640x512, default [32,16,8] and eval [64,32,16] hypotheses per stage
     feat_vis = lambda net, s: ops.map_views(net.model.feat_ext, torch.unbind(s["imgs"], 1))
     for name, nums, scales in (("cfg3 Vis-MVSNet 1+4 views 640x512 depth_nums [32,16,8]", [32, 16, 8], [4, 2, 1]),

@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(K1M_THREADS, K1M_MIN_BLOCKS) k1m_cost_volume_k
     // this lane's 16-byte vector of the volume, advanced one plane per hypothesis
     float4 *outp = reinterpret_cast<float4 *>(p.out + (((long long)b * p.D + d_begin) * HW + pix) * C + sub * 4);
     const long long plane_vecs = HW * L;
+    float *outg = p.out + (((long long)b * p.D + d_begin) * HW + pix) * L + sub;   // group correlation: one float per lane, plane and view
 
     unsigned rec = (unsigned)__cvta_generic_to_shared(&s_rec[wrp][pxi][0]);
     unsigned rec_st = rec + (h_off * S + sv) * 16, rec_st_cell = rec + REC_CELL + (h_off * S + sv) * 4;   // the records this lane writes
@@ -501,10 +502,8 @@ __global__ void __launch_bounds__(K1M_THREADS, K1M_MIN_BLOCKS) k1m_cost_volume_k
                     g += r0.y * wa.y;
                     g += r1.x * wb.x;
                     g += r1.y * wb.y;
-                    if (active) {
-                        vmax = fmaxf(vmax, fabsf(g));
-                        __stcs(p.out + s * p.out_view_stride + (((long long)b * p.D + d) * HW + pix) * L + sub, g);
-                    }
+                    vmax = fmaxf(vmax, fabsf(g));
+                    if (active) __stcs(outg + s * p.out_view_stride, g);   // this lane's group of plane d; + the view's volume (uniform)
                 }
             }
             if (K1M_AHEAD(AGG) && k + 1 < K1M_HC && d + 1 < d_end) K1M_RELOAD(k + 1)
@@ -528,6 +527,7 @@ __global__ void __launch_bounds__(K1M_THREADS, K1M_MIN_BLOCKS) k1m_cost_volume_k
                 __stcs(outp, make_float4(oa.x, oa.y, ob.x, ob.y));
             }
             outp += plane_vecs;
+            outg += plane_vecs;       // (floats: a plane of the L-group volume has HW * L of them)
         }
 #undef K1M_RELOAD
 #undef K1M_RELOAD_VIEW
