@@ -36,6 +36,13 @@ METRICS = [
     ("launch__registers_per_thread", "regs/thread"),
     ("launch__occupancy_limit_shared_mem", "occ limit smem (CTAs)"),
     ("smsp__inst_executed.sum", "warp instructions"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1/shared data pipe (LSU wavefronts) %"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
+    ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "warps stalled: fixed-latency wait / issue"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "warps stalled: long scoreboard / issue"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "warps stalled: short scoreboard / issue"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "warps stalled: math pipe throttle / issue"),
     ("launch__grid_size", "grid"),
     ("launch__block_size", "block"),
 ]
