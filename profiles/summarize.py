@@ -39,6 +39,8 @@ METRICS = [
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
     ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1/shared data pipe (LSU wavefronts) %"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "shared data pipe: LSU wavefronts (LDS / STS) % of peak"),
+    ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "shared data pipe: tensor-core operand wavefronts % of peak"),
     ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "warps stalled: fixed-latency wait / issue"),
     ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "warps stalled: long scoreboard / issue"),
     ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "warps stalled: short scoreboard / issue"),
