@@ -279,6 +279,13 @@ MVSB200_API int mvsb200_vis_uncert_net(const float *entropy, int N, int H, int W
 MVSB200_API int mvsb200_conv2d(int B, int H, int W, int Cin, int Cout, int k, int stride, int relu, const float *x, const float *w,
                                const float *scale, const float *bias, float *y, mvsb200_stream_t stream);
 
+/* K7b: y = act(y * scale[c] + bias[c] (+ residual)) in place over a channels-last map y [n_pixels, C] (C % 4 == 0, 16-byte
+ * aligned): the fused epilogue behind a convolution library call that has none -- CVP-MVSNet's `conv` = Conv2d(bias) +
+ * LeakyReLU(0.1) (models/CVP_MVSNet/models/modules.py:24-28; slope 0.1), eval-mode BatchNorm + ReLU (+ skip) of the 2-D
+ * BasicBlocks (slope 0).  scale, residual may be NULL; slope = 1 is no activation. */
+MVSB200_API int mvsb200_bias_act(float *y, long long n_pixels, int C, const float *scale, const float *bias, const float *residual,
+                                 float slope, mvsb200_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * K8: geometric-consistency filter of one depth map against its N source depth maps (evaluation/filtering.py:59-84
  * with utils/utils_3D.py:64-73,98-132,162-178,243-273,296-311), row f3 of SURVEY.md 8.

@@ -151,3 +151,37 @@ def test_k5_depth_hypotheses_against_oracle():
     got = cal_depth_hypo(d[:1], K[:1, 0].to(DEV), K[:1, :1].to(DEV), E[:1, 0].to(DEV), E[:1, :1].to(DEV), dmin[:1, 0].to(DEV), dmax[:1, 0].to(DEV))
     step = (got[0, 5] - got[0, 4])[5:].cpu().numpy()
     assert np.allclose(step, (905.0 - 425.0) / 128, rtol=1e-4)
+
+
+def test_bias_act_kernel_and_fused_pyramid():
+    """K7b (mvsb200_bias_act): y = act(y * scale + bias (+ residual)) in place over channels-last maps -- against the torch
+    expression, bit for bit (one fma / add per element, same order); and the CVP FeaturePyramid through it (cuDNN
+    convolution without bias + ONE fused pass) against the plain nn.Conv2d + nn.LeakyReLU modules."""
+    from wild_deep_mvs_b200 import ops
+    from wild_deep_mvs_b200.cvpmvsnet import FeaturePyramid
+    torch.manual_seed(0)
+    y = torch.randn(2, 16, 37, 53, device=DEV).contiguous(memory_format=torch.channels_last)
+    b, s = torch.randn(16, device=DEV), torch.rand(16, device=DEV) + 0.5
+    r = torch.randn_like(y)
+    want = torch.nn.functional.leaky_relu(y + b.view(1, -1, 1, 1), 0.1)
+    assert torch.equal(ops.bias_act_(y.clone(memory_format=torch.channels_last), b, slope=0.1), want)
+    want = torch.relu(torch.addcmul(b.view(1, -1, 1, 1), y, s.view(1, -1, 1, 1)) + r)      # fma(y, s, b) + r
+    got = ops.bias_act_(y.clone(memory_format=torch.channels_last), b, scale=s, residual=r, slope=0.0)
+    assert (got - want).abs().max() <= 1e-6 * want.abs().max()
+    yn = y.permute(0, 2, 3, 1).contiguous()
+    assert torch.equal(ops.bias_act_(yn.clone(), b, slope=1.0, nhwc=True), yn + b)
+    with pytest.raises(Exception):
+        ops.bias_act_(torch.randn(1, 6, 4, 4, device=DEV).contiguous(memory_format=torch.channels_last), torch.zeros(6, device=DEV))
+    net = FeaturePyramid().to(DEV).eval()
+    img = torch.rand(2, 3, 72, 104, device=DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            fused = net(img, 3)
+        with torch.enable_grad():
+            plain = [t.detach() for t in net(img, 3)]
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    for a, c in zip(fused, plain):
+        assert a.shape == c.shape and (a - c).abs().max() <= 2e-6 * c.abs().max()

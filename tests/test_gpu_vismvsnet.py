@@ -156,3 +156,31 @@ def test_featext_on_library_kernels_against_reference_golden(golden):
         torch.backends.cudnn.allow_tf32 = old
     for a, b in zip(lib, plain):
         assert a.shape == b.shape and rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 1e-4
+
+
+def test_featext_fused_inference_path_against_reference_golden(golden):
+    """Row f1, the DEFAULT inference path of FeatExt: cuDNN convolutions with eval-mode BatchNorm folded into them and
+    bias / ReLU / skip fused into the call -- against the features the reference produced (tests/golden/featext.npz) and
+    against the plain modules (the reference's own execution) at another size."""
+    g = golden("featext")
+    net = Frontend().model.feat_ext
+    net.load_state_dict({k[len("model.feat_ext."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("model.feat_ext.")},
+                        strict=True)
+    net = net.to(DEV).eval()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the reference golden is fp32 (CPU)
+    try:
+        with torch.no_grad():
+            got = net(torch.from_numpy(g["img"]).to(DEV))
+        for k in range(3):
+            assert got[k].shape == g["feat_s%d" % (k + 1)].shape
+            assert rel_linf(got[k].cpu().numpy(), g["feat_s%d" % (k + 1)]) < 2e-5
+        x = torch.rand(2, 3, 136, 200, device=DEV)
+        with torch.no_grad():
+            fused = net(x)
+        with torch.enable_grad():
+            plain = [t.detach() for t in net(x)]
+        for a, b in zip(fused, plain):
+            assert a.shape == b.shape and rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 2e-5
+    finally:
+        torch.backends.cudnn.allow_tf32 = old

@@ -9,6 +9,7 @@
 // every weight vector it loads is used for four pixels (128 FMAs per 12 shared-memory loads).  The input tile with
 // its halo is staged channel-quad-major, the layer's weights [tap][ci][co] once per CTA.
 #include "common.cuh"
+#include <cstdint>
 
 namespace mvsb200 {
 
@@ -145,9 +146,60 @@ static int dispatch_c2(const C2Params &p, int cin, int cout, cudaStream_t st)
     return MVSB200_E_INVALID;
 }
 
+// K7b: y = act(y * scale[c] + bias[c] (+ residual)) in place over a channels-last map (one pass over the map instead of the separate
+// broadcast-add and activation kernels a convolution library call without a fused epilogue is followed by):
+// the epilogue of CVP-MVSNet's `conv` = Conv2d(bias) + LeakyReLU(0.1) (models/CVP_MVSNet/models/modules.py:24-28).
+// slope = 0 is ReLU, slope = 1 no activation.  One thread per 16 bytes; C % 4 == 0, so a vector holds channels c .. c+3.
+__global__ void __launch_bounds__(256) k7_bias_act_kernel(float4 *y, long long n4, int C4, const float4 *scale, const float4 *bias,
+                                                          const float4 *residual, float slope)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int c4 = (int)(i % C4);
+        float4 v = y[i];
+        const float4 b = __ldg(bias + c4);
+        if (scale) {
+            const float4 s = __ldg(scale + c4);
+            v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
+        } else {
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        if (residual) {
+            const float4 r = __ldg(residual + i);
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+        v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+        y[i] = v;
+    }
+}
+
 }  // namespace mvsb200
 
 using namespace mvsb200;
+
+extern "C" int mvsb200_bias_act(float *y, long long n_pixels, int C, const float *scale, const float *bias, const float *residual,
+                                float slope, mvsb200_stream_t stream)
+{
+    MVSB200_REQUIRE(y && bias, "bias_act: null pointer");
+    MVSB200_REQUIRE(n_pixels >= 0 && C > 0 && C % 4 == 0, "bias_act: C=%d must be a positive multiple of 4", C);
+    MVSB200_REQUIRE(((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(scale) |
+                      reinterpret_cast<uintptr_t>(residual)) & 15) == 0, "bias_act: y, scale, bias and residual must be 16-byte aligned");
+    if (n_pixels == 0) return MVSB200_OK;
+    const long long n4 = n_pixels * (C / 4);
+    int sms = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;      // grid-stride: 16 resident-sized waves of 256 threads per SM
+    k7_bias_act_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4 *>(y), n4, C / 4,
+                                                                          reinterpret_cast<const float4 *>(scale),
+                                                                          reinterpret_cast<const float4 *>(bias),
+                                                                          reinterpret_cast<const float4 *>(residual), slope);
+    return check_launch("k7_bias_act_kernel");
+}
 
 extern "C" int mvsb200_conv2d(int B, int H, int W, int Cin, int Cout, int k, int stride, int relu, const float *x, const float *w,
                               const float *scale, const float *bias, float *y, mvsb200_stream_t stream)

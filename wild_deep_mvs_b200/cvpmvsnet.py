@@ -12,8 +12,9 @@ Per pyramid level (coarsest first):
   K3  softmax + (per-pixel) depth regression, and the 4-bin confidence on the last level (net.py:161-162,203-219)
   K5  the fp64 per-pixel epipolar solve of `calDepthHypo` (modules.py:131-226; mvsb200_cvp_depth_delta) -- only the median of
       its result (a device sort) is a PyTorch op
-FeaturePyramid (2-D CNN, all same-sized views as one batch) and the bicubic x2 depth up-sampling (net.py:169-170) stay in
-PyTorch on the device ("next" row f1 of SURVEY.md 8-f).
+FeaturePyramid (2-D CNN, all same-sized views as one batch; row f1) runs its convolutions on cuDNN and their bias +
+LeakyReLU epilogue as one in-place library pass (K7b; MVSB200_CVP_PYRAMID=torch selects the plain modules); the bicubic
+x2 depth up-sampling (net.py:169-170) stays in PyTorch on the device.
 Eval mode runs the kernels above; training mode (row f2) uses the K1 / K3 forward + backward kernels behind autograd
 Functions with the regulariser as PyTorch modules (network._forward_train; tests/test_gpu_backward.py).
 """
@@ -44,8 +45,19 @@ class FeaturePyramid(nn.Module):
 
     def _features(self, img):
         f = img.contiguous(memory_format=torch.channels_last)
+        fused = f.is_cuda and not torch.is_grad_enabled() and os.environ.get("MVSB200_CVP_PYRAMID", "fused") == "fused"
         for name in self._ORDER:
-            f = getattr(self, name)(f)
+            m = getattr(self, name)
+            if fused:
+                # cuDNN convolution without its bias, then ONE in-place pass for bias + LeakyReLU (K7b) instead of the
+                # broadcast-add and the activation kernel nn.Conv2d(bias) + nn.LeakyReLU run (each a full read + write
+                # of the 64-channel full-resolution maps: 15 of the pyramid's 24.5 ms at cfg4)
+                f = F.conv2d(f, m[0].weight, None, 1, 1)
+                if not f.is_contiguous(memory_format=torch.channels_last):
+                    f = f.contiguous(memory_format=torch.channels_last)
+                ops.bias_act_(f, m[0].bias, slope=m[1].negative_slope)
+            else:
+                f = m(f)
         return f
 
     def forward(self, img, scales=5):

@@ -705,6 +705,32 @@ def conv2d(x, layer):
     return y
 
 
+@_on_operand_device
+def bias_act_(y, bias, scale=None, residual=None, slope=0.0, nhwc=False):
+    """In place y = act(y * scale[c] + bias[c] (+ residual)) over a channels-last map (K7b, mvsb200_bias_act): the fused
+    epilogue behind a cuDNN convolution call that has none.  `y` is [N,C,H,W] in torch.channels_last memory (what cuDNN
+    returns for channels-last inputs) or, with nhwc=True, [N,H,W,C] contiguous; C % 4 == 0; slope 0 = ReLU, 0.1 = CVP's
+    LeakyReLU, 1 = none.  Returns y."""
+    if y.dim() != 4:
+        raise L.Mvsb200Error("bias_act_: y must be 4-D")
+    if nhwc and y.is_contiguous():
+        C, npix = y.shape[3], y.shape[0] * y.shape[1] * y.shape[2]
+    elif not nhwc and y.is_contiguous(memory_format=torch.channels_last):
+        C, npix = y.shape[1], y.shape[0] * y.shape[2] * y.shape[3]
+    else:
+        raise L.Mvsb200Error("bias_act_: y must be dense channels-last memory")
+    if not (y.is_cuda and y.dtype == torch.float32) or bias.numel() != C:
+        raise L.Mvsb200Error("bias_act_: y must be CUDA float32 with %d == len(bias) channels" % C)
+    if residual is not None and (residual.shape != y.shape or residual.stride() != y.stride() or residual.dtype != torch.float32):
+        raise L.Mvsb200Error("bias_act_: residual must have y's shape and layout")
+    bias = _dev_f32(bias.contiguous(), "bias")
+    if scale is not None:
+        scale = _dev_f32(scale.contiguous(), "scale")
+    L.check(L.load().mvsb200_bias_act(_ptr(y), npix, C, _ptr(scale), _ptr(bias), _ptr(residual), ctypes.c_float(slope), _stream()),
+            "mvsb200_bias_act")
+    return y
+
+
 # ------------------------------------------------------------------------------------------------
 # K5
 # ------------------------------------------------------------------------------------------------

@@ -178,13 +178,65 @@ class FeatExt(nn.Module):
             outs.append(v)
         return tuple(ops.conv3d(o, f).squeeze(1) for o, f in zip(outs, pk["final"]))
 
+    def _fused_params(self):
+        """Eval-mode BatchNorm folded into the convolution that precedes it (w * scale, bias), channels-last, cached."""
+        key = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        if getattr(self, "_fused_key", None) != key:
+            def fold(conv, bn):
+                s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+                return ((conv.weight * s.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last),
+                        (bn.bias - bn.running_mean * s).contiguous())
+
+            def block(b):
+                d = {"c1": fold(b.conv1, b.bn1), "c2": fold(b.conv2, b.bn2), "stride": b.stride, "ds": None}
+                if b.downsample is not None:
+                    d["ds"] = fold(b.downsample[0], b.downsample[1])
+                return d
+            with torch.no_grad():
+                self._fused = {"init": fold(self.init_conv[0], self.init_conv[1]),
+                               "enc": [[block(b) for b in layer] for layer in self.unet.enc_blocks],
+                               "dec": [[block(b) for b in d[2]] for d in self.unet.dec_blocks]}
+            self._fused_key = key
+        return self._fused
+
+    @staticmethod
+    def _block_fused(b, x):
+        """BasicBlock (nn_utils.py:123-171) as two cuDNN calls with fused epilogues: conv + bias + ReLU, conv + bias + skip + ReLU."""
+        st = (b["stride"], b["stride"])
+        y = torch.cudnn_convolution_relu(x, b["c1"][0], b["c1"][1], st, (1, 1), (1, 1), 1)
+        r = x if b["ds"] is None else F.conv2d(x, b["ds"][0], b["ds"][1], st)
+        return torch.cudnn_convolution_add_relu(y, b["c2"][0], r, 1.0, b["c2"][1], (1, 1), (1, 1), (1, 1), 1)
+
+    def _forward_fused(self, x):
+        P = self._fused_params()
+        x = torch.cudnn_convolution_relu(x, P["init"][0], P["init"][1], (2, 2), (2, 2), (1, 1), 1)
+        enc = []
+        for layer in P["enc"]:
+            for b in layer:
+                x = self._block_fused(b, x)
+            enc.append(x)
+        outs = [x]
+        for i, d in enumerate(self.unet.dec_blocks):
+            x = d[0](x)
+            x = d[1](torch.cat([x, enc[-2 - i]], 1))
+            for b in P["dec"][i]:
+                x = self._block_fused(b, x)
+            outs.append(x)
+        return self.final_conv_1(outs[0]), self.final_conv_2(outs[1]), self.final_conv_3(outs[2])
+
     def forward(self, x):
-        # run() is parity-tested against the reference but, at 4.8 ms for five 640x512 views, slower than the cuDNN
-        # modules below (3.0 ms): 2-D layers with 64-128 channels waste two thirds of the tile engine's taps.  It is
-        # therefore opt-in (MVSB200_VIS_FEATEXT=lib) until K7 grows a tensor-core path for wide layers.
-        if os.environ.get("MVSB200_VIS_FEATEXT") == "lib" and not self.training and x.is_cuda and not torch.is_grad_enabled():
+        # run() is parity-tested against the reference but, at 4.8 ms for five 640x512 views, slower than cuDNN: 2-D layers
+        # with 64-128 channels waste two thirds of the tile engine's taps.  It is therefore opt-in (MVSB200_VIS_FEATEXT=lib)
+        # until K7 grows a tensor-core path for wide layers.  Default in inference: the cuDNN convolutions with BatchNorm
+        # folded and bias / ReLU / skip fused into the call (no separate elementwise passes); MVSB200_VIS_FEATEXT=torch
+        # selects the plain modules (the reference's own execution, also the training path).
+        mode = os.environ.get("MVSB200_VIS_FEATEXT", "fused")
+        inference = not self.training and x.is_cuda and not torch.is_grad_enabled()
+        if mode == "lib" and inference:
             return tuple(f.permute(0, 3, 1, 2) for f in self.run(x))      # reference layout as views of channels-last memory
         x = x.contiguous(memory_format=torch.channels_last)
+        if mode == "fused" and inference:
+            return self._forward_fused(x)
         o1, o2, o3 = self.unet(self.init_conv(x))
         return self.final_conv_1(o1), self.final_conv_2(o2), self.final_conv_3(o3)
 
