@@ -282,9 +282,11 @@ MVSB200_API int mvsb200_conv2d(int B, int H, int W, int Cin, int Cout, int k, in
 /* K7b: y = act(y * scale[c] + bias[c] (+ residual)) in place over a channels-last map y [n_pixels, C] (C % 4 == 0, 16-byte
  * aligned): the fused epilogue behind a convolution library call that has none -- CVP-MVSNet's `conv` = Conv2d(bias) +
  * LeakyReLU(0.1) (models/CVP_MVSNet/models/modules.py:24-28; slope 0.1), eval-mode BatchNorm + ReLU (+ skip) of the 2-D
- * BasicBlocks (slope 0).  scale, residual may be NULL; slope = 1 is no activation. */
+ * BasicBlocks (slope 0).  scale, bias, residual may be NULL (not both bias and residual); slope = 1 is no activation -- with
+ * only a residual it is the skip connection added AFTER the activation of a layer that ran as two launches.
+ * amax (optional, a ZEROED device scalar) receives max|y| (the z-march engine's operand scale for the next layer). */
 MVSB200_API int mvsb200_bias_act(float *y, long long n_pixels, int C, const float *scale, const float *bias, const float *residual,
-                                 float slope, mvsb200_stream_t stream);
+                                 float slope, float *amax, mvsb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K8: geometric-consistency filter of one depth map against its N source depth maps (evaluation/filtering.py:59-84

@@ -74,7 +74,7 @@ SIGNATURES = {
     "mvsb200_conv2d": (_i, [_i] * 8 + [_vp] * 6),
     "mvsb200_geometric_filter": (_i, [_vp, _i, _i, ctypes.POINTER(_vp), ctypes.POINTER(_i), ctypes.POINTER(_i), _i, _vp, _vp, _vp,
                                       ctypes.c_float, ctypes.c_float, ctypes.c_float, _i, _vp, _vp, _vp, _vp, _vp]),
-    "mvsb200_bias_act": (_i, [_vp, ctypes.c_longlong, _i, _vp, _vp, _vp, ctypes.c_float, _vp]),
+    "mvsb200_bias_act": (_i, [_vp, ctypes.c_longlong, _i, _vp, _vp, _vp, ctypes.c_float, _vp, _vp]),
     "mvsb200_gathered_masks": (_i, [_i] * 6 + [_vp] * 5 + [ctypes.c_float] + [_vp] * 7),
     "mvsb200_vis_fuse": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "mvsb200_gather_unique_id": (_i, [_vp]),

@@ -151,13 +151,14 @@ static int dispatch_c2(const C2Params &p, int cin, int cout, cudaStream_t st)
 // the epilogue of CVP-MVSNet's `conv` = Conv2d(bias) + LeakyReLU(0.1) (models/CVP_MVSNet/models/modules.py:24-28).
 // slope = 0 is ReLU, slope = 1 no activation.  One thread per 16 bytes; C % 4 == 0, so a vector holds channels c .. c+3.
 __global__ void __launch_bounds__(256) k7_bias_act_kernel(float4 *y, long long n4, int C4, const float4 *scale, const float4 *bias,
-                                                          const float4 *residual, float slope)
+                                                          const float4 *residual, float slope, float *amax)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
+    float vmax = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         const int c4 = (int)(i % C4);
         float4 v = y[i];
-        const float4 b = __ldg(bias + c4);
+        const float4 b = bias ? __ldg(bias + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (scale) {
             const float4 s = __ldg(scale + c4);
             v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
@@ -171,6 +172,12 @@ __global__ void __launch_bounds__(256) k7_bias_act_kernel(float4 *y, long long n
         v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
         v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
         y[i] = v;
+        vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    if (amax) {   // max |y| for the z-march conv engine's operand scale (a zeroed device scalar)
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, m));
+        if ((threadIdx.x & 31) == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned int *>(amax), __float_as_uint(vmax));
     }
 }
 
@@ -179,9 +186,9 @@ __global__ void __launch_bounds__(256) k7_bias_act_kernel(float4 *y, long long n
 using namespace mvsb200;
 
 extern "C" int mvsb200_bias_act(float *y, long long n_pixels, int C, const float *scale, const float *bias, const float *residual,
-                                float slope, mvsb200_stream_t stream)
+                                float slope, float *amax, mvsb200_stream_t stream)
 {
-    MVSB200_REQUIRE(y && bias, "bias_act: null pointer");
+    MVSB200_REQUIRE(y && (bias || residual), "bias_act: null pointer");
     MVSB200_REQUIRE(n_pixels >= 0 && C > 0 && C % 4 == 0, "bias_act: C=%d must be a positive multiple of 4", C);
     MVSB200_REQUIRE(((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(scale) |
                       reinterpret_cast<uintptr_t>(residual)) & 15) == 0, "bias_act: y, scale, bias and residual must be 16-byte aligned");
@@ -197,7 +204,7 @@ extern "C" int mvsb200_bias_act(float *y, long long n_pixels, int C, const float
     k7_bias_act_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4 *>(y), n4, C / 4,
                                                                           reinterpret_cast<const float4 *>(scale),
                                                                           reinterpret_cast<const float4 *>(bias),
-                                                                          reinterpret_cast<const float4 *>(residual), slope);
+                                                                          reinterpret_cast<const float4 *>(residual), slope, amax);
     return check_launch("k7_bias_act_kernel");
 }
 

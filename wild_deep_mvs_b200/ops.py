@@ -455,8 +455,7 @@ def conv3d(x, layer, x2=None, skip=None, engine=None, out=None, amax=None):
                                       _ptr(absmax(x2)) if x2 is not None else None, _ptr(amax), _stream()), "mvsb200_conv3d_zm")
         set_absmax(y, amax)
         return y
-    if (engine == "zm" and x.device == layer.w.device and x2 is None and C1 % 16 == 0 and layer.skip_mode != L.SKIP_AFTER_RELU
-            and layer.k == (3, 3, 3)):
+    if engine == "zm" and x.device == layer.w.device and x2 is None and C1 % 16 == 0 and layer.k == (3, 3, 3):
         # weights too large to stay resident: two launches over the halves of the input channels (see PackedConv.halves)
         half = L.Conv3dDesc.from_buffer_copy(desc)
         half.Cin = C1 // 2
@@ -468,12 +467,20 @@ def conv3d(x, layer, x2=None, skip=None, engine=None, out=None, amax=None):
             half.static_params = 1 if (PDL and a._launches > 0 and b._launches > 0) else 0
             a._launches += 1
             b._launches += 1
-            half.relu, half.skip_mode = a.relu, (a.skip_mode if skip is not None else L.SKIP_NONE)
+            # a skip that is added AFTER the activation cannot ride on either launch (the second one's skip operand is
+            # the first one's partial sum): it is one in-place pass over the output afterwards (K7b)
+            after = layer.skip_mode == L.SKIP_AFTER_RELU and skip is not None
+            half.relu, half.skip_mode = a.relu, (a.skip_mode if (skip is not None and not after) else L.SKIP_NONE)
             L.check(lib.mvsb200_conv3d_zm_slice(ctypes.byref(half), _ptr(x), C1, 0, None, _ptr(a.zm_packed(half)), _ptr(a.scale),
-                                                _ptr(a.bias), _ptr(skip), _ptr(y), xa, None, None, _stream()), "mvsb200_conv3d_zm_slice")
+                                                _ptr(a.bias), None if after else _ptr(skip), _ptr(y), xa, None, None, _stream()),
+                    "mvsb200_conv3d_zm_slice")
             half.relu, half.skip_mode = b.relu, L.SKIP_BEFORE_RELU
             L.check(lib.mvsb200_conv3d_zm_slice(ctypes.byref(half), _ptr(x), C1, C1 // 2, None, _ptr(b.zm_packed(half)), _ptr(b.scale),
-                                                None, _ptr(y), _ptr(y), xa, None, _ptr(amax), _stream()), "mvsb200_conv3d_zm_slice")
+                                                None, _ptr(y), _ptr(y), xa, None, None if after else _ptr(amax), _stream()),
+                    "mvsb200_conv3d_zm_slice")
+            if after:
+                L.check(lib.mvsb200_bias_act(_ptr(y), y.numel() // y.shape[-1], y.shape[-1], None, None, _ptr(skip), ctypes.c_float(1.0),
+                                             _ptr(amax), _stream()), "mvsb200_bias_act")
             set_absmax(y, amax)
             return y
     if engine != "fp32" and x.device == layer.w.device and lib.mvsb200_conv3d_tc_supported(ctypes.byref(desc)):
@@ -726,7 +733,7 @@ def bias_act_(y, bias, scale=None, residual=None, slope=0.0, nhwc=False):
     bias = _dev_f32(bias.contiguous(), "bias")
     if scale is not None:
         scale = _dev_f32(scale.contiguous(), "scale")
-    L.check(L.load().mvsb200_bias_act(_ptr(y), npix, C, _ptr(scale), _ptr(bias), _ptr(residual), ctypes.c_float(slope), _stream()),
+    L.check(L.load().mvsb200_bias_act(_ptr(y), npix, C, _ptr(scale), _ptr(bias), _ptr(residual), ctypes.c_float(slope), None, _stream()),
             "mvsb200_bias_act")
     return y
 
