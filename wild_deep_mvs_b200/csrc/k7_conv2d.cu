@@ -61,11 +61,14 @@ __global__ void __launch_bounds__(C2_THREADS) k7_conv2d_kernel(const C2Params p)
     const int g = threadIdx.x % CG;
     const int q = threadIdx.x / CG;
     const int qx = q % (C2_TW / C2_PX), ly = q / (C2_TW / C2_PX);
-    float acc[C2_PX][C2_CT];
+    // accumulators as channel PAIRS: packed fp32 FMAs (FFMA2: two IEEE fp32 FMAs per instruction, same rounding as the
+    // scalar form) with the weight pair as the vector operand -- the registers an LDS.128 fills are already pairs -- and
+    // the input value as the scalar
+    float2 acc[C2_PX][C2_CT / 2];
 #pragma unroll
     for (int j = 0; j < C2_PX; j++)
 #pragma unroll
-        for (int c = 0; c < C2_CT; c++) acc[j][c] = 0.f;
+        for (int c = 0; c < C2_CT / 2; c++) acc[j][c] = make_float2(0.f, 0.f);
 
 #pragma unroll 1
     for (int ky = 0; ky < K; ky++) {
@@ -82,12 +85,13 @@ __global__ void __launch_bounds__(C2_THREADS) k7_conv2d_kernel(const C2Params p)
                 for (int k = 0; k < 4; k++) {
                     const float4 w0 = *reinterpret_cast<const float4 *>(wt + (c4 * 4 + k) * COUT);
                     const float4 w1 = *reinterpret_cast<const float4 *>(wt + (c4 * 4 + k) * COUT + 4);
-                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
                     for (int j = 0; j < C2_PX; j++) {
                         const float v = (k == 0) ? in[j].x : (k == 1) ? in[j].y : (k == 2) ? in[j].z : in[j].w;
+                        const float2 vv = make_float2(v, v);
 #pragma unroll
-                        for (int c = 0; c < C2_CT; c++) acc[j][c] = fmaf(v, wv[c], acc[j][c]);
+                        for (int c = 0; c < C2_CT / 2; c++) acc[j][c] = __ffma2_rn(vv, wv[c], acc[j][c]);
                     }
                 }
             }
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(C2_THREADS) k7_conv2d_kernel(const C2Params p)
         float r[C2_CT];
 #pragma unroll
         for (int c = 0; c < C2_CT; c++) {
-            r[c] = fmaf(acc[j][c], sc[c], bi[c]);
+            r[c] = fmaf((c & 1) ? acc[j][c / 2].y : acc[j][c / 2].x, sc[c], bi[c]);
             if (p.relu) r[c] = fmaxf(r[c], 0.f);
         }
         float *dst = p.y + (((long long)b * p.Ho + oy) * p.Wo + ox) * COUT + g * C2_CT;
