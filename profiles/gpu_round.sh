@@ -13,6 +13,8 @@ timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1
 echo "pytest rc=$?" >> $OUT/pytest_gpu_$TAG.log
 tail -5 $OUT/pytest_gpu_$TAG.log
 
+timeout 300 python __graft_entry__.py --smoke > $OUT/smoke_$TAG.log 2>&1
+echo "smoke rc=$?"; tail -1 $OUT/smoke_$TAG.log
 timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_err_$TAG.log
 echo "bench rc=$?"
 cat $OUT/bench_$TAG.json
@@ -27,7 +29,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$KR
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extras > $OUT/ncu_full_$TAG.log 2>&1
 echo "ncu full rc=$?"
 # memory checker over the kernel parity tests (every kernel of the library at small sizes)
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_backward.py tests/test_gpu_filter.py -x -q -m gpu -k "not cfg1_size and not training_step" \
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_backward.py tests/test_gpu_filter.py tests/test_gpu_cvp.py -x -q -m gpu -k "not cfg1_size and not training_step and not full_size and not cfg4" \
     > $OUT/sanitizer_$TAG.log 2>&1
 echo "sanitizer rc=$?" | tee -a $OUT/sanitizer_$TAG.log
 tail -3 $OUT/sanitizer_$TAG.log
