@@ -57,18 +57,37 @@ def sample(views, h, w):
     return {k: v.to(DEV) for k, v in synth.make_sample(1, views, h, w, seed=0).items()}
 
 
+def graphed_forward_ms(name, net, s, out, **kw):
+    """The same forward replayed as ONE CUDA graph (net.graphed_forward); None if the model cannot be captured."""
+    try:
+        with torch.no_grad():
+            g = net.graphed_forward(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"], **kw)
+            got = g()
+            torch.cuda.synchronize()
+            assert torch.equal(got["depth"], out["depth"]), "graphed forward differs from the eager one"
+            return timed(lambda: g(), reps=20, warmup=3)
+    except Exception as e:  # noqa: BLE001 -- reported in the line
+        sys.stderr.write("%s: graphed forward unavailable: %r\n" % (name, e))
+        torch.cuda.synchronize()
+        return None
+
+
 def run(name, net, s, vox, feat_fn, **kw):
     net = net.to(DEV).eval()
     call = lambda: net(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"], **kw)
     out = call()
     assert torch.isfinite(out["depth"]).all(), name
     ms_fwd = timed(call)
+    ms_graph = graphed_forward_ms(name, net, s, out, **kw)
     with torch.no_grad():
         ms_feat = timed(lambda: feat_fn(net, s))
     ms_hot = ms_fwd - ms_feat
     r = {"config": name, "voxels": vox, "forward_ms": round(ms_fwd, 3), "features_ms": round(ms_feat, 3),
          "hot_path_ms": round(ms_hot, 3), "hot_path_Mvox_per_s": round(vox / ms_hot / 1e3, 1),
          "depth_maps_per_s": round(1e3 / ms_fwd, 1), "depth_shape": list(out["depth"].shape)}
+    if ms_graph is not None:
+        r["forward_graphed_ms"] = round(ms_graph, 3)
+        r["depth_maps_per_s_graphed"] = round(1e3 / ms_graph, 1)
     print(json.dumps(add_roofline(r)), flush=True)
     return r
 

@@ -184,3 +184,23 @@ def test_featext_fused_inference_path_against_reference_golden(golden):
             assert a.shape == b.shape and rel_linf(a.cpu().numpy(), b.cpu().numpy()) < 2e-5
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+def test_graphed_forward_equals_eager_forward():
+    """`Frontend.graphed_forward`: the whole eval-mode forward (images -> dict, same kwargs) as ONE CUDA graph gives the eager
+    forward's outputs bit for bit, and follows new inputs copied into the captured buffers."""
+    torch.manual_seed(0)
+    net = Frontend()
+    synth.randomize_norm_stats(net, seed=2)
+    net = net.to(DEV).eval()
+    kw = dict(depth_nums=[8, 4, 4], interval_scales=[4, 2, 1])
+    s = {k: v.to(DEV) for k, v in synth.make_sample(1, 3, 64, 80, seed=0).items()}
+    args = lambda d: (d["imgs"], d["K"], d["R"], d["t"], d["depth_min"], d["depth_max"])
+    want = net(*args(s), **kw)
+    g = net.graphed_forward(*args(s), **kw)
+    got = g()
+    assert torch.equal(got["depth"], want["depth"]) and torch.equal(got["photometric_confidence"], want["photometric_confidence"])
+    s2 = {k: v.to(DEV) for k, v in synth.make_sample(1, 3, 64, 80, seed=5).items()}
+    want2 = net(*args(s2), **kw)
+    got2 = g(*args(s2))
+    assert torch.equal(got2["depth"], want2["depth"]) and not torch.equal(want2["depth"], want["depth"])

@@ -297,6 +297,13 @@ class Frontend(nn.Module):
         super().__init__()
         self.model = network()
 
+    def graphed_forward(self, imgs, K, R, t, depth_min, depth_max, reference_frame=0, **kwargs):
+        """The whole eval-mode `forward` (images -> dict, same kwargs) captured into ONE CUDA graph for inputs of these shapes
+        (mvsnet.GraphedForward): a callable taking the same six tensors (None = keep the captured values) and returning the
+        captured output dict (overwritten by the next replay).  The eager forward of this model is launch bound."""
+        from .mvsnet import GraphedForward
+        return GraphedForward(self, imgs, K, R, t, depth_min, depth_max, reference_frame, **kwargs)
+
     def forward(self, imgs, K, R, t, depth_min, depth_max, reference_frame=0, **kwargs):
         src_idx = list(range(reference_frame)) + list(range(reference_frame + 1, K.shape[1]))
         if isinstance(imgs, torch.Tensor):

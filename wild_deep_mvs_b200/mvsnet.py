@@ -230,13 +230,14 @@ class GraphedHotPath:
 
 
 class GraphedForward:
-    """MVSNet.forward (eval) as one CUDA graph; see MVSNet.graphed_forward."""
+    """The eval-mode `forward(imgs, K, R, t, depth_min, depth_max, ...)` of a drop-in model (MVSNet, Vis-MVSNet or
+    CVP-MVSNet `Frontend`) as one CUDA graph; see the models' graphed_forward."""
 
-    def __init__(self, net, imgs, K, R, t, depth_min, depth_max, reference_frame=0, warmup=2):
+    def __init__(self, net, imgs, K, R, t, depth_min, depth_max, reference_frame=0, warmup=2, **kwargs):
         if net.training or not isinstance(imgs, torch.Tensor):
             raise L.Mvsb200Error("graphed_forward: eval mode and same-sized views (a [B,V,3,H,W] tensor) only")
         self.inputs = [x.clone() for x in (imgs, K, R, t, depth_min, depth_max)]
-        run = lambda: net(*self.inputs, reference_frame=reference_frame)
+        run = lambda: net(*self.inputs, reference_frame=reference_frame, **kwargs)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

@@ -503,6 +503,13 @@ class Frontend(nn.Module):
         return _GraphedCascade(self, feats, ref_cam, src_cams, depth_min, depth_interval, depth_nums, interval_scales,
                                out_depth=out_depth)
 
+    def graphed_forward(self, imgs, K, R, t, depth_min, depth_max, reference_frame=0, **kwargs):
+        """The whole eval-mode `forward` (images -> dict, same kwargs) captured into ONE CUDA graph for inputs of these shapes
+        (mvsnet.GraphedForward): a callable taking the same six tensors (None = keep the captured values) and returning the
+        captured output dict (overwritten by the next replay).  The eager forward of this model is launch bound."""
+        from .mvsnet import GraphedForward
+        return GraphedForward(self, imgs, K, R, t, depth_min, depth_max, reference_frame, **kwargs)
+
     def forward(self, imgs, K, R, t, depth_min, depth_max, reference_frame=0, **kwargs):
         depth_interval = (depth_max - depth_min) / 128
         interval_scales = kwargs.get("interval_scales", self.interval_scales)
