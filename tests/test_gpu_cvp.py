@@ -185,3 +185,18 @@ def test_bias_act_kernel_and_fused_pyramid():
         torch.backends.cudnn.allow_tf32 = old
     for a, c in zip(fused, plain):
         assert a.shape == c.shape and (a - c).abs().max() <= 2e-6 * c.abs().max()
+
+
+def test_graphed_forward_equals_eager_forward():
+    """`Frontend.graphed_forward`: the whole CVP-MVSNet forward (pyramid, K5 median interval, every level) captured into ONE
+    CUDA graph -- legal only because the forward has no host read or host -> device copy left -- equals the eager forward."""
+    torch.manual_seed(0)
+    net = Frontend()
+    synth.randomize_norm_stats(net, seed=3)
+    net = net.to(DEV).eval()
+    s = {k: v.to(DEV) for k, v in synth.make_sample(1, 3, 128, 160, seed=0).items()}
+    a = (s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"])
+    want = net(*a, nscale=2)
+    g = net.graphed_forward(*a, nscale=2)
+    got = g()
+    assert torch.equal(got["depth"], want["depth"]) and torch.equal(got["photometric_confidence"], want["photometric_confidence"])

@@ -229,18 +229,24 @@ class network(nn.Module):
         seams["reg_out_coarse"] = score
         depth = out["depth"]
         ests = [depth]
+        nan_flags = []
         for level in range(nscale - 2, -1, -1):
             depth_up = F.interpolate(depth[None, :], size=None, scale_factor=2, mode="bicubic", align_corners=None).squeeze(0)
             hypos = cal_depth_hypo(depth_up, ref_in_ms[:, level], src_in_ms[:, :, level], ref_ex, src_ex, depth_min,
                                    depth_max).contiguous()
-            if torch.isnan(hypos).any():
-                print("NAN")   # the reference only prints (net.py:188-189)
+            nan_flags.append(torch.isnan(hypos).any())   # checked once, after the last level (below)
             score = reg.run(cost_volume(level, hypos))
             out = ops.depth_regress(score, hypos, conf_mode=L.CONF_SUM4 if level == 0 else L.CONF_NONE)
             seams["hypos_l%d" % level] = hypos
             seams["reg_out_l%d" % level] = score
             depth = out["depth"]
             ests.append(depth)
+        # The reference prints "NAN" per level (net.py:188-189,196-197) -- a host read of a device flag, i.e. a pipeline
+        # drain per level.  Here the flags stay on the device and are read ONCE at the end; not at all while the forward is
+        # being captured into a CUDA graph (graphed_forward), where a host read is illegal.
+        if nan_flags and not torch.cuda.is_current_stream_capturing():
+            if torch.stack(nan_flags).any():
+                print("NAN")
         return ests, out["conf"], seams
 
     def _forward_train(self, ref_img, src_imgs, ref_in, src_in, ref_ex, src_ex, depth_min, depth_max, nscale):
@@ -308,17 +314,20 @@ class Frontend(nn.Module):
         src_idx = list(range(reference_frame)) + list(range(reference_frame + 1, K.shape[1]))
         if isinstance(imgs, torch.Tensor):
             ref_img = imgs[:, reference_frame]
-            src_imgs = torch.unbind(imgs[:, src_idx], dim=1)
+            src_imgs = [imgs[:, i] for i in src_idx]
         else:
             ref_img = imgs[reference_frame]
             src_imgs = imgs[:reference_frame] + imgs[reference_frame + 1:]
         b, n = ref_img.shape[0], len(src_imgs)
-        last = torch.tensor([0., 0., 0., 1.], device=K.device, dtype=K.dtype)
+        # (0, 0, 0, 1) built on the device (fill kernels): no host -> device copy, so the forward can be captured into a CUDA graph
+        last = torch.cat((torch.zeros(3, device=K.device, dtype=K.dtype), torch.ones(1, device=K.device, dtype=K.dtype)))
+        # (views picked with Python indices, not `x[:, src_idx]`: a list index becomes a host tensor that is copied to the device)
+        pick = lambda x: torch.stack([x[:, i] for i in src_idx], 1)
         ref_ex = torch.cat((torch.cat((R[:, reference_frame], t[:, reference_frame]), dim=2),
                             last.view(1, 1, 4).expand(b, 1, 4)), dim=1)
-        src_ex = torch.cat((torch.cat((R[:, src_idx], t[:, src_idx]), dim=3),
+        src_ex = torch.cat((torch.cat((pick(R), pick(t)), dim=3),
                             last.view(1, 1, 1, 4).expand(b, n, 1, 4)), dim=2)
-        output = self.model(ref_img, src_imgs, K[:, reference_frame], K[:, src_idx], ref_ex, src_ex,
+        output = self.model(ref_img, src_imgs, K[:, reference_frame], pick(K), ref_ex, src_ex,
                             depth_min[:, reference_frame], depth_max[:, reference_frame], **kwargs)
         return {"depth": output["depth_est_list"][0].squeeze(1), "depth_est_list": output["depth_est_list"],
                 "depth_pair_list": [], "photometric_confidence": output["prob_confidence"].unsqueeze(1)}
