@@ -227,6 +227,9 @@ constexpr int K1M_THREADS = 128;
 // Window re-loads one hypothesis ahead of the arithmetic (see the kernel): measured on B200 (profiles/k1_ab.py) -- group
 // correlation 0.112 -> 0.103 ms, variance-mean with per-pixel hypotheses 0.487 -> 0.462 ms, but cfg2's variance 0.262 -> 0.269 ms
 // (its arithmetic block is the longest and already covers the load latency): on for the first two, off otherwise.
+#ifndef K1M_GROUP
+#define K1M_GROUP 1      // views whose re-load checks precede their arithmetic together (inline mode); measured: see profiles/k1_ab.py
+#endif
 #ifndef K1M_AHEAD
 #define K1M_AHEAD(AGG) ((AGG) == MVSB200_AGG_GROUPCORR || (AGG) == MVSB200_AGG_VARIANCE_MEAN)
 #endif
@@ -476,7 +479,10 @@ __global__ void __launch_bounds__(K1M_THREADS, K1M_MIN_BLOCKS) k1m_cost_volume_k
 #pragma unroll
             for (int s = 0; s < S; s++) {
                 const float4 wt = lds128(rec + (k * S + s) * 16);             // {w00, w01, w10, w11}
-                if (!K1M_AHEAD(AGG)) { K1M_RELOAD_VIEW(s, cells[s]) }
+                if (!K1M_AHEAD(AGG) && s % K1M_GROUP == 0) {     // the re-load checks of K1M_GROUP views, then their arithmetic as one block
+#pragma unroll
+                    for (int u = s; u < s + K1M_GROUP && u < S; u++) { K1M_RELOAD_VIEW(u, cells[u]) }
+                }
                 // accumulation order nw, ne, sw, se (ATen grid_sampler_2d)
                 const float2 p00 = make_float2(wt.x, wt.x), p01 = make_float2(wt.y, wt.y), p10 = make_float2(wt.z, wt.z), p11 = make_float2(wt.w, wt.w);
                 float2 wa = __fmul2_rn(make_float2(ta[s].x, ta[s].y), p00), wb = __fmul2_rn(make_float2(ta[s].z, ta[s].w), p00);
