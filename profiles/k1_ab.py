@@ -39,8 +39,8 @@ def child(so):
         ts.sort()
         return ts[len(ts) // 2], ts[0]
 
-    def mvs_case(C, h, w, D, agg, per_pixel):
-        V = 5
+    def mvs_case(C, h, w, D, agg, per_pixel, views=5):
+        V = views
         feats = [ops.to_nhwc(f.to(dev)) for f in synth.make_features(1, V, C, h, w, seed=0)]
         K, R, t, dmin, dmax = synth.make_cameras(1, V, 4 * h, 4 * w)
         K = K.clone()
@@ -52,29 +52,39 @@ def child(so):
             depth = (depth.view(1, D, 1, 1) + torch.rand(1, 1, h, w, device=dev)).expand(1, D, h, w).contiguous()
         out = torch.empty(1, D, h, w, C, device=dev)
         amax = torch.zeros(1, device=dev)
-        return lambda: ops.build_cost_volume(feats[0], feats[1:], warp, depth, D, L.GEOM_MVS, agg, out=out, amax=amax)
+        temp = torch.ones(1, device=dev) if agg == L.AGG_SOFTMIN else None
+        return lambda: ops.build_cost_volume(feats[0], feats[1:], warp, depth, D, L.GEOM_MVS, agg, temp=temp, out=out, amax=amax)
 
-    def vis_case(h, w, D):
+    def vis_case(h, w, D, B=1, start_map=True, scale=1.0):
         V, C = 5, 32
-        feats = [ops.to_nhwc(f.to(dev)) for f in synth.make_features(1, V, C, h, w, seed=0)]
+        feats = [ops.to_nhwc(f.to(dev)).expand(B, -1, -1, -1).contiguous() for f in synth.make_features(1, V, C, h, w, seed=0)]
         K, R, t, dmin, dmax = synth.make_cameras(1, V, 4 * h, 4 * w)
         cams = torch.zeros(1, V, 2, 4, 4)
         cams[:, :, 0, :3, :3] = R
         cams[:, :, 0, :3, 3:] = t
         cams[:, :, 0, 3, 3] = 1
         cams[:, :, 1, :3, :3] = K
-        cams = cams.to(dev)
+        cams = cams.to(dev).expand(B, -1, -1, -1, -1).contiguous()
         warp = ops.vis_homography_params(cams[:, 0], cams[:, 1:], 0.25)
-        start = (dmin[:, :1].view(1, 1, 1) + 40 * torch.rand(1, h, w)).to(dev)
-        interval = torch.full((1,), 2.5 * 192 / 128, device=dev)
-        out = torch.empty(4, 1, D, h, w, 8, device=dev)
+        if start_map:
+            start = (dmin[:, :1].view(1, 1, 1) + 40 * torch.rand(B, h, w)).to(dev)
+        else:
+            start = dmin[:, :1].view(1).expand(B).contiguous().to(dev)
+        interval = torch.full((B,), 2.5 * 192 / 128 * scale, device=dev)
+        out = torch.empty(4, B, D, h, w, 8, device=dev)
         amax = torch.zeros(1, device=dev)
         return lambda: ops.build_cost_volume(feats[0], feats[1:], warp, start, D, L.GEOM_VIS, L.AGG_GROUPCORR, interval=interval,
                                              out=out, amax=amax)
 
     cases = [("cfg2", lambda: mvs_case(32, 128, 160, 192, L.AGG_VARIANCE, False)),
              ("cvp-like", lambda: mvs_case(16, 592, 800, 8, L.AGG_VARIANCE_MEAN, True)),
-             ("vis-like", lambda: vis_case(128, 160, 32))]
+             ("vis-like", lambda: vis_case(128, 160, 32)),
+             ("vis-s1x8", lambda: vis_case(64, 80, 64, B=8, start_map=False, scale=2.0)),     # cfg5 stage 1: scalar start, 8 views per launch
+             ("vis-s2x8", lambda: vis_case(128, 160, 32, B=8, scale=1.0)),
+             ("vis-s3x8", lambda: vis_case(256, 320, 16, B=8, scale=0.5)),
+             ("cvp-l4", lambda: mvs_case(16, 74, 100, 96, L.AGG_VARIANCE_MEAN, False)),      # cfg4 coarsest level: scalar hypotheses
+             ("cvp-l0", lambda: mvs_case(16, 1184, 1600, 8, L.AGG_VARIANCE_MEAN, True)),
+             ("cfg1", lambda: mvs_case(32, 128, 160, 48, L.AGG_SOFTMIN, False, views=3))]
     for name, mk in cases:
         try:
             med, mn = timed(mk())

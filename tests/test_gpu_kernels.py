@@ -42,6 +42,19 @@ def warp16(rot, trans):
     return w
 
 
+@pytest.fixture(autouse=True, params=["pixel-tile", "depth-marching"])
+def k1_kernel(request, monkeypatch):
+    """K1 has two kernels and picks one per shape (k1_cost_volume.cu: the depth-marching one for long scalar sweeps, the
+    pixel-tile one otherwise).  The K1 parity tests run every case through BOTH (MVSB200_K1 = v1 | m forces one; shapes the
+    depth-marching kernel does not cover fall through to the other); every other test runs once."""
+    if "k1_" not in request.node.name and "errors_are_loud" not in request.node.name:
+        if request.param == "depth-marching":
+            pytest.skip("not a K1 test: runs once")
+        return None
+    monkeypatch.setenv("MVSB200_K1", "v1" if request.param == "pixel-tile" else "m")
+    return request.param
+
+
 # ------------------------------------------------------------------------------------------------
 # geometry prologues
 # ------------------------------------------------------------------------------------------------

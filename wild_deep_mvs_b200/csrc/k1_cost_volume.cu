@@ -657,8 +657,16 @@ extern "C" int mvsb200_build_cost_volume(const mvsb200_cost_volume_desc *d, cons
     p.B = d->B; p.S = d->S; p.D = d->D; p.H = d->H; p.W = d->W; p.depth_mode = d->depth_mode;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid;
-    static const bool use_v1 = [] { const char *e = getenv("MVSB200_K1"); return e && e[0] == 'v' && e[1] == '1'; }();   // A/B runs
-    if (!use_v1 && k1m_supported(d)) {   // depth-marching kernel
+    // Which kernel: the depth-marching one pays off where a block marches a LONG run of hypotheses whose samples move by a
+    // fraction of a source pixel (scalar hypotheses, D >= 96: cfg2 0.259 vs 0.310 ms); for short sweeps and per-pixel
+    // hypotheses -- Vis-MVSNet's stages (D = 16 ... 64 around the previous stage's depth), CVP-MVSNet's refinement levels
+    // (D = 8, one source pixel per hypothesis by construction), MVSNet-s (D = 48) -- its start-up (the geometry of a
+    // mini-chunk, the first windows of every view) is not amortised and the pixel-tile kernel wins (profiles/k1_ab.py:
+    // Vis stage 3 0.95 vs 1.24 ms, CVP level 0 0.98 vs 1.86 ms, cfg1 0.067 vs 0.085 ms).  MVSB200_K1 = v1 | m forces one (A/B runs).
+    const char *k1_env = getenv("MVSB200_K1");   // read per call: the parity tests run both kernels in one process
+    const int forced = !k1_env ? 0 : (k1_env[0] == 'v' ? 1 : (k1_env[0] == 'm' ? 2 : 0));
+    const bool long_march = d->depth_mode != MVSB200_DEPTH_VOLUME && d->depth_mode != MVSB200_DEPTH_START_MAP && d->D >= 96;
+    if (k1m_supported(d) && forced != 1 && (forced == 2 || long_march)) {   // depth-marching kernel
         int seg = 0;
         if (int rc = k1m_grid(d, grid, seg, "build_cost_volume")) return rc;
         p.chunks = 0;
