@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_cost_volume_kernel(const K1P
 
 
 // ------------------------------------------------------------------------------------------------------------------
-// K1-M, the depth-marching kernel (default for 1, 2 or 4 source views and C = 16 / 32).
+// K1-M, the depth-marching kernel (1, 2 or 4 source views, C = 16 / 32; chosen for long sweeps over scalar hypotheses, see
+// mvsb200_build_cost_volume at the end of this file: the pixel-tile kernel above is the faster one for short sweeps).
 //
 // What bounds this path is the traffic from L1 into the register file (128 B / clk / SM): every (pixel, hypothesis, view)
 // needs four C-wide taps, 512 bytes for C = 32 (profiles/k1_r2_hypothesis_major.md).  Consecutive hypotheses of a pixel move
@@ -218,18 +219,20 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_cost_volume_kernel(const K1P
 // (one LDS.128 + one LDS.32 per (hypothesis, view): 5 wavefronts of the LSU pipe, this kernel's busiest unit after the
 // change; broadcast 128-bit shared loads cost 4 wavefronts each, so packed-pair duplicates are made with moves instead).
 // The pixels that share a warp are stacked ACROSS the epipolar direction so that they change cells together, and the
-// window re-load is a real warp-uniform branch (the compiler otherwise if-converts it into ~30 always-issued instructions).
+// window re-load is a real warp-uniform branch (the compiler otherwise if-converts it into ~56 always-issued instructions
+// per hypothesis, see K1M_REAL_BRANCH_*).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int K1M_THREADS = 128;
+// Experiment switches (profiles/k1_ab.py builds the variants with -D; the defaults are what measured best on B200):
 #ifndef K1M_MIN_BLOCKS
-#define K1M_MIN_BLOCKS 4
+#define K1M_MIN_BLOCKS 4 // blocks per SM the register allocation aims at: 5 (96 registers, spilled view constants) 0.262 -> 0.300 ms
 #endif
-// Window re-loads one hypothesis ahead of the arithmetic (see the kernel): measured on B200 (profiles/k1_ab.py) -- group
-// correlation 0.112 -> 0.103 ms, variance-mean with per-pixel hypotheses 0.487 -> 0.462 ms, but cfg2's variance 0.262 -> 0.269 ms
-// (its arithmetic block is the longest and already covers the load latency): on for the first two, off otherwise.
 #ifndef K1M_GROUP
-#define K1M_GROUP 1      // views whose re-load checks precede their arithmetic together (inline mode); measured: see profiles/k1_ab.py
+#define K1M_GROUP 1      // views whose re-load checks precede their arithmetic together (inline mode): 2 / 4 -> 0.267 / 0.287 ms
 #endif
+// Window re-loads one hypothesis ahead of the arithmetic (see the kernel): group correlation 0.112 -> 0.103 ms, variance-mean
+// with per-pixel hypotheses 0.487 -> 0.462 ms, but cfg2's variance 0.262 -> 0.269 ms (its arithmetic block is the longest and
+// already covers the load latency): on for the first two, off otherwise.
 #ifndef K1M_AHEAD
 #define K1M_AHEAD(AGG) ((AGG) == MVSB200_AGG_GROUPCORR || (AGG) == MVSB200_AGG_VARIANCE_MEAN)
 #endif
