@@ -18,10 +18,16 @@ struct K3Params {
     long long HW;
 };
 
+// DL = depth lanes per pixel: 8 for deep volumes (MVSNet's D = 192: the lanes split the sweep and combine through shared
+// memory), 1 for the shallow ones of the cascades (Vis-MVSNet stages D = 16 ... 64, CVP refinement levels D = 8): with a
+// handful of hypotheses per lane the partial-sum exchange and its three barriers cost more than the sweep -- a thread then
+// owns its pixel, a block 256 pixels.
+template <int DL>
 __global__ void __launch_bounds__(K3_THREADS) k3_depth_regress_kernel(const K3Params p)
 {
+    constexpr int K3_DL = DL, K3_PIX = K3_THREADS / DL;
     __shared__ float red[4][K3_DL][K3_PIX];
-    const int b = blockIdx.y, lane = threadIdx.x & 31, dl = threadIdx.x >> 5;
+    const int b = blockIdx.y, lane = threadIdx.x % K3_PIX, dl = threadIdx.x / K3_PIX;
     const long long pix_raw = (long long)blockIdx.x * K3_PIX + lane;
     const bool active = pix_raw < p.HW;
     const long long pix = active ? pix_raw : p.HW - 1;
@@ -184,8 +190,14 @@ extern "C" int mvsb200_depth_regress(const float *score, int B, int D, int H, in
     p.depth_out = depth_out; p.conf_out = conf_mode ? conf_out : nullptr; p.entropy_out = entropy_out; p.prob_out = prob_out;
     p.B = B; p.D = D; p.depth_mode = depth_mode; p.conf_mode = conf_mode;
     p.HW = (long long)H * W;
-    dim3 grid((unsigned)((p.HW + K3_PIX - 1) / K3_PIX), (unsigned)B);
-    k3_depth_regress_kernel<<<grid, K3_THREADS, 0, (cudaStream_t)stream>>>(p);
+    // one thread per pixel needs enough pixels to fill the machine while each thread walks D serially
+    if (D <= 32 || (D <= 64 && (long long)B * p.HW >= (1ll << 18))) {
+        dim3 grid((unsigned)((p.HW + K3_THREADS - 1) / K3_THREADS), (unsigned)B);
+        k3_depth_regress_kernel<1><<<grid, K3_THREADS, 0, (cudaStream_t)stream>>>(p);
+    } else {
+        dim3 grid((unsigned)((p.HW + K3_PIX - 1) / K3_PIX), (unsigned)B);
+        k3_depth_regress_kernel<K3_DL><<<grid, K3_THREADS, 0, (cudaStream_t)stream>>>(p);
+    }
     return check_launch("k3_depth_regress_kernel");
 }
 
