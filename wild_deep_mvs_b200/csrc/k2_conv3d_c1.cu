@@ -15,11 +15,15 @@
 namespace mvsb200 {
 
 constexpr int C1_TX = 32, C1_THREADS = 8 * C1_TX, C1_EX = C1_TX + 2;
+#ifndef C1_NBUF
+#define C1_NBUF 3      // staged plane buffers per CTA (prefetch distance C1_NBUF - 1 planes)
+#endif
 // ROWS = vertically adjacent output columns per thread (rows ROWS*ly .. ROWS*ly + ROWS-1 of an 8*ROWS x 32 tile): 2 for
 // Cin = 8; wider inputs keep 1 (two columns of 16+ channels do not fit the register file at 3 CTAs / SM)
 template <int CIN> struct C1Tile {
     static constexpr int ROWS = CIN == 8 ? 2 : 1;
     static constexpr int TY = 8 * ROWS, EY = TY + 2, NPOS = EY * C1_EX;
+    static constexpr int NBUF = CIN <= 16 ? C1_NBUF : 2;     // wide inputs keep two buffers (shared memory: CTAs per SM)
 };
 
 template <int CIN> struct C1Params {
@@ -28,7 +32,7 @@ template <int CIN> struct C1Params {
     int B, D, H, W, zseg, nseg, tiles_x, tiles_y;
     float scale, bias;
     int relu;
-    float w[27 * CIN];   // [tap][ci]
+    alignas(16) float w[27 * CIN];   // [tap][ci]: the four weights of a channel quad are one 16-byte uniform load
 };
 
 __device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, bool valid)
@@ -44,7 +48,7 @@ template <int CIN>
 __global__ void __launch_bounds__(C1_THREADS, 3) k2_conv3d_c1_kernel(const __grid_constant__ C1Params<CIN> p)
 {
     constexpr int C4 = CIN / 4, ROWS = C1Tile<CIN>::ROWS, C1_TY = C1Tile<CIN>::TY, C1_NPOS = C1Tile<CIN>::NPOS;
-    extern __shared__ __align__(16) float4 c1_smem[];   // [2][C4][NPOS]
+    extern __shared__ __align__(16) float4 c1_smem[];   // [C1_NBUF][C4][NPOS]
     int t = blockIdx.x;
     const int tx = t % p.tiles_x; t /= p.tiles_x;
     const int ty = t % p.tiles_y; t /= p.tiles_y;
@@ -79,15 +83,22 @@ __global__ void __launch_bounds__(C1_THREADS, 3) k2_conv3d_c1_kernel(const __gri
         cp_async_commit();
     };
 
-    // acc[j][k]: output column j of this thread, output plane z-1+k, while input plane z is consumed
-    float acc[ROWS][3];
+    // acc[j][k]: output column j of this thread, output plane z-1+k, while input plane z is consumed -- as TWO partial sums
+    // (.x: channels 0, 1 of every quad, .y: channels 2, 3 ... see below), added when the plane is complete
+    float2 acc[ROWS][3];
 #pragma unroll
-    for (int j = 0; j < ROWS; j++) acc[j][0] = acc[j][1] = acc[j][2] = 0.f;
-    stage(zb - 1, 0);
+    for (int j = 0; j < ROWS; j++) acc[j][0] = acc[j][1] = acc[j][2] = make_float2(0.f, 0.f);
+    // C1_NBUF plane buffers: the copies of planes z+1 ... z+NBUF-1 are in flight while plane z is consumed (with two
+    // buffers the loop waited a full L2 / HBM round trip per plane: halving its FMA instructions did not move its time)
+    constexpr int NBUF = C1Tile<CIN>::NBUF;
+#pragma unroll
+    for (int i = 0; i < NBUF - 1; i++) {
+        if (zb - 1 + i <= ze) stage(zb - 1 + i, i); else cp_async_commit();
+    }
     for (int z = zb - 1, it = 0; z <= ze; z++, it++) {
-        const int buf = it & 1;
-        if (z < ze) stage(z + 1, buf ^ 1); else cp_async_commit();
-        cp_async_wait<1>();
+        const int buf = it % NBUF;
+        if (z + NBUF - 1 <= ze) stage(z + NBUF - 1, (it + NBUF - 1) % NBUF); else cp_async_commit();
+        cp_async_wait<NBUF - 1>();
         __syncthreads();
         if ((unsigned)z < (unsigned)p.D) {
             const float4 *sp = c1_smem + buf * C4 * C1_NPOS + (ROWS * ly) * C1_EX + lx;
@@ -104,11 +115,12 @@ __global__ void __launch_bounds__(C1_THREADS, 3) k2_conv3d_c1_kernel(const __gri
                             if (dy < 0 || dy > 2) continue;
 #pragma unroll
                             for (int k = 0; k < 3; k++) {   // kz = 2 - k feeds output plane z-1+k
+                                // packed fp32 FMAs (FFMA2): channel pairs (x, y) and (z, w) of the staged vector against the
+                                // matching weight pairs, which arrive as ONE uniform 16-byte load per (tap, quad) and feed
+                                // both columns of the thread: half the FMA instructions of the scalar form
                                 const int w = (((2 - k) * 3 + dy) * 3 + dx) * CIN + c4 * 4;
-                                acc[j][k] = fmaf(v.x, p.w[w], acc[j][k]);
-                                acc[j][k] = fmaf(v.y, p.w[w + 1], acc[j][k]);
-                                acc[j][k] = fmaf(v.z, p.w[w + 2], acc[j][k]);
-                                acc[j][k] = fmaf(v.w, p.w[w + 3], acc[j][k]);
+                                acc[j][k] = __ffma2_rn(make_float2(v.x, v.y), make_float2(p.w[w], p.w[w + 1]), acc[j][k]);
+                                acc[j][k] = __ffma2_rn(make_float2(v.z, v.w), make_float2(p.w[w + 2], p.w[w + 3]), acc[j][k]);
                             }
                         }
                     }
@@ -120,14 +132,14 @@ __global__ void __launch_bounds__(C1_THREADS, 3) k2_conv3d_c1_kernel(const __gri
                 float *dst = p.y + (((long long)b * p.D + zo) * p.H + oy) * p.W + ox;
 #pragma unroll
                 for (int j = 0; j < ROWS; j++) {
-                    float r = fmaf(acc[j][0], p.scale, p.bias);
+                    float r = fmaf(acc[j][0].x + acc[j][0].y, p.scale, p.bias);
                     if (p.relu) r = fmaxf(r, 0.f);
                     if (oy + j < p.H) dst[(long long)j * p.W] = r;
                 }
             }
         }
 #pragma unroll
-        for (int j = 0; j < ROWS; j++) { acc[j][0] = acc[j][1]; acc[j][1] = acc[j][2]; acc[j][2] = 0.f; }
+        for (int j = 0; j < ROWS; j++) { acc[j][0] = acc[j][1]; acc[j][1] = acc[j][2]; acc[j][2] = make_float2(0.f, 0.f); }
         __syncthreads();   // the buffer just read is refilled by the next iteration's prefetch
     }
 }
@@ -143,7 +155,7 @@ static int launch_c1(const mvsb200_conv3d_desc *d, const float *x, const float *
     p.tiles_x = (d->W + C1_TX - 1) / C1_TX;
     p.tiles_y = (d->H + C1Tile<CIN>::TY - 1) / C1Tile<CIN>::TY;
     // depth segments: trade the z-halo (2 extra planes per segment) against the balance of the last wave of CTAs
-    const size_t smem = (size_t)2 * (CIN / 4) * C1Tile<CIN>::NPOS * sizeof(float4);
+    const size_t smem = (size_t)C1Tile<CIN>::NBUF * (CIN / 4) * C1Tile<CIN>::NPOS * sizeof(float4);
     const long long base = (long long)p.tiles_x * p.tiles_y * d->B;
     int resident = (int)((220 * 1024) / smem);
     if (resident > 3) resident = 3;   // __launch_bounds__(C1_THREADS, 3)
