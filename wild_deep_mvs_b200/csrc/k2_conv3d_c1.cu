@@ -16,14 +16,14 @@ namespace mvsb200 {
 
 constexpr int C1_TX = 32, C1_THREADS = 8 * C1_TX, C1_EX = C1_TX + 2;
 #ifndef C1_NBUF
-#define C1_NBUF 3      // staged plane buffers per CTA (prefetch distance C1_NBUF - 1 planes)
+#define C1_NBUF 3      // staged plane buffers per CTA (>= 3: the plane being refilled is never the one being read)
 #endif
 // ROWS = vertically adjacent output columns per thread (rows ROWS*ly .. ROWS*ly + ROWS-1 of an 8*ROWS x 32 tile): 2 for
 // Cin = 8; wider inputs keep 1 (two columns of 16+ channels do not fit the register file at 3 CTAs / SM)
 template <int CIN> struct C1Tile {
     static constexpr int ROWS = CIN == 8 ? 2 : 1;
     static constexpr int TY = 8 * ROWS, EY = TY + 2, NPOS = EY * C1_EX;
-    static constexpr int NBUF = CIN <= 16 ? C1_NBUF : 2;     // wide inputs keep two buffers (shared memory: CTAs per SM)
+    static constexpr int NBUF = C1_NBUF;
 };
 
 template <int CIN> struct C1Params {
@@ -91,15 +91,17 @@ __global__ void __launch_bounds__(C1_THREADS, 3) k2_conv3d_c1_kernel(const __gri
     // C1_NBUF plane buffers: the copies of planes z+1 ... z+NBUF-1 are in flight while plane z is consumed (with two
     // buffers the loop waited a full L2 / HBM round trip per plane: halving its FMA instructions did not move its time)
     constexpr int NBUF = C1Tile<CIN>::NBUF;
+    static_assert(NBUF >= 3, "the single barrier per plane needs the refilled buffer to differ from the one being read");
 #pragma unroll
     for (int i = 0; i < NBUF - 1; i++) {
         if (zb - 1 + i <= ze) stage(zb - 1 + i, i); else cp_async_commit();
     }
     for (int z = zb - 1, it = 0; z <= ze; z++, it++) {
         const int buf = it % NBUF;
+        cp_async_wait<NBUF - 2>();      // plane z has landed (this thread's pieces) ...
+        __syncthreads();                // ... for every thread; and every thread is done reading plane z-1,
+        // whose buffer is the one refilled now: ONE barrier per plane (needs NBUF >= 3)
         if (z + NBUF - 1 <= ze) stage(z + NBUF - 1, (it + NBUF - 1) % NBUF); else cp_async_commit();
-        cp_async_wait<NBUF - 1>();
-        __syncthreads();
         if ((unsigned)z < (unsigned)p.D) {
             const float4 *sp = c1_smem + buf * C4 * C1_NPOS + (ROWS * ly) * C1_EX + lx;
 #pragma unroll
@@ -140,7 +142,6 @@ __global__ void __launch_bounds__(C1_THREADS, 3) k2_conv3d_c1_kernel(const __gri
         }
 #pragma unroll
         for (int j = 0; j < ROWS; j++) { acc[j][0] = acc[j][1]; acc[j][1] = acc[j][2]; acc[j][2] = make_float2(0.f, 0.f); }
-        __syncthreads();   // the buffer just read is refilled by the next iteration's prefetch
     }
 }
 
