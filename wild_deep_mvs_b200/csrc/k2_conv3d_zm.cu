@@ -95,6 +95,7 @@ struct ZmParams {
     int unit_bytes;          // bytes of one converted unit buffer = max(g1, g2) * NPX stage buffers
     int x_cstride, x_coff;   // x may be a channel slice of a wider tensor: voxel pitch and first channel (floats)
     int profile;
+    int wide;                // Cout = 8 with y (and skip) 32-byte aligned: the epilogue moves a voxel's 8 channels per 256-bit access
     int pdl;                 // launched as a programmatic dependent launch: x / x2 / skip / amax reads follow griddepcontrol.wait
 };
 
@@ -313,6 +314,20 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm)
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
 
+// 256-bit global accesses (sm_100): 8 channels of a voxel in ONE instruction -- the L1 data pipe counts wavefronts =
+// instructions x lines touched, and the epilogue's stores / skip loads touch a line per one or two threads (the strided
+// outputs of a transposed layer's parity class: one per thread), so two 128-bit accesses cost twice the wavefronts of one
+__device__ __forceinline__ void stg256(float *p, const float4 &a, const float4 &b)
+{
+    asm volatile("st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+                 :: "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "l"(p) : "memory");
+}
+__device__ __forceinline__ void ldg256(const float *p, float4 &a, float4 &b)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+
 #define ZM_T0() (prof ? clock64() : 0ll)
 #define ZM_ACC(var, t0) do { if (prof) var += clock64() - (t0); } while (0)
 
@@ -427,11 +442,18 @@ k2_conv3d_zm_kernel(const ZmParams p, const __grid_constant__ CUtensorMap tm_x, 
             const long long o_yx = (((long long)t.b * p.Do * p.Ho + oy) * p.Wo + ox) * p.Cout + co0;
             const int oz0 = (MODE == ZM_DECONV) ? 2 * t.zb : t.zb;
             auto load_skip = [&](int q, float4 (&sk)[C4]) {
+                const bool want = q < t.nq && ok_yx && oz0 + q < p.Do && p.skip_mode != MVSB200_SKIP_NONE;
 #pragma unroll
-                for (int c4 = 0; c4 < C4; c4++) {
-                    sk[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (q < t.nq && ok_yx && oz0 + q < p.Do && p.skip_mode != MVSB200_SKIP_NONE && c4 * 4 < ncol)
-                        sk[c4] = ldg4(p.skip + o_yx + (oz0 + q) * plane_stride + c4 * 4);
+                for (int c4 = 0; c4 < C4; c4 += 2) {
+                    sk[c4] = sk[c4 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!want) continue;
+                    const float *src = p.skip + o_yx + (oz0 + q) * plane_stride + c4 * 4;
+                    if (CT == 8 && p.wide) {
+                        ldg256(src, sk[c4], sk[c4 + 1]);
+                    } else {
+                        if (c4 * 4 < ncol) sk[c4] = ldg4(src);
+                        if (c4 * 4 + 4 < ncol) sk[c4 + 1] = ldg4(src + 4);
+                    }
                 }
             };
             constexpr bool AHEAD = (CT == 8);   // CT = 16: a second skip buffer would spill; its two teams overlap instead
@@ -506,6 +528,7 @@ k2_conv3d_zm_kernel(const ZmParams p, const __grid_constant__ CUtensorMap tm_x, 
                 if (team == 0) named_bar_sync(1, TEAM_WARPS * 32); else named_bar_sync(2, TEAM_WARPS * 32);
                 ZM_ACC(pe_bar, tq);
                 if (ok) {
+                    float4 first = make_float4(0.f, 0.f, 0.f, 0.f);   // CT == 8: channels 0..3, held for the 256-bit store
 #pragma unroll
                     for (int c4 = 0; c4 < C4; c4++) {
                         if (c4 * 4 >= ncol) break;
@@ -522,7 +545,12 @@ k2_conv3d_zm_kernel(const ZmParams p, const __grid_constant__ CUtensorMap tm_x, 
                         if (p.relu) { r[0] = fmaxf(r[0], 0.f); r[1] = fmaxf(r[1], 0.f); r[2] = fmaxf(r[2], 0.f); r[3] = fmaxf(r[3], 0.f); }
                         if (p.skip_mode == MVSB200_SKIP_AFTER_RELU) { r[0] += sk[c4].x; r[1] += sk[c4].y; r[2] += sk[c4].z; r[3] += sk[c4].w; }
                         vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(r[0]), fabsf(r[1]))), fmaxf(fabsf(r[2]), fabsf(r[3])));
-                        st4(p.y + o + c4 * 4, make_float4(r[0], r[1], r[2], r[3]));
+                        const float4 cur = make_float4(r[0], r[1], r[2], r[3]);
+                        if (CT == 8 && p.wide) {          // (Cout = 8: ncol = 8) one 256-bit store per voxel
+                            if (c4 == 0) first = cur; else stg256(p.y + o, first, cur);
+                        } else {
+                            st4(p.y + o + c4 * 4, cur);
+                        }
                     }
                 }
                 // One team: no second barrier -- the next plane writes the OTHER exchange buffer, and the barrier of that
@@ -1228,6 +1256,7 @@ extern "C" int mvsb200_conv3d_zm_slice(const mvsb200_conv3d_desc *d, const float
     p.g1 = p.g2 = p.nraw = p.raw_bytes = p.unit_bytes = 0;
     p.x_cstride = x_channels; p.x_coff = x_first_channel;
     p.profile = g_zm_prof_on;
+    p.wide = (d->Cout == 8 && (reinterpret_cast<uintptr_t>(y) & 31) == 0 && (!skip || (reinterpret_cast<uintptr_t>(skip) & 31) == 0)) ? 1 : 0;
     p.pdl = d->static_params ? 1 : 0;
     int sm_count = 0, dev = 0;
     cudaGetDevice(&dev);
