@@ -95,7 +95,7 @@ struct ZmParams {
     int unit_bytes;          // bytes of one converted unit buffer = max(g1, g2) * NPX stage buffers
     int x_cstride, x_coff;   // x may be a channel slice of a wider tensor: voxel pitch and first channel (floats)
     int profile;
-    int wide;                // Cout = 8 with y (and skip) 32-byte aligned: the epilogue moves a voxel's 8 channels per 256-bit access
+    int wide;                // Cout % 8 == 0 with y (and skip) 32-byte aligned: the epilogue moves 8 channels per 256-bit access
     int pdl;                 // launched as a programmatic dependent launch: x / x2 / skip / amax reads follow griddepcontrol.wait
 };
 
@@ -448,7 +448,7 @@ k2_conv3d_zm_kernel(const ZmParams p, const __grid_constant__ CUtensorMap tm_x, 
                     sk[c4] = sk[c4 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (!want) continue;
                     const float *src = p.skip + o_yx + (oz0 + q) * plane_stride + c4 * 4;
-                    if (CT == 8 && p.wide) {
+                    if (p.wide) {
                         ldg256(src, sk[c4], sk[c4 + 1]);
                     } else {
                         if (c4 * 4 < ncol) sk[c4] = ldg4(src);
@@ -528,7 +528,7 @@ k2_conv3d_zm_kernel(const ZmParams p, const __grid_constant__ CUtensorMap tm_x, 
                 if (team == 0) named_bar_sync(1, TEAM_WARPS * 32); else named_bar_sync(2, TEAM_WARPS * 32);
                 ZM_ACC(pe_bar, tq);
                 if (ok) {
-                    float4 first = make_float4(0.f, 0.f, 0.f, 0.f);   // CT == 8: channels 0..3, held for the 256-bit store
+                    float4 first = make_float4(0.f, 0.f, 0.f, 0.f);   // the even channel quad, held for the 256-bit store
 #pragma unroll
                     for (int c4 = 0; c4 < C4; c4++) {
                         if (c4 * 4 >= ncol) break;
@@ -546,8 +546,8 @@ k2_conv3d_zm_kernel(const ZmParams p, const __grid_constant__ CUtensorMap tm_x, 
                         if (p.skip_mode == MVSB200_SKIP_AFTER_RELU) { r[0] += sk[c4].x; r[1] += sk[c4].y; r[2] += sk[c4].z; r[3] += sk[c4].w; }
                         vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(r[0]), fabsf(r[1]))), fmaxf(fabsf(r[2]), fabsf(r[3])));
                         const float4 cur = make_float4(r[0], r[1], r[2], r[3]);
-                        if (CT == 8 && p.wide) {          // (Cout = 8: ncol = 8) one 256-bit store per voxel
-                            if (c4 == 0) first = cur; else stg256(p.y + o, first, cur);
+                        if (p.wide) {                     // (ncol is 8 or 16) one 256-bit store per 8 channels
+                            if ((c4 & 1) == 0) first = cur; else stg256(p.y + o + (c4 - 1) * 4, first, cur);
                         } else {
                             st4(p.y + o + c4 * 4, cur);
                         }
@@ -1256,7 +1256,7 @@ extern "C" int mvsb200_conv3d_zm_slice(const mvsb200_conv3d_desc *d, const float
     p.g1 = p.g2 = p.nraw = p.raw_bytes = p.unit_bytes = 0;
     p.x_cstride = x_channels; p.x_coff = x_first_channel;
     p.profile = g_zm_prof_on;
-    p.wide = (d->Cout == 8 && (reinterpret_cast<uintptr_t>(y) & 31) == 0 && (!skip || (reinterpret_cast<uintptr_t>(skip) & 31) == 0)) ? 1 : 0;
+    p.wide = (d->Cout % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 31) == 0 && (!skip || (reinterpret_cast<uintptr_t>(skip) & 31) == 0)) ? 1 : 0;
     p.pdl = d->static_params ? 1 : 0;
     int sm_count = 0, dev = 0;
     cudaGetDevice(&dev);
