@@ -328,6 +328,9 @@ __device__ __forceinline__ void ldg256(const float *p, float4 &a, float4 &b)
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 }
 
+#ifndef ZM_WIDE_OK
+#define ZM_WIDE_OK true
+#endif
 #define ZM_T0() (prof ? clock64() : 0ll)
 #define ZM_ACC(var, t0) do { if (prof) var += clock64() - (t0); } while (0)
 
@@ -448,7 +451,7 @@ k2_conv3d_zm_kernel(const ZmParams p, const __grid_constant__ CUtensorMap tm_x, 
                     sk[c4] = sk[c4 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (!want) continue;
                     const float *src = p.skip + o_yx + (oz0 + q) * plane_stride + c4 * 4;
-                    if (p.wide) {
+                    if (p.wide && ZM_WIDE_OK) {
                         ldg256(src, sk[c4], sk[c4 + 1]);
                     } else {
                         if (c4 * 4 < ncol) sk[c4] = ldg4(src);
@@ -546,7 +549,7 @@ k2_conv3d_zm_kernel(const ZmParams p, const __grid_constant__ CUtensorMap tm_x, 
                         if (p.skip_mode == MVSB200_SKIP_AFTER_RELU) { r[0] += sk[c4].x; r[1] += sk[c4].y; r[2] += sk[c4].z; r[3] += sk[c4].w; }
                         vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(r[0]), fabsf(r[1]))), fmaxf(fabsf(r[2]), fabsf(r[3])));
                         const float4 cur = make_float4(r[0], r[1], r[2], r[3]);
-                        if (p.wide) {                     // (ncol is 8 or 16) one 256-bit store per 8 channels
+                        if (p.wide && ZM_WIDE_OK) {       // (ncol is 8 or 16) one 256-bit store per 8 channels
                             if ((c4 & 1) == 0) first = cur; else stg256(p.y + o + (c4 - 1) * 4, first, cur);
                         } else {
                             st4(p.y + o + c4 * 4, cur);
