@@ -141,3 +141,54 @@ def test_cfg4_full_size_against_reference(ref):
     assert max(errs) < DEPTH_TOL, errs
     bad = (got["photometric_confidence"] - want["conf"]).abs() > 1e-3
     assert bad.float().mean() < 2e-2, bad.float().mean()
+
+
+def test_gathered_masks_full_size_against_reference_functions(ref):
+    """K9 at full resolution (1 + 4 views of 1600 x 1184 depth maps): the consumer of the gathered maps against the
+    reference's own functions executed on the same GPU -- `flows_from_single_depthmap` and `normalize` are imported from the
+    UNMODIFIED utils/utils_3D.py (oracle/_ref), the glue around them restates models/trainer.py:209-219,256-274 line for line
+    (the trainer module itself is not part of the hot-path archive).  Masks may differ only where the pixel sits on a boundary
+    (grid at +-1, relative difference at the threshold)."""
+    import torch.nn.functional as F
+    from utils.utils_3D import flows_from_single_depthmap, normalize          # the reference's (import_reference put it on sys.path)
+    from wild_deep_mvs_b200.filtering import gathered_masks
+    from wild_deep_mvs_b200.mvsnet import build_proj_matrices
+    N, h, w, i_ref, clamp = 5, 1184, 1600, 2, 0.05
+    K, R, t, dmin, dmax = synth.make_cameras(1, N, h, w)
+    proj = build_proj_matrices(K, R, t).to(DEV)
+    g = torch.Generator().manual_seed(3)
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    gathered = torch.stack([620 + 0.05 * xs - 0.04 * ys + 25 * torch.sin(xs / 90 + v) + 8 * torch.rand(h, w, generator=g)
+                            for v in range(N)])[None].to(DEV)
+    gathered[0, 1, 300:420, 500:900] *= 1.15          # a region where one source disagrees
+    depth_est = gathered[:, i_ref].clone()
+    imgs = torch.rand(1, N, 3, h, w, generator=g).to(DEV)
+    src_idx = [v for v in range(N) if v != i_ref]
+    with torch.no_grad():
+        # models/trainer.py:209-219 (get_flow_from_depthmap)
+        px_flow, depth_src = flows_from_single_depthmap(depth_est, proj, i_ref)
+        flows = normalize(px_flow, h, w)
+        flows[depth_src <= 0] = -10
+        flows = torch.clamp(flows, -10, 10)
+        # models/trainer.py:258-274
+        inside = (flows < 1).all(dim=-1) & (flows > -1).all(dim=-1)
+        want = torch.zeros_like(inside)
+        diffs = torch.zeros_like(depth_src)
+        for i, s in enumerate(src_idx):
+            wd = F.grid_sample(gathered[:, s].unsqueeze(1), flows[:, i], align_corners=False).squeeze(1)
+            diffs[:, i] = torch.abs(depth_src[:, i] - wd) / torch.clamp(wd, 1e-8)
+            want[:, i] = inside[:, i] & (diffs[:, i] < clamp)
+        out = gathered_masks(depth_est, gathered, proj, i_ref, clamp, imgs=imgs, want=("flows", "depth_src", "warped"))
+        warped_ref = torch.stack([F.grid_sample(imgs[:, s], flows[:, i], align_corners=False) for i, s in enumerate(src_idx)], 1)
+    assert float((out["flows"] - flows).abs().max()) < 5e-5
+    assert rel(out["depth_src"], depth_src) < 1e-5
+    bad = out["masks"] != want
+    edge = (flows.abs() - 1).abs().amin(dim=-1)
+    margin = torch.minimum(edge, (diffs - clamp).abs() / clamp)
+    off = bad & ~(margin < 2e-4)
+    print("K9 full size: %d of %d mask pixels differ, %d of them off a boundary; kept %.3f" % (int(bad.sum()), bad.numel(), int(off.sum()),
+                                                                                                 float(want.float().mean())))
+    assert not off.any() and bad.float().mean() < 1e-3
+    assert 0.2 < float(want.float().mean()) < 0.98
+    close = (out["warped"] - warped_ref).abs() <= 1e-4
+    assert close.float().mean() > 0.999          # (bilinear samples of random images: last-bit grid differences move a few)
