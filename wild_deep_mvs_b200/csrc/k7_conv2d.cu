@@ -26,7 +26,11 @@ template <int CIN, int COUT, int K, int S> struct C2Cfg {
     static constexpr int TH = C2_THREADS * C2_PX / (C2_TW * CG);   // tile rows
     static constexpr int IH = (TH - 1) * S + K, IW = (C2_TW - 1) * S + K, NPOS = IH * IW;
     static constexpr int C4 = CIN / 4;
-    static constexpr size_t SMEM = (size_t)C4 * NPOS * 16 + (size_t)K * K * CIN * COUT * 4;
+    // 5x5 layers stage their weights one filter ROW at a time (51 KB of weights next to an 81 KB input tile left one CTA
+    // per SM for the 16 -> 32 layer); 3x3 layers keep the whole filter resident
+    static constexpr bool ROW_WEIGHTS = (K == 5);
+    static constexpr int W_FLOATS = (ROW_WEIGHTS ? K : K * K) * CIN * COUT;
+    static constexpr size_t SMEM = (size_t)C4 * NPOS * 16 + (size_t)W_FLOATS * 4;
     static_assert(CIN % 4 == 0 && COUT % C2_CT == 0 && TH >= 1, "unsupported channel counts");
 };
 
@@ -45,8 +49,9 @@ __global__ void __launch_bounds__(C2_THREADS) k7_conv2d_kernel(const C2Params p)
     const int ox0 = tx * C2_TW, oy0 = ty * T::TH;
     const int ix0 = ox0 * S - PAD, iy0 = oy0 * S - PAD;
 
-    for (int i = threadIdx.x; i < K * K * CIN * COUT / 4; i += C2_THREADS)
-        reinterpret_cast<float4 *>(s_w)[i] = __ldg(reinterpret_cast<const float4 *>(p.w) + i);
+    if (!T::ROW_WEIGHTS)
+        for (int i = threadIdx.x; i < T::W_FLOATS / 4; i += C2_THREADS)
+            reinterpret_cast<float4 *>(s_w)[i] = __ldg(reinterpret_cast<const float4 *>(p.w) + i);
     const float *img = p.x + (long long)b * p.H * p.W * CIN;
     for (int i = threadIdx.x; i < NPOS * C4; i += C2_THREADS) {
         const int c4 = i % C4, pos = i / C4;   // consecutive threads: consecutive 16-byte pieces of a pixel
@@ -72,9 +77,15 @@ __global__ void __launch_bounds__(C2_THREADS) k7_conv2d_kernel(const C2Params p)
 
 #pragma unroll 1
     for (int ky = 0; ky < K; ky++) {
+        if (T::ROW_WEIGHTS) {
+            if (ky > 0) __syncthreads();      // the previous row's weights have been consumed
+            for (int i = threadIdx.x; i < T::W_FLOATS / 4; i += C2_THREADS)
+                reinterpret_cast<float4 *>(s_w)[i] = __ldg(reinterpret_cast<const float4 *>(p.w) + (size_t)ky * (T::W_FLOATS / 4) + i);
+            __syncthreads();
+        }
 #pragma unroll
         for (int kx = 0; kx < K; kx++) {
-            const float *wt = s_w + ((ky * K + kx) * CIN) * COUT + g * C2_CT;
+            const float *wt = s_w + (((T::ROW_WEIGHTS ? 0 : ky * K) + kx) * CIN) * COUT + g * C2_CT;
             const int base = (ly * S + ky) * IW + qx * S + kx;
 #pragma unroll
             for (int c4 = 0; c4 < C4; c4++) {
