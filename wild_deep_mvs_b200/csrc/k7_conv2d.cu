@@ -26,9 +26,10 @@ template <int CIN, int COUT, int K, int S> struct C2Cfg {
     static constexpr int TH = C2_THREADS * C2_PX / (C2_TW * CG);   // tile rows
     static constexpr int IH = (TH - 1) * S + K, IW = (C2_TW - 1) * S + K, NPOS = IH * IW;
     static constexpr int C4 = CIN / 4;
-    // 5x5 layers stage their weights one filter ROW at a time (51 KB of weights next to an 81 KB input tile left one CTA
-    // per SM for the 16 -> 32 layer); 3x3 layers keep the whole filter resident
-    static constexpr bool ROW_WEIGHTS = (K == 5);
+    // Layers whose whole filter + input tile exceed 64 KB of shared memory stage their weights one filter ROW at a time
+    // (the 5x5 layers: 51 KB of weights next to an 81 KB input tile left ONE CTA per SM for 16 -> 32; 32 -> 32 3x3: 80 KB,
+    // two per SM for a grid of 2.7 CTAs per SM); the others keep the whole filter resident
+    static constexpr bool ROW_WEIGHTS = ((size_t)C4 * NPOS * 16 + (size_t)K * K * CIN * COUT * 4 > 64 * 1024);
     static constexpr int W_FLOATS = (ROW_WEIGHTS ? K : K * K) * CIN * COUT;
     static constexpr size_t SMEM = (size_t)C4 * NPOS * 16 + (size_t)W_FLOATS * 4;
     static_assert(CIN % 4 == 0 && COUT % C2_CT == 0 && TH >= 1, "unsupported channel counts");
