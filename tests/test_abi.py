@@ -19,6 +19,13 @@ def test_header_declares_the_expected_entry_points():
         assert n in names
 
 
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md shows, for every symbol of the C ABI, what it replaces in the reference (or that it is a support call)."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in _declared() if n not in doc]
+    assert not missing, missing
+
+
 def test_library_builds_and_exports_every_declared_symbol():
     from wild_deep_mvs_b200 import build, _lib
     so = build.build()
