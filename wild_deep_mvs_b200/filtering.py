@@ -10,9 +10,10 @@ import ctypes
 import torch
 
 from . import _lib as L
-from .ops import _dev_f32, _ptr, _stream
+from .ops import _dev_f32, _on_operand_device, _ptr, _stream
 
 
+@_on_operand_device
 def geometric_filter(depth, src_depths, K, R, t, depth_threshold=0.01, max_reproj_error=1.0, min_tri_angle=1.0,
                      num_consistent=3, want_votes=False):
     """depth [h,w]; src_depths: list of N maps [hi,wi] (sizes may differ); K, R [1+N,3,3]; t [1+N,3,1] or [1+N,3];
@@ -43,6 +44,7 @@ def geometric_filter(depth, src_depths, K, R, t, depth_threshold=0.01, max_repro
     return out
 
 
+@_on_operand_device
 def gathered_masks(ref_depth, gathered, proj_mat, ref_idx, geom_clamping=0.05, imgs=None, want=()):
     """The consumer of the all-gathered depth maps (K9, mvsb200_gathered_masks): the geometric half of the reference's
     `masked_photometricloss` (models/trainer.py:240-278) -- `get_flow_from_depthmap` (:209-219) + the re-projection mask.
