@@ -103,3 +103,66 @@ def test_depth_gather_single_process():
     assert g.world == 1 and g.local.shape == (2, 3, 5) and g.local.data_ptr() == g.all.data_ptr()
     g.local.fill_(7.0)
     assert g.all_gather() is g.all and float(g.all.sum()) == 7.0 * 30
+
+
+def _consumer_scene(N=2, h=12, w=16):
+    """N pinhole views of a slanted plane: per-view depth maps (what each rank would compute) and 4x4 projections."""
+    import numpy as np
+    proj = np.zeros((1, N, 4, 4), np.float32)
+    maps = np.zeros((N, h, w), np.float32)
+    ys, xs = np.meshgrid(np.arange(h, dtype=np.float64), np.arange(w, dtype=np.float64), indexing="ij")
+    n, c = np.array([0.1, -0.05, 1.0]), 500.0
+    for v in range(N):
+        K = np.array([[120.0, 0, w / 2.0], [0, 118.0, h / 2.0], [0, 0, 1]])
+        a = 0.03 * v
+        R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+        t = np.array([[-15.0 * v], [1.0 * v], [0.0]])
+        P = np.eye(4)
+        P[:3, :3], P[:3, 3:] = K @ R, K @ t
+        proj[0, v] = P
+        rays = np.stack([xs, ys, np.ones_like(xs)], -1) @ np.linalg.inv(K).T @ R
+        o = -R.T @ t.reshape(3)
+        maps[v] = (c - n @ o) / (rays @ n)
+    maps[1, 3:6, 4:9] *= 1.3       # view 1's estimate is wrong in a block: the re-projection test must fail there
+    return proj, maps
+
+
+def _consumer_worker(rank, world, port, q):
+    """models/trainer.py:101,246-274 of the reference on two ranks: rank r's reference view is view r, the ONE all-gather
+    brings every rank's depth map, and each rank masks ITS map against the gathered ones (the K9 operator; here its CPU
+    oracle, the collective is what is under test)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.filter import gathered_masks
+        proj, maps = _consumer_scene(world)
+        g = shard.DepthGather(1, maps.shape[1:], "cpu")
+        g.local[0].copy_(torch.from_numpy(maps[rank]))                 # "K3 writes its map into the send slice"
+        gathered = g.all_gather().numpy()                              # [world, h, w] on every rank
+        out = gathered_masks(maps[rank][None], gathered[None], proj, rank, 0.05)
+        q.put((rank, gathered.tolist(), out["masks"].tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gathered_maps_feed_the_consumer_on_every_rank_world2_gloo():
+    import numpy as np
+    from oracle.filter import gathered_masks
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_consumer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = {r: (np.asarray(gm, np.float32), np.asarray(m)) for r, gm, m in (q.get(timeout=120) for _ in range(world))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    proj, maps = _consumer_scene(world)
+    for rank in range(world):
+        gathered, masks = results[rank]
+        assert np.array_equal(gathered, maps)                          # every rank holds every view's map, in view order
+        want = gathered_masks(maps[rank][None], maps[None], proj, rank, 0.05)["masks"]
+        assert np.array_equal(masks, want)
+    # the corrupted block of view 1 is rejected from both sides, the rest of the overlap is kept
+    assert not results[1][1][0, 0, 3:6, 4:9].any() and results[0][1].mean() > 0.3
