@@ -18,10 +18,16 @@ constexpr int C1_TX = 32, C1_THREADS = 8 * C1_TX, C1_EX = C1_TX + 2;
 #ifndef C1_NBUF
 #define C1_NBUF 3      // staged plane buffers per CTA (>= 3: the plane being refilled is never the one being read)
 #endif
+#ifndef C1_ROWS8
+#define C1_ROWS8 2     // output columns per thread for Cin = 8 (experiment switch: 4 = 9 instead of 12 shared loads per output, 2 CTAs / SM)
+#endif
+#ifndef C1_MIN_BLOCKS
+#define C1_MIN_BLOCKS 3
+#endif
 // ROWS = vertically adjacent output columns per thread (rows ROWS*ly .. ROWS*ly + ROWS-1 of an 8*ROWS x 32 tile): 2 for
 // Cin = 8; wider inputs keep 1 (two columns of 16+ channels do not fit the register file at 3 CTAs / SM)
 template <int CIN> struct C1Tile {
-    static constexpr int ROWS = CIN == 8 ? 2 : 1;
+    static constexpr int ROWS = CIN == 8 ? C1_ROWS8 : 1;
     static constexpr int TY = 8 * ROWS, EY = TY + 2, NPOS = EY * C1_EX;
     static constexpr int NBUF = C1_NBUF;
 };
@@ -45,7 +51,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int CIN>
-__global__ void __launch_bounds__(C1_THREADS, 3) k2_conv3d_c1_kernel(const __grid_constant__ C1Params<CIN> p)
+__global__ void __launch_bounds__(C1_THREADS, C1_MIN_BLOCKS) k2_conv3d_c1_kernel(const __grid_constant__ C1Params<CIN> p)
 {
     constexpr int C4 = CIN / 4, ROWS = C1Tile<CIN>::ROWS, C1_TY = C1Tile<CIN>::TY, C1_NPOS = C1Tile<CIN>::NPOS;
     extern __shared__ __align__(16) float4 c1_smem[];   // [C1_NBUF][C4][NPOS]
@@ -159,7 +165,7 @@ static int launch_c1(const mvsb200_conv3d_desc *d, const float *x, const float *
     const size_t smem = (size_t)C1Tile<CIN>::NBUF * (CIN / 4) * C1Tile<CIN>::NPOS * sizeof(float4);
     const long long base = (long long)p.tiles_x * p.tiles_y * d->B;
     int resident = (int)((220 * 1024) / smem);
-    if (resident > 3) resident = 3;   // __launch_bounds__(C1_THREADS, 3)
+    if (resident > C1_MIN_BLOCKS) resident = C1_MIN_BLOCKS;   // __launch_bounds__(C1_THREADS, C1_MIN_BLOCKS)
     const long long slots = 148ll * resident;
     double best = -1.0;
     p.zseg = d->D;
