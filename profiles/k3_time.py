@@ -26,3 +26,15 @@ for name, B, D, H, W in (("vis s3 pairs", 32, 16, 256, 320), ("vis s2 pairs", 32
         print("%-14s %.4f ms" % (name, timed(fn)), flush=True)
     except Exception as e:
         print(name, "FAILED", repr(e)[:200])
+# the bench's call (MVSNet: scalar hypotheses per batch, 4-bin confidence, preallocated outputs), L2 flushed and L2 hot
+score = torch.randn(1, 192, 128, 160, device=dev)
+values = torch.linspace(425.0, 935.0, 192, device=dev).view(1, 192)
+od, oc = torch.empty(1, 128, 160, device=dev), torch.empty(1, 128, 160, device=dev)
+fn = lambda: ops.depth_regress(score, values, conf_mode=L.CONF_SUM4, out_depth=od, out_conf=oc)
+print("%-14s %.4f ms" % ("cfg2 bench", timed(fn)), flush=True)
+fn(); torch.cuda.synchronize()
+ts = []
+for _ in range(20):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+print("%-14s %.4f ms" % ("cfg2 bench hot", sorted(ts)[10]), flush=True)

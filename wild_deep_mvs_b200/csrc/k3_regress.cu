@@ -3,7 +3,7 @@
 // K3 reads the score volume [B,D,H,W] with a block of 32 pixels x 8 depth lanes: consecutive lanes of a warp sit on
 // consecutive pixels (every load of a depth slice is one coalesced 128-byte line) and the 8 warps of a block split the
 // depth axis (d = warp, warp + 8, ...), combining their partial max / normaliser / expectations through shared
-// memory.  The three sweeps re-read a 32 x D x 4-byte column set that stays in L1.  (One thread per pixel, the first
+// memory.  The three sweeps run out of registers (a lane's share of the column is loaded once, see NV below).  (One thread per pixel, the first
 // version, left 20 k threads walking D serially: 60 us of pure latency for 16 MB.)
 #include "common.cuh"
 
@@ -22,8 +22,20 @@ struct K3Params {
 // memory), 1 for the shallow ones of the cascades (Vis-MVSNet stages D = 16 ... 64, CVP refinement levels D = 8): with a
 // handful of hypotheses per lane the partial-sum exchange and its three barriers cost more than the sweep -- a thread then
 // owns its pixel, a block 256 pixels.
-template <int DL>
-__global__ void __launch_bounds__(K3_THREADS) k3_depth_regress_kernel(const K3Params p)
+//
+// NV > 0: the lane's share of the column (at most NV scores: d = dl, dl + DL, ...) is loaded ONCE into registers -- all
+// loads of the sweep in flight together -- and the three sweeps run out of registers; NV = 0 streams the column three
+// times (columns deeper than NV * DL).  Same operations in the same order either way: the results are bit-identical.
+// Measured (profiles/k3_nv_round2k.log): NV = 24 with five resident blocks per SM (48 registers) beats the streaming kernel by
+// ~10 % on every shape; NV = 32 at 63 registers (four blocks: the 640 blocks of cfg2 then need a second wave) is slower than it.
+#ifndef K3_NV
+#define K3_NV 24
+#endif
+#ifndef K3_MIN_BLOCKS
+#define K3_MIN_BLOCKS 5
+#endif
+template <int DL, int NV>
+__global__ void __launch_bounds__(K3_THREADS, K3_MIN_BLOCKS) k3_depth_regress_kernel(const K3Params p)
 {
     constexpr int K3_DL = DL, K3_PIX = K3_THREADS / DL;
     __shared__ float red[4][K3_DL][K3_PIX];
@@ -34,14 +46,38 @@ __global__ void __launch_bounds__(K3_THREADS) k3_depth_regress_kernel(const K3Pa
     const float *s = p.score + (long long)b * p.D * p.HW + pix;
     const int D = p.D;
 
+    // sweep(f): f(i, d, score) for the lane's hypotheses d = dl + i * DL, in order
+    float v[NV > 0 ? NV : 1];
+    if (NV > 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            const int d = dl + i * K3_DL;
+            if (d >= D) break;
+            v[i] = __ldg(s + d * p.HW);
+        }
+    }
+#define K3_SWEEP(BODY)                                                                        \
+    if (NV > 0) {                                                                             \
+        _Pragma("unroll") for (int i = 0; i < NV; i++) {                                      \
+            const int d = dl + i * K3_DL;                                                     \
+            if (d >= D) break;                                                                \
+            const float sc = v[i];                                                            \
+            BODY                                                                              \
+        }                                                                                     \
+    } else {                                                                                  \
+        for (int d = dl; d < D; d += K3_DL) {                                                 \
+            const float sc = __ldg(s + d * p.HW);                                             \
+            BODY                                                                              \
+        }                                                                                     \
+    }
     float mx = -INFINITY;
-    for (int d = dl; d < D; d += K3_DL) mx = fmaxf(mx, __ldg(s + d * p.HW));
+    K3_SWEEP(mx = fmaxf(mx, sc);)
     red[0][dl][lane] = mx;
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < K3_DL; k++) mx = fmaxf(mx, red[0][k][lane]);
     float sum = 0.f;
-    for (int d = dl; d < D; d += K3_DL) sum += expf(__ldg(s + d * p.HW) - mx);
+    K3_SWEEP(sum += expf(sc - mx);)
     red[1][dl][lane] = sum;
     __syncthreads();
     sum = 0.f;
@@ -51,14 +87,15 @@ __global__ void __launch_bounds__(K3_THREADS) k3_depth_regress_kernel(const K3Pa
     const float interval = (p.depth_mode >= MVSB200_DEPTH_START) ? __ldg(p.interval + b) : 0.f;
     float e_idx = 0.f, e_dep = 0.f, ent = 0.f;
     float *prob = (p.prob_out && active) ? p.prob_out + (long long)b * D * p.HW + pix : nullptr;
-    for (int d = dl; d < D; d += K3_DL) {
-        const float pr = expf(__ldg(s + d * p.HW) - mx) / sum;
+    K3_SWEEP(
+        const float pr = expf(sc - mx) / sum;
         if (prob) prob[d * p.HW] = pr;
         e_idx += pr * (float)d;
         if (p.depth_mode == MVSB200_DEPTH_VALUES) e_dep += pr * __ldg(p.depth + (long long)b * D + d);
         else if (p.depth_mode == MVSB200_DEPTH_VOLUME) e_dep += pr * __ldg(p.depth + ((long long)b * D + d) * p.HW + pix);
         if (p.entropy_out) ent += -pr * logf(fminf(fmaxf(pr, 1e-9f), 1.f));
-    }
+    )
+#undef K3_SWEEP
     __syncthreads();   // red[0] / red[1] are reused below
     red[0][dl][lane] = e_idx;
     red[2][dl][lane] = e_dep;
@@ -193,10 +230,12 @@ extern "C" int mvsb200_depth_regress(const float *score, int B, int D, int H, in
     // one thread per pixel needs enough pixels to fill the machine while each thread walks D serially
     if (D <= 32 || (D <= 64 && (long long)B * p.HW >= (1ll << 18))) {
         dim3 grid((unsigned)((p.HW + K3_THREADS - 1) / K3_THREADS), (unsigned)B);
-        k3_depth_regress_kernel<1><<<grid, K3_THREADS, 0, (cudaStream_t)stream>>>(p);
+        if (D <= K3_NV) k3_depth_regress_kernel<1, K3_NV><<<grid, K3_THREADS, 0, (cudaStream_t)stream>>>(p);
+        else k3_depth_regress_kernel<1, 0><<<grid, K3_THREADS, 0, (cudaStream_t)stream>>>(p);
     } else {
         dim3 grid((unsigned)((p.HW + K3_PIX - 1) / K3_PIX), (unsigned)B);
-        k3_depth_regress_kernel<K3_DL><<<grid, K3_THREADS, 0, (cudaStream_t)stream>>>(p);
+        if (D <= K3_NV * K3_DL) k3_depth_regress_kernel<K3_DL, K3_NV><<<grid, K3_THREADS, 0, (cudaStream_t)stream>>>(p);
+        else k3_depth_regress_kernel<K3_DL, 0><<<grid, K3_THREADS, 0, (cudaStream_t)stream>>>(p);
     }
     return check_launch("k3_depth_regress_kernel");
 }
