@@ -85,7 +85,10 @@ def child(so):
              ("cvp-l4", lambda: mvs_case(16, 74, 100, 96, L.AGG_VARIANCE_MEAN, False)),      # cfg4 coarsest level: scalar hypotheses
              ("cvp-l0", lambda: mvs_case(16, 1184, 1600, 8, L.AGG_VARIANCE_MEAN, True)),
              ("cfg1", lambda: mvs_case(32, 128, 160, 48, L.AGG_SOFTMIN, False, views=3))]
+    only = os.environ.get("K1AB_CASES")     # comma-separated case names (default: all)
     for name, mk in cases:
+        if only and name not in only.split(","):
+            continue
         try:
             med, mn = timed(mk())
             print("%-40s %-9s %.4f ms (min %.4f)" % (os.path.basename(so), name, med, mn), flush=True)

@@ -549,7 +549,8 @@ __global__ void __launch_bounds__(K1M_THREADS, K1M_MIN_BLOCKS) k1m_cost_volume_k
 }
 
 // Host: pixel tiles of (128 / C) x 4; the depth axis is cut into as few segments as still give the grid ~8 waves of blocks
-// (a segment starts with one forced window load per view, so longer is better).
+// (a segment starts with one forced window load per view, so longer is better).  Measured at cfg2 (profiles/k1m_nseg_round2k.log):
+// 3, 4 (the choice below) and 5 segments tie at 0.260 ms, 6 / 8 / 12 cost 0.264 / 0.271 / 0.285 ms.
 static bool k1m_supported(const mvsb200_cost_volume_desc *d)
 {
     return (d->C == 16 || d->C == 32) && (d->S == 1 || d->S == 2 || d->S == 4);
@@ -569,6 +570,7 @@ static int k1m_grid(const mvsb200_cost_volume_desc *d, dim3 &grid, int &seg, con
     MVSB200_REQUIRE(tiles < (1ll << 31), "%s: image too large", what);
     const int chunks = (d->D + K1M_HC - 1) / K1M_HC;
     long long nseg = (32ll * sms + tiles * d->B - 1) / (tiles * d->B);
+    if (const char *e = getenv("MVSB200_K1M_NSEG")) { if (atoi(e) > 0) nseg = atoi(e); }   // experiment switch (profiles/k1_ab.py)
     if (nseg > chunks) nseg = chunks;
     if (nseg < 1) nseg = 1;
     seg = (int)((chunks + nseg - 1) / nseg) * K1M_HC;
