@@ -9,7 +9,6 @@ strict=True from the drop-in's state_dict into the reference's modules -- the ke
 Tolerance: the north-star bar, depth maps within 1e-3 relative L-inf of the reference PyTorch path -- at EVERY stage /
 pyramid level, on the whole map.
 """
-import numpy as np
 import pytest
 import torch
 
